@@ -1,0 +1,178 @@
+/*
+ * mope_b200 -- C ABI of the B200-native ontogenetic-phylogeny log-likelihood.
+ *
+ * This is the drop-in boundary for ONE hot path of ammodramus/mope: what emcee calls once per
+ * walker per step through mope's inference / likelihoods API.  Reference interfaces replaced
+ * (paths relative to the reference tree):
+ *
+ *   mope_b200_create            <- Inference.__init__                       mope/inference.py:263-738
+ *                                  (tables: TransitionData / TransitionDataBottleneck loaders,
+ *                                   mope/transition_data_2d.py:78-111, transition_data_bottleneck.py:74-96;
+ *                                   leaf emissions: _binom.get_binom_likelihoods_cython, mope/_binom.pyx:49-92)
+ *   mope_b200_eval              <- Inference.loglike                        mope/inference.py:770-910
+ *                                  = likelihoods.get_log_likelihood_somatic_newick  mope/likelihoods.py:308-403
+ *                                  + ascertainment.get_locus_asc_probs              mope/ascertainment.py:132-236
+ *                                  + Inference.poisson_log_like                     mope/inference.py:1113-1129
+ *                                  (matrix fetch: TransitionData.get_transition_probabilities_2d,
+ *                                   mope/transition_data_2d.py:133-238 incl. _util.check_transition_matrix
+ *                                   mope/_util.pyx:129-148 and _interp.bilinear_interpolate mope/_interp.pyx:7-37;
+ *                                   branch updates: mope/_likes.pyx:42-56,139-152,232-248; root: :312-322,426-442)
+ *   mope_b200_transition_matrix <- TransitionData.get_transition_probabilities_2d / bottleneck twin
+ *   mope_b200_leaf_likelihoods  <- _binom.get_binom_likelihoods_cython      mope/_binom.pyx:49-92
+ *   mope_b200_branch_update     <- _likes.compute_{length,rate,bottleneck}_transition_likelihood
+ *   mope_b200_non_asc_probs     <- _poisson_binom.get_non_asc_probs         mope/_poisson_binom.pyx:18-90
+ *
+ * Conventions: plain C, no exceptions across the boundary.  Every function returns 0 on success or a
+ * negative MOPE_E_* code; mope_b200_last_error() gives the message of the last failure on the calling
+ * thread.  All arithmetic is fp64.  Device memory is OWNED BY THE CALLER (PyTorch in the Python host):
+ * the caller asks for sizes with the *_bytes queries, allocates, and passes device pointers in.
+ * Functions taking a `stream` enqueue their work on that CUDA stream (cudaStream_t passed as void*);
+ * unless documented otherwise they return after the work is enqueued.  A context is bound to one device
+ * and is not re-entrant (external locking), matching the reference's process-private Inference object.
+ */
+#ifndef MOPE_B200_H
+#define MOPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOPE_OK 0
+#define MOPE_E_INVALID (-1)   /* bad argument / malformed description */
+#define MOPE_E_CUDA (-2)      /* CUDA runtime error (message has the CUDA string) */
+#define MOPE_E_NOMEM (-3)     /* arena / workspace too small */
+#define MOPE_E_NODEVICE (-4)  /* no usable sm_100 device */
+
+/* per-walker status bits written by mope_b200_eval (the reference raises ValueError for each) */
+#define MOPE_ST_OK 0
+#define MOPE_ST_TIME_TOO_LARGE 1    /* transition_data_2d.py:165-167 */
+#define MOPE_ST_MUT_TOO_SMALL 2     /* transition_data_2d.py:168-170, transition_data_bottleneck.py:124-126 */
+#define MOPE_ST_MUT_TOO_LARGE 4     /* transition_data_2d.py:171-173, transition_data_bottleneck.py:127-129 */
+#define MOPE_ST_NB_TOO_SMALL 8      /* transition_data_bottleneck.py:118-120 */
+#define MOPE_ST_NB_TOO_LARGE 16     /* transition_data_bottleneck.py:121-123 */
+#define MOPE_ST_NOT_FINITE 32       /* transition_data_2d.py:135-136,158-161 */
+#define MOPE_ST_NO_BOTTLENECK_TABLE 64 /* likelihoods.py:381-382 */
+
+typedef struct mope_ctx mope_ctx;
+
+/* Transition tables, host pointers, row-major, complete sorted grids (the in-RAM state of
+ * TransitionData(memory=True)).  drift[g][u] is the F x F matrix for gens[g], us[u]; P[i][j] =
+ * Pr(child bin j | parent bin i).  bot may be NULL (no --bottlenecks file). */
+typedef struct {
+    int32_t F;
+    int32_t n_gens, n_us;
+    const double* drift;   /* [n_gens][n_us][F][F] */
+    const double* gens;    /* [n_gens] ascending (generations, as float64 like _sorted_gens) */
+    const double* us;      /* [n_us] ascending (per-generation mutation probability) */
+    int32_t n_nbs, n_bot_us;
+    const double* bot;     /* [n_nbs][n_bot_us][F][F] or NULL */
+    const double* nbs;     /* [n_nbs] ascending bottleneck sizes */
+    const double* bot_us;  /* [n_bot_us] ascending */
+    double N;              /* Wright-Fisher population size of the tables */
+    const double* freqs;   /* [F] bin frequencies */
+} mope_tables_desc;
+
+/* One pedigree type (data file + tree + ages file) after the reference's init-time processing
+ * (fixed loci dropped, families counted).  Nodes are numbered in the reference's postorder
+ * (newick.Node.walk('postorder')); node b < n_branches is also branch b; the root is node n_branches. */
+typedef struct {
+    int32_t n_leaves, n_branches, n_loci, n_fam, n_mult, n_asc;
+    const double* counts;        /* [n_loci][n_leaves] focal-allele counts, NaN = missing tissue */
+    const double* coverage;      /* [n_loci][n_leaves] */
+    const double* row_mult;      /* [n_mult][n_loci] multiplier (age) value of every locus row */
+    const double* asc_mult;      /* [n_mult][n_asc] multiplier values of every distinct ascertainment row pair */
+    const int32_t* fam_asc;      /* [n_fam] index of the family's ascertainment row pair (0..n_asc-1) */
+    const double* fam_count;     /* [n_fam] number of loci of the family (asc_ages['count']) */
+    const double* fam_lgamma;    /* [n_fam] gammaln(count+1) */
+    const int32_t* br_parent;    /* [n_branches] parent node id */
+    const int32_t* br_leaf;      /* [n_branches] leaf column (0..n_leaves-1) or -1 for an internal node */
+    const int32_t* br_var;       /* [n_branches] index of the branch's parameter name (0..n_var-1) */
+    const int32_t* br_mult;      /* [n_branches] multiplier column (0..n_mult-1) or -1 */
+    const int32_t* br_bottleneck;/* [n_branches] 1 for a `^` branch */
+} mope_pedigree_desc;
+
+typedef struct {
+    int32_t n_var;                   /* distinct branch parameter names; ndim = 2*n_var + 2 */
+    int32_t n_ped;
+    const mope_pedigree_desc* peds;  /* [n_ped] */
+    double min_phred_score;          /* -1 = none (mope/_binom.pyx:76-79) */
+    double min_freq;                 /* ascertainment threshold (--min-het-freq) */
+    double genome_size;
+    double poisson_like_penalty;
+} mope_model_desc;
+
+/* Bytes of device memory the context needs for tables, emissions and model arrays. */
+int mope_b200_arena_bytes(const mope_tables_desc* tables, const mope_model_desc* model, size_t* out_bytes);
+
+/* Build a context on `device`.  Uploads the tables, runs the leaf-emission kernel, compiles the branch
+ * schedule.  `arena` is caller-owned device memory of at least mope_b200_arena_bytes(); it must outlive
+ * the context.  Synchronous. */
+int mope_b200_create(const mope_tables_desc* tables, const mope_model_desc* model, int device,
+                     void* arena, size_t arena_bytes, void* stream, mope_ctx** out);
+
+int mope_b200_destroy(mope_ctx* ctx);
+
+/* Workspace (caller-owned device scratch) needed to evaluate `n_walkers` in one pass.  Smaller
+ * workspaces are accepted by mope_b200_eval as long as they hold one walker; it then runs in chunks. */
+int mope_b200_workspace_bytes(const mope_ctx* ctx, int n_walkers, size_t* out_min_bytes, size_t* out_full_bytes);
+
+/* Evaluate Inference.loglike for a batch of walkers.
+ *   params  host [n_walkers][ndim]: log10 branch lengths (n_var), log10 scaled mutation rates (n_var),
+ *           log10 ab, log10 ppoly -- the vector `loglike` receives (log_posterior's sign folding and the
+ *           prior stay in the host wrapper, mope/inference.py:1132-1149).
+ *   stat    host [n_walkers][F] root distribution (likelihoods.get_stationary_distribution_double_beta,
+ *           mope/likelihoods.py:57-60; computed by the host wrapper with the reference's own SciPy call).
+ *   out_ll  host [n_walkers].  Walkers whose parameters leave the tables get NaN and a non-zero status.
+ *   out_status   host [n_walkers] MOPE_ST_* bits, may be NULL.
+ *   out_root_ll  host [n_walkers][n_ped] tree log-likelihood before ascertainment, may be NULL.
+ *   out_log_asc  host [n_walkers][sum_ped n_asc] per distinct ascertainment row pair, may be NULL.
+ * Host<->device copies of params/stat/outputs happen inside; the call returns after the results are in
+ * the host arrays (it synchronises `stream`). */
+int mope_b200_eval(mope_ctx* ctx, const double* params, const double* stat, int n_walkers,
+                   void* workspace, size_t workspace_bytes, void* stream,
+                   double* out_ll, int32_t* out_status, double* out_root_ll, double* out_log_asc);
+
+/* Same computation with everything already resident on the device (device pointers; params/stat/out as
+ * above).  Enqueues only; no host synchronisation.  Per-walker interpolation plans are still derived on
+ * the host from `params_host` (tiny), so the host copy of params is required too. */
+int mope_b200_eval_device(mope_ctx* ctx, const double* params_host, const double* stat_dev, int n_walkers,
+                          void* workspace, size_t workspace_bytes, void* stream,
+                          double* out_ll_dev, int32_t* out_status_host);
+
+/* Number of kernels this library launched since the context was created. */
+int64_t mope_b200_launch_count(const mope_ctx* ctx);
+
+/* Operator-level entry points (parity tests mirror the reference's operator contracts). */
+
+/* P = get_transition_probabilities_2d(x, scaled_mut): bottleneck=0 -> drift tables, x = scaled time,
+ * result clamped/renormalised; bottleneck=1 -> bottleneck tables, x = Nb, no check.  out_P host [F][F].
+ * Returns 0 and *out_status = MOPE_ST_* (out_P untouched when status != 0). */
+int mope_b200_transition_matrix(mope_ctx* ctx, int bottleneck, double x, double scaled_mut,
+                                void* stream, double* out_P, int32_t* out_status);
+
+/* likes[l][s][f] = Binom(counts[l][s]; coverage[l][s], p_f) exactly as _binom.get_binom_likelihoods_cython;
+ * host pointers; uses ctx for the device only. */
+int mope_b200_leaf_likelihoods(mope_ctx* ctx, const double* counts, const double* coverage, int n_loci,
+                               int n_leaves, const double* freqs, int F, double min_phred_score,
+                               void* stream, double* out_likes);
+
+/* parent[r][:] *= P_r @ child[r][:] for n_rows rows.  kind: 0 fixed length, 1 per-row lengths (rate),
+ * 2 bottleneck.  lengths: host [1] (kind 0/2) or [n_rows] (kind 1).  child/parent host [n_rows][F]. */
+int mope_b200_branch_update(mope_ctx* ctx, int kind, const double* child, double* parent, int n_rows,
+                            const double* lengths, double scaled_mut, void* stream, int32_t* out_status);
+
+/* Poisson-binomial non-ascertainment probabilities for n_sets read sets (ragged: qual_off[n_sets+1]
+ * offsets into qualities).  out host [n_sets][F]. */
+int mope_b200_non_asc_probs(mope_ctx* ctx, const double* qualities, const int64_t* qual_off, int n_sets,
+                            const double* freqs, int F, double min_empirical_freq, void* stream, double* out);
+
+const char* mope_b200_last_error(void);
+const char* mope_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOPE_B200_H */

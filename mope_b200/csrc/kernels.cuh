@@ -1,0 +1,643 @@
+// mope_b200 device code (sm_100a).  fp64 throughout.
+//
+// Kernels
+//   emission_kernel   leaf emission tensor E[leaf][row][f]           (mope/_binom.pyx:49-92)
+//   interp_kernel     per-(walker, key) transition matrices from the grid tables, with the
+//                     reference's clamp + row renormalisation          (transition_data_2d.py:133-238,
+//                                                                      _interp.pyx:7-37, _util.pyx:129-148)
+//   tree_kernel       fused Felsenstein pruning pass over a 64-row tile: every branch of the tree as a
+//                     DMMA (mma.sync m8n8k4 f64) GEMM tile, parent products, root reduction
+//                                                                     (likelihoods.py:308-403, _likes.pyx)
+//   finalize_kernel   per-walker deterministic reduction: sum of locus log-likelihoods, ascertainment
+//                     and Poisson terms                               (inference.py:872-894,1113-1129)
+//   pb_kernel         Poisson-binomial non-ascertainment probabilities (_poisson_binom.pyx:18-90)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace mope {
+
+constexpr int TM = 64;        // rows (loci) per tile
+constexpr int KC = 16;        // K chunk in doubles (128 B per row)
+constexpr int LDSM = KC + 4;  // smem row stride in doubles: 20 -> conflict-free 8 B fragment loads
+constexpr int NSTAGE = 4;     // cp.async pipeline depth
+constexpr int NTHREADS = 256; // 8 warps: 4 along M (16 rows each) x 2 along N
+
+struct TreeOp {
+    int32_t src_kind;  // 0 leaf emissions, 1 scratch slot
+    int32_t src;       // leaf column or slot id
+    int32_t dst;       // parent scratch slot (-1 when the parent is the root and this is its only/last use)
+    int32_t first;     // 1: parent = Y, 0: parent *= Y
+    int32_t kind;      // 0 shared matrix (fixed length or bottleneck), 1 per-row times (rate)
+    int32_t key;       // kind 0: matrix key index; kind 1: rate key index
+    int32_t mult;      // kind 1: multiplier column
+    int32_t last;      // 1: parent is the root and is complete after this op -> root reduction
+};
+
+struct RateInfo {
+    double len;      // branch length parameter (time per unit multiplier)
+    int64_t off;     // offset (doubles) of segment gbase's matrix block inside the walker pool
+    int32_t gbase;   // first generation-grid index materialised
+    int32_t gcount;  // number of consecutive grid matrices materialised
+};
+
+struct InterpJob {
+    int64_t src[4];  // offsets (doubles) into the table pool: q11 (t1,x1), q12 (t1,x2), q21 (t2,x1), q22 (t2,x2)
+    double w[4];     // w11, w12, w21, w22
+    int64_t dst;     // offset (doubles) into the matrix pool
+    int32_t flags;   // bit0: clamp + renormalise rows; bit1: identity; bit2: two-term blend (q11*w11 + q12*w12)
+    int32_t pad;
+};
+
+struct TreeParams {
+    const double* E;        // [n_leaves][R_pad][Fp]
+    int64_t E_leaf_stride;  // R_pad * Fp
+    double* scratch;        // [gridDim.x][n_slots][TM][Fp]
+    const TreeOp* ops;
+    int32_t n_ops, n_slots;
+    int32_t R, L, R_pad, Fp, F, NT, n_tiles, W;
+    const double* pool;      // per-launch matrix pool
+    const int64_t* mat_off;  // [W][n_mat] offsets (doubles) into pool
+    int32_t n_mat, n_rate;
+    const RateInfo* rate;    // [W][n_rate]
+    const double* mult;      // [n_mult][R_pad]
+    const double* gens;      // [n_gens]
+    int32_t n_gens;
+    double Npop;
+    const double* stat;      // [W][Fp]
+    double* tile_ll;         // [W][n_tiles]
+    double* asc_dot;         // [W][R - L]
+    double* Yout;            // operator-level mode (single op): Y rows go to Yout[w][row][Fp] instead of a slot
+};
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// leaf emissions (mope/_binom.pyx:20-23,49-92; GSL gsl_ran_binomial_pdf algorithm)
+// ------------------------------------------------------------------------------------------------
+// One warp per (leaf, row).  logp / log1mp / p-class per frequency come from the host (libm), so the
+// only device transcendental calls are lgamma (3 per row) and exp (1 per element).
+struct EmissionParams {
+    const double* counts;    // [L][S]
+    const double* coverage;  // [L][S]
+    const double* logp;      // [F]
+    const double* log1mp;    // [F]
+    const int8_t* pclass;    // [F] 0: 0<p<1, 1: p==0, 2: p==1
+    const int8_t* asc_e0;    // [F] 1 where freq < min_freq
+    const int8_t* asc_eN;    // [F] 1 where freq > 1-min_freq
+    double* E;               // [S][R_pad][Fp]
+    int32_t L, S, R, R_pad, F, Fp;
+};
+
+__device__ __forceinline__ double lnchoose_dev(unsigned n, unsigned m) {
+    if (m == n || m == 0) return 0.0;
+    if (m * 2u > n) m = n - m;
+    return __dsub_rn(__dsub_rn(lgamma((double)n + 1.0), lgamma((double)m + 1.0)), lgamma((double)(n - m) + 1.0));
+}
+
+__global__ void emission_kernel(EmissionParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total = (long long)p.S * p.R_pad;
+    if (warp >= total) return;
+    const int s = (int)(warp / p.R_pad);
+    const int r = (int)(warp % p.R_pad);
+    double* out = p.E + ((size_t)s * p.R_pad + r) * p.Fp;
+    if (r >= p.R) {  // padding rows
+        for (int f = lane; f < p.Fp; f += 32) out[f] = 0.0;
+        return;
+    }
+    if (r >= p.L) {  // ascertainment pseudo-rows: e0 (even) / eN (odd), ascertainment.py:178-184
+        const int8_t* e = ((r - p.L) & 1) ? p.asc_eN : p.asc_e0;
+        for (int f = lane; f < p.Fp; f += 32) out[f] = (f < p.F && e[f]) ? 1.0 : 0.0;
+        return;
+    }
+    const double x = p.counts[(size_t)r * p.S + s];
+    const double nn = p.coverage[(size_t)r * p.S + s];
+    if (isnan(x)) {  // missing tissue
+        for (int f = lane; f < p.Fp; f += 32) out[f] = (f < p.F) ? 1.0 : 0.0;
+        return;
+    }
+    const unsigned uk = (unsigned)x, un = (unsigned)nn;
+    if (uk > un) {
+        for (int f = lane; f < p.Fp; f += 32) out[f] = 0.0;
+        return;
+    }
+    const double lc = lnchoose_dev(un, uk);
+    const double dk = (double)uk, dnk = (double)(un - uk);
+    for (int f = lane; f < p.Fp; f += 32) {
+        double v = 0.0;
+        if (f < p.F) {
+            const int cls = p.pclass[f];
+            if (cls == 1) v = (uk == 0) ? 1.0 : 0.0;
+            else if (cls == 2) v = (uk == un) ? 1.0 : 0.0;
+            else {
+                // ln_Cnk + k*log(p) + (n-k)*log1p(-p), left to right, no fma contraction
+                double e = __dadd_rn(__dadd_rn(lc, __dmul_rn(dk, p.logp[f])), __dmul_rn(dnk, p.log1mp[f]));
+                v = exp(e);
+            }
+        }
+        out[f] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// interpolation of transition matrices (transition_data_2d.py:195-238, _interp.pyx:30-35,
+// _util.pyx:129-148).  One warp per matrix row; sequential row sum as in the reference.
+// Output block: Fp x Fp matrix (zero padded) followed by Fp row sums (of the un-normalised blend).
+// ------------------------------------------------------------------------------------------------
+__global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* tables, double* pool, int F, int Fp) {
+    extern __shared__ double srow[];  // [warps_per_block][Fp]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double* row = srow + (size_t)wib * Fp;
+    const int rows_per_job = Fp;
+    const long long gw = (long long)blockIdx.x * wpb + wib;
+    const long long total = (long long)n_jobs * rows_per_job;
+    if (gw >= total) return;
+    const int j = (int)(gw / rows_per_job);
+    const int i = (int)(gw % rows_per_job);
+    const InterpJob jb = jobs[j];
+    double* dst = pool + jb.dst + (size_t)i * Fp;
+    double* dsum = pool + jb.dst + (size_t)Fp * Fp;
+    if (i >= F) {  // zero padding rows
+        for (int f = lane; f < Fp; f += 32) dst[f] = 0.0;
+        if (lane == 0) dsum[i] = 0.0;
+        return;
+    }
+    if (jb.flags & 2) {  // identity short-cut (transition_data_2d.py:184-187)
+        for (int f = lane; f < Fp; f += 32) dst[f] = (f == i) ? 1.0 : 0.0;
+        if (lane == 0) dsum[i] = 1.0;
+        return;
+    }
+    const double* q11 = tables + jb.src[0] + (size_t)i * F;
+    const double* q12 = tables + jb.src[1] + (size_t)i * F;
+    const double* q21 = tables + jb.src[2] + (size_t)i * F;
+    const double* q22 = tables + jb.src[3] + (size_t)i * F;
+    const bool two = (jb.flags & 4) != 0;
+    const bool check = (jb.flags & 1) != 0;
+    for (int f = lane; f < F; f += 32) {
+        double v;
+        if (two) {
+            v = __dadd_rn(__dmul_rn(q11[f], jb.w[0]), __dmul_rn(q12[f], jb.w[1]));
+        } else {
+            // ((q11*w11 + q21*w21) + q12*w12) + q22*w22
+            v = __dadd_rn(__dmul_rn(q11[f], jb.w[0]), __dmul_rn(q21[f], jb.w[2]));
+            v = __dadd_rn(v, __dmul_rn(q12[f], jb.w[1]));
+            v = __dadd_rn(v, __dmul_rn(q22[f], jb.w[3]));
+        }
+        if (check) {
+            if (v > 1.0) v = 1.0;
+            else if (v < 0.0) v = 0.0;
+        }
+        row[f] = v;
+    }
+    __syncwarp();
+    double s = 0.0;
+    for (int f = 0; f < F; ++f) s = __dadd_rn(s, row[f]);  // same left-to-right order as the reference loop
+    const bool div = check && (s > 1.0);
+    for (int f = lane; f < Fp; f += 32) {
+        double v = (f < F) ? row[f] : 0.0;
+        if (div) v = __ddiv_rn(v, s);
+        dst[f] = v;
+    }
+    if (lane == 0) dsum[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused pruning pass
+// ------------------------------------------------------------------------------------------------
+struct TreeSmem {
+    double rowdot[2][TM];
+    double row_a[TM], row_d[TM];
+    int32_t row_g[TM];      // generation-grid index gi of the row (rate ops); -1 = identity / padding row
+    int32_t seg_lo, seg_hi; // tile segment range (absolute grid indices), seg_lo > seg_hi = nothing to do
+};
+
+template <int NTW>
+struct TileCfg {
+    static constexpr int PROWS = 2 * NTW * 8;                          // P rows staged per pass
+    static constexpr int STAGE_DOUBLES = (TM + PROWS) * LDSM;
+    static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_DOUBLES * sizeof(double) + sizeof(TreeSmem);
+};
+
+// issue the cp.async copies of one K chunk: V rows [0,TM) and P rows [0,prow_count)
+template <int NTW>
+__device__ __forceinline__ void load_chunk(double* stage, const double* __restrict__ Vsrc, const double* __restrict__ Psrc,
+                                           int Fp, int kc, int prow_count) {
+    const int koff = kc * KC;
+    const int total = (TM + prow_count) * (KC / 2);  // 16-byte pieces
+    for (int idx = threadIdx.x; idx < total; idx += NTHREADS) {
+        const int r = idx >> 3, piece = idx & 7;
+        const double* g = (r < TM) ? (Vsrc + (size_t)r * Fp + koff + piece * 2)
+                                   : (Psrc + (size_t)(r - TM) * Fp + koff + piece * 2);
+        cp_async16(stage + r * LDSM + piece * 2, g);
+    }
+}
+
+// acc += V[64 x K] * P[rows x K]^T for this warp's 16 rows x (ntw valid) n-tiles.  wt (may be null): per-row
+// scale of V in shared memory (rate segments).
+template <int NTW>
+__device__ __forceinline__ void gemm_pass(double (&acc)[2][NTW][2], double* stages, const double* __restrict__ Vsrc,
+                                          const double* __restrict__ Psrc, int Fp, int prow_count, int ntw_valid,
+                                          const double* wt, int seg_for_wt, const TreeSmem* ts) {
+    using Cfg = TileCfg<NTW>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int nchunks = Fp / KC;
+    // prologue
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+        if (s < nchunks) load_chunk<NTW>(stages + (size_t)s * Cfg::STAGE_DOUBLES, Vsrc, Psrc, Fp, s, prow_count);
+        cp_async_commit();
+    }
+    double w0 = 1.0, w1 = 1.0;
+    if (wt != nullptr) {
+        // per-row weight of this segment: a if seg == gi-1, d if seg == gi
+        const int r0 = wm * 16 + (lane >> 2), r1 = r0 + 8;
+        const int g0 = ts->row_g[r0], g1 = ts->row_g[r1];
+        w0 = (g0 >= 0) ? ((seg_for_wt == g0 - 1 ? ts->row_a[r0] : 0.0) + (seg_for_wt == g0 ? ts->row_d[r0] : 0.0)) : 0.0;
+        w1 = (g1 >= 0) ? ((seg_for_wt == g1 - 1 ? ts->row_a[r1] : 0.0) + (seg_for_wt == g1 ? ts->row_d[r1] : 0.0)) : 0.0;
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        cp_async_wait<NSTAGE - 2>();
+        __syncthreads();
+        {
+            const int nc = c + NSTAGE - 1;
+            if (nc < nchunks) load_chunk<NTW>(stages + (size_t)(nc % NSTAGE) * Cfg::STAGE_DOUBLES, Vsrc, Psrc, Fp, nc, prow_count);
+            cp_async_commit();
+        }
+        const double* st = stages + (size_t)(c % NSTAGE) * Cfg::STAGE_DOUBLES;
+        const double* As = st + (wm * 16 + (lane >> 2)) * LDSM + (lane & 3);
+        const double* Bs = st + (TM + wn * NTW * 8 + (lane >> 2)) * LDSM + (lane & 3);
+#pragma unroll
+        for (int q = 0; q < KC / 4; ++q) {
+            double a0 = As[q * 4];
+            double a1 = As[8 * LDSM + q * 4];
+            if (wt != nullptr) { a0 *= w0; a1 *= w1; }
+#pragma unroll
+            for (int j = 0; j < NTW; ++j) {
+                if (j < ntw_valid) {
+                    const double b = Bs[j * 8 * LDSM + q * 4];
+                    dmma(acc[0][j][0], acc[0][j][1], a0, b);
+                    dmma(acc[1][j][0], acc[1][j][1], a1, b);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // all warps done with the stages before the next pass refills them
+}
+
+template <int NTW>
+__global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant__ TreeParams p) {
+    using Cfg = TileCfg<NTW>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* stages = reinterpret_cast<double*>(smem_raw);
+    TreeSmem* ts = reinterpret_cast<TreeSmem*>(smem_raw + (size_t)NSTAGE * Cfg::STAGE_DOUBLES * sizeof(double));
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int Fp = p.Fp;
+    double* my_scratch = p.scratch + (size_t)blockIdx.x * p.n_slots * TM * Fp;
+    const int npass = (p.NT + 2 * NTW - 1) / (2 * NTW);
+    const long long n_items = (long long)p.W * p.n_tiles;
+
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int w = (int)(item / p.n_tiles);
+        const int tile = (int)(item % p.n_tiles);
+        const int row0 = tile * TM;
+
+        for (int oi = 0; oi < p.n_ops; ++oi) {
+            const TreeOp op = p.ops[oi];
+            const double* Vsrc = (op.src_kind == 0)
+                                     ? p.E + (size_t)op.src * p.E_leaf_stride + (size_t)row0 * Fp
+                                     : my_scratch + (size_t)op.src * TM * Fp;
+            double* dst = (op.dst >= 0) ? my_scratch + (size_t)op.dst * TM * Fp : nullptr;
+
+            const double* Pbase = nullptr;
+            const RateInfo* ri = nullptr;
+            if (op.kind == 0) {
+                Pbase = p.pool + p.mat_off[(size_t)w * p.n_mat + op.key];
+            } else {
+                ri = &p.rate[(size_t)w * p.n_rate + op.key];
+                // per-row generation index and time weights (transition_data_2d.py:183-224)
+                if (threadIdx.x == 0) { ts->seg_lo = 0x7fffffff; ts->seg_hi = -1; }
+                __syncthreads();
+                if (threadIdx.x < TM) {
+                    const int r = row0 + threadIdx.x;
+                    int gi = -1;
+                    double a = 0.0, d = 0.0;
+                    if (r < p.R) {
+                        const double t = __dmul_rn(p.Npop, __dmul_rn(p.mult[(size_t)op.mult * p.R_pad + r], ri->len));
+                        if (!(t < p.gens[0])) {
+                            int lo = 0, hi = p.n_gens;  // searchsorted left
+                            while (lo < hi) { int mid = (lo + hi) >> 1; if (p.gens[mid] < t) lo = mid + 1; else hi = mid; }
+                            gi = lo < p.n_gens ? lo : p.n_gens - 1;
+                            const double t2 = p.gens[gi];
+                            const double t1 = p.gens[gi > 0 ? gi - 1 : p.n_gens - 1];
+                            const double den = __dsub_rn(t2, t1);
+                            a = __ddiv_rn(__dsub_rn(t2, t), den);
+                            d = __ddiv_rn(__dsub_rn(t, t1), den);
+                            if (gi == 0) a = 0.0;  // wrapped neighbour carries an exactly-zero weight
+                            atomicMin(&ts->seg_lo, gi > 0 ? gi - 1 : 0);
+                            atomicMax(&ts->seg_hi, gi);
+                        }
+                    }
+                    ts->row_g[threadIdx.x] = gi;
+                    ts->row_a[threadIdx.x] = a;
+                    ts->row_d[threadIdx.x] = d;
+                }
+                __syncthreads();
+            }
+            if (op.last) {
+                if (threadIdx.x < 2 * TM) (&ts->rowdot[0][0])[threadIdx.x] = 0.0;
+                // visibility to the epilogue is ordered by the __syncthreads inside gemm_pass
+            }
+
+            for (int pass = 0; pass < npass; ++pass) {
+                const int t0 = pass * 2 * NTW;                       // first n-tile of the pass
+                const int prow_count = min(Cfg::PROWS, Fp - t0 * 8);
+                int ntw_valid = p.NT - (t0 + wn * NTW);
+                ntw_valid = ntw_valid < 0 ? 0 : (ntw_valid > NTW ? NTW : ntw_valid);
+
+                double acc[2][NTW][2];
+#pragma unroll
+                for (int j = 0; j < NTW; ++j) { acc[0][j][0] = acc[0][j][1] = acc[1][j][0] = acc[1][j][1] = 0.0; }
+
+                if (op.kind == 0) {
+                    gemm_pass<NTW>(acc, stages, Vsrc, Pbase + (size_t)t0 * 8 * Fp, Fp, prow_count, ntw_valid, nullptr, 0, ts);
+                } else {
+                    const int slo = ts->seg_lo, shi = ts->seg_hi;
+                    const size_t blk = (size_t)Fp * Fp + Fp;
+                    for (int seg = slo; seg <= shi; ++seg) {
+                        const double* Pseg = p.pool + ri->off + (size_t)(seg - ri->gbase) * blk + (size_t)t0 * 8 * Fp;
+                        gemm_pass<NTW>(acc, stages, Vsrc, Pseg, Fp, prow_count, ntw_valid, ts->row_a, seg, ts);
+                    }
+                }
+
+                // ---------------- epilogue ----------------
+                const int rA = wm * 16 + (lane >> 2);  // tile-local rows of acc[0], acc[1] = rA, rA + 8
+                double dot0 = 0.0, dot1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NTW; ++j) {
+                    if (j < ntw_valid) {
+                        const int col = (t0 + wn * NTW + j) * 8 + 2 * (lane & 3);
+#pragma unroll
+                        for (int mi = 0; mi < 2; ++mi) {
+                            const int rl = rA + 8 * mi;
+                            double y0 = acc[mi][j][0], y1 = acc[mi][j][1];
+                            if (op.kind == 1) {
+                                const int gi = ts->row_g[rl];
+                                if (gi < 0) {  // identity short-cut (or padding row): Y = V
+                                    const double2 v = *reinterpret_cast<const double2*>(Vsrc + (size_t)rl * Fp + col);
+                                    y0 = v.x; y1 = v.y;
+                                } else {
+                                    // row renormalisation of the blended matrix (_util.pyx:138-147)
+                                    const size_t blk = (size_t)Fp * Fp + Fp;
+                                    const double* s2 = p.pool + ri->off + (size_t)(gi - ri->gbase) * blk + (size_t)Fp * Fp;
+                                    const double a = ts->row_a[rl], d = ts->row_d[rl];
+                                    double den0 = d * s2[col], den1 = d * s2[col + 1];
+                                    if (gi > 0 && a != 0.0) {
+                                        const double* s1 = s2 - blk;
+                                        den0 += a * s1[col]; den1 += a * s1[col + 1];
+                                    }
+                                    if (den0 > 1.0) y0 /= den0;
+                                    if (den1 > 1.0) y1 /= den1;
+                                }
+                            }
+                            if (p.Yout != nullptr) {
+                                *reinterpret_cast<double2*>(p.Yout + ((size_t)w * p.R_pad + row0 + rl) * Fp + col) = make_double2(y0, y1);
+                                continue;
+                            }
+                            if (!op.first) {
+                                const double2 pv = *reinterpret_cast<const double2*>(dst + (size_t)rl * Fp + col);
+                                y0 *= pv.x; y1 *= pv.y;
+                            }
+                            if (op.last) {
+                                const double2 sv = *reinterpret_cast<const double2*>(p.stat + (size_t)w * Fp + col);
+                                if (mi == 0) dot0 += y0 * sv.x + y1 * sv.y;
+                                else dot1 += y0 * sv.x + y1 * sv.y;
+                            } else {
+                                *reinterpret_cast<double2*>(dst + (size_t)rl * Fp + col) = make_double2(y0, y1);
+                            }
+                        }
+                    }
+                }
+                if (op.last) {
+                    dot0 += __shfl_xor_sync(0xffffffffu, dot0, 1);
+                    dot0 += __shfl_xor_sync(0xffffffffu, dot0, 2);
+                    dot1 += __shfl_xor_sync(0xffffffffu, dot1, 1);
+                    dot1 += __shfl_xor_sync(0xffffffffu, dot1, 2);
+                    if ((lane & 3) == 0) {  // one writer per (N-warp, row); passes are sequential
+                        ts->rowdot[wn][rA] += dot0;
+                        ts->rowdot[wn][rA + 8] += dot1;
+                    }
+                }
+            }  // pass
+            // zero the K-padding columns [8*NT, Fp) of the parent tile once (first write), so that it is a
+            // valid V operand later
+            if (p.Yout == nullptr && !op.last && op.first && 8 * p.NT < Fp) {
+                const int padw = Fp - 8 * p.NT;
+                for (int idx = threadIdx.x; idx < TM * padw; idx += NTHREADS)
+                    dst[(size_t)(idx / padw) * Fp + 8 * p.NT + (idx % padw)] = 0.0;
+            }
+            __syncthreads();  // parent tile visible to the whole CTA before it is read as an operand
+
+            if (op.last && p.Yout == nullptr) {
+                // root reduction (_likes.pyx:312-322, 426-442): real rows -> sum of logs in fixed order;
+                // ascertainment rows -> raw dot products
+                if (warp == 0) {
+                    double part = 0.0;
+                    for (int h = 0; h < 2; ++h) {
+                        const int rl = lane + 32 * h;
+                        const int r = row0 + rl;
+                        const double dt = ts->rowdot[0][rl] + ts->rowdot[1][rl];
+                        if (r < p.L) part += log(dt);
+                        else if (r < p.R) p.asc_dot[(size_t)w * (p.R - p.L) + (r - p.L)] = dt;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    if (lane == 0) p.tile_ll[(size_t)w * p.n_tiles + tile] = part;
+                }
+                __syncthreads();
+            }
+        }  // ops
+    }      // items
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: one CTA per walker (inference.py:872-894, 1113-1129; _likes.pyx:426-442)
+// ------------------------------------------------------------------------------------------------
+struct FinalizeParams {
+    const double* tile_ll;   // [W][n_tiles]
+    const double* asc_dot;   // [W][2*n_asc]
+    const int32_t* fam_asc;  // [n_fam]
+    const double* fam_count; // [n_fam]
+    const double* fam_lgamma;// [n_fam]
+    const int32_t* widx;     // [W] global walker index of each walker of the chunk (outputs are indexed by it)
+    double* out_ll;          // [*] accumulated (+=) across pedigrees
+    double* out_root_ll;     // [W][ped_stride] or null
+    double* out_log_asc;     // [W][asc_stride] or null
+    int32_t n_tiles, n_asc, n_fam, W;
+    int32_t ped_index, ped_stride, asc_offset, asc_stride, accumulate;
+    double log_genome, penalty;
+};
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+    // fixed-order tree: deterministic run to run
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p) {
+    __shared__ double sh[256];
+    const int w = blockIdx.x;
+    const int wg = p.widx[w];
+    double a = 0.0;
+    for (int t = threadIdx.x; t < p.n_tiles; t += 256) a += p.tile_ll[(size_t)w * p.n_tiles + t];
+    const double root_ll = block_sum_256(a, sh);
+
+    double asc_sum = 0.0, pois = 0.0;
+    const double* ad = p.asc_dot + (size_t)w * 2 * p.n_asc;
+    for (int f = threadIdx.x; f < p.n_fam; f += 256) {
+        const int u = p.fam_asc[f];
+        double pp = 1.0;
+        pp -= ad[2 * u];
+        pp -= ad[2 * u + 1];
+        const double la = log(pp);
+        const double c = p.fam_count[f];
+        asc_sum += la * c;
+        const double loglam = la + p.log_genome;
+        pois += (-exp(loglam) + c * loglam) - p.fam_lgamma[f];
+    }
+    asc_sum = block_sum_256(asc_sum, sh);
+    pois = block_sum_256(pois, sh);
+    if (p.out_log_asc != nullptr) {
+        for (int u = threadIdx.x; u < p.n_asc; u += 256) {
+            double pp = 1.0;
+            pp -= ad[2 * u];
+            pp -= ad[2 * u + 1];
+            p.out_log_asc[(size_t)wg * p.asc_stride + p.asc_offset + u] = log(pp);
+        }
+    }
+    if (threadIdx.x == 0) {
+        double ll = root_ll - asc_sum;
+        if (p.penalty > 0.0) ll += pois * p.penalty;
+        if (p.accumulate) p.out_ll[wg] += ll;
+        else p.out_ll[wg] = ll;
+        if (p.out_root_ll != nullptr) p.out_root_ll[(size_t)wg * p.ped_stride + p.ped_index] = root_ll;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Poisson-binomial non-ascertainment probabilities (_poisson_binom.pyx:18-90), DP truncated to the K
+// columns that are read back.  One CTA per read set, one thread per frequency; qualities are staged
+// through shared memory in coalesced chunks.
+// ------------------------------------------------------------------------------------------------
+constexpr int PB_MAXK = 32;
+__global__ void pb_kernel(const double* __restrict__ qual, const int64_t* __restrict__ off, const double* __restrict__ freqs,
+                          int F, double min_freq, double* __restrict__ out, int* __restrict__ overflow) {
+    __shared__ double sq[256];
+    const int set = blockIdx.x;
+    const int64_t q0 = off[set], q1 = off[set + 1];
+    const int nq = (int)(q1 - q0);
+    const int K = (int)ceil(min_freq * (double)nq);
+    if (K > PB_MAXK) { if (threadIdx.x == 0) atomicExch(overflow, K); return; }
+    for (int fbase = 0; fbase < F; fbase += blockDim.x) {
+        const int fi = fbase + threadIdx.x;
+        const double f = fi < F ? freqs[fi] : 0.0;
+        double P[PB_MAXK + 1];
+#pragma unroll
+        for (int k = 0; k <= PB_MAXK; ++k) P[k] = 0.0;
+        for (int base = 0; base < nq; base += 256) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < 256; t += blockDim.x)
+                sq[t] = (base + t < nq) ? pow(10.0, -qual[q0 + base + t] / 10.0) : 0.0;
+            __syncthreads();
+            const int lim = min(256, nq - base);
+            for (int jj = 0; jj < lim; ++jj) {
+                const double e = sq[jj];
+                const double ap = f * (1.0 - e) + (1 - f) * e;
+                if (base + jj == 0) {
+                    P[0] = 1 - ap;
+                    P[1] = ap;
+                } else {
+#pragma unroll
+                    for (int k = PB_MAXK; k >= 1; --k) P[k] = ap * P[k - 1] + (1 - ap) * P[k];
+                    P[0] = (1 - ap) * P[0];
+                }
+            }
+        }
+        if (fi < F) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < PB_MAXK; ++k) if (k < K) acc += P[k];
+            out[(size_t)set * F + fi] = (nq > 0) ? acc : 0.0;
+        }
+    }
+}
+
+// simple helpers
+__global__ void pad_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, int n_rows, int F, int Fp, int rows_pad) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)rows_pad * Fp;
+    if (idx >= total) return;
+    const int r = (int)(idx / Fp), f = (int)(idx % Fp);
+    dst[idx] = (r < n_rows && f < F) ? src[(size_t)r * F + f] : 0.0;
+}
+__global__ void unpad_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, int n_rows, int F, int Fp) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n_rows * F;
+    if (idx >= total) return;
+    const int r = (int)(idx / F), f = (int)(idx % F);
+    dst[idx] = src[(size_t)r * Fp + f];
+}
+
+// stat[widx[i]][0..F) -> dst[i][0..Fp) zero padded
+__global__ void gather_pad_kernel(const double* __restrict__ src, const int32_t* __restrict__ widx, double* __restrict__ dst,
+                                  int n, int F, int Fp) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * Fp) return;
+    const int i = (int)(idx / Fp), f = (int)(idx % Fp);
+    dst[idx] = (f < F) ? src[(size_t)widx[i] * F + f] : 0.0;
+}
+// E[s][r][f] (padded) -> out[l][s][f]
+__global__ void emission_to_lsf_kernel(const double* __restrict__ E, double* __restrict__ out, int L, int S, int F, int Fp, int R_pad) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)L * S * F) return;
+    const int f = (int)(idx % F);
+    const int s = (int)((idx / F) % S);
+    const int l = (int)(idx / ((long long)F * S));
+    out[idx] = E[((size_t)s * R_pad + l) * Fp + f];
+}
+// parent[r][f] *= Y[r][f] (Y padded)
+__global__ void mul_unpad_kernel(const double* __restrict__ Y, double* __restrict__ parent, int n_rows, int F, int Fp) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_rows * F) return;
+    const int r = (int)(idx / F), f = (int)(idx % F);
+    parent[idx] *= Y[(size_t)r * Fp + f];
+}
+
+}  // namespace mope

@@ -1,0 +1,1117 @@
+// mope_b200 host side of the C ABI (include/mope_b200.h).  No torch types; plain pointers and sizes.
+//
+// Host responsibilities (all tiny, exact, per call):
+//   * the scalar part of TransitionData.get_transition_probabilities_2d -- range checks, searchsorted,
+//     bilinear weights (transition_data_2d.py:148-238, transition_data_bottleneck.py:96-183) -- for every
+//     (walker, matrix key), turned into InterpJob records for interp_kernel;
+//   * the branch schedule (postorder walk of likelihoods.py:352-397) compiled once into TreeOp records;
+//   * chunking walkers so that the per-chunk matrix pool fits the caller's workspace.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/mope_b200.h"
+#include "kernels.cuh"
+
+using namespace mope;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(MOPE_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int round_up_i(int x, int a) { return (x + a - 1) / a * a; }
+
+struct Bump {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    bool dry = false;  // size query only
+    template <typename T>
+    T* take(size_t n) {
+        used = align_up(used, 256);
+        T* p = dry ? nullptr : reinterpret_cast<T*>(base + used);
+        used += n * sizeof(T);
+        return p;
+    }
+    bool ok() const { return dry || used <= cap; }
+};
+
+struct Pedigree {
+    int n_leaves = 0, n_branches = 0, L = 0, n_fam = 0, n_mult = 0, n_asc = 0;
+    int R = 0, R_pad = 0, n_tiles = 0, n_slots = 0, n_ops = 0;
+    double* E = nullptr;
+    double* mult = nullptr;  // [n_mult][R_pad]
+    int32_t* fam_asc = nullptr;
+    double* fam_count = nullptr;
+    double* fam_lgamma = nullptr;
+    TreeOp* ops = nullptr;
+    std::vector<TreeOp> ops_h;
+    int asc_offset = 0;
+};
+
+struct FixedKey { int var; int bott; };
+struct RateKey { int var; double min_mult, max_mult; };
+
+}  // namespace
+
+struct mope_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int F = 0, Fp = 0, NT = 0;
+    int n_gens = 0, n_us = 0, n_nbs = 0, n_bot_us = 0;
+    bool has_bot = false;
+    double N = 0;
+    std::vector<double> gens, us, nbs, bot_us, freqs;
+    double min_coal = 0, max_coal = 0, min_mut = 0, max_mut = 0, min_bmut = 0, max_bmut = 0, min_nb = 0, max_nb = 0;
+    // device tables
+    double* tables = nullptr;  // drift [G][U][F][F] then bot [NB][UB][F][F]
+    int64_t bot_base = 0;
+    double* gens_dev = nullptr;
+    // model
+    int n_var = 0, ndim = 0, n_ped = 0, asc_total = 0;
+    double min_phred = -1, min_freq = 0, genome = 0, penalty = 0;
+    std::vector<Pedigree> peds;
+    std::vector<FixedKey> fixed_keys;
+    std::vector<RateKey> rate_keys;
+    int max_slots = 0, max_tiles = 0, max_asc2 = 0;
+    // host staging (pinned, grow-only)
+    char* pinned = nullptr;
+    size_t pinned_cap = 0;
+    // small library-owned device scratch for the operator-level entry points
+    char* opbuf = nullptr;
+    size_t opbuf_cap = 0;
+    int64_t launches = 0;
+    int tree_variant = 13;
+};
+
+namespace {
+
+int ensure_pinned(mope_ctx* c, size_t bytes) {
+    if (bytes <= c->pinned_cap) return 0;
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->pinned = nullptr;
+    c->pinned_cap = 0;
+    size_t cap = align_up(bytes + bytes / 4, 1 << 16);
+    CUDA_TRY(cudaMallocHost(&c->pinned, cap));
+    c->pinned_cap = cap;
+    return 0;
+}
+
+int ensure_opbuf(mope_ctx* c, size_t bytes) {
+    if (bytes <= c->opbuf_cap) return 0;
+    if (c->opbuf) cudaFree(c->opbuf);
+    c->opbuf = nullptr;
+    c->opbuf_cap = 0;
+    size_t cap = align_up(bytes, 1 << 20);
+    CUDA_TRY(cudaMalloc(&c->opbuf, cap));
+    c->opbuf_cap = cap;
+    return 0;
+}
+
+// searchsorted(side='left')
+inline int lower_bound_idx(const std::vector<double>& v, double x) {
+    return (int)(std::lower_bound(v.begin(), v.end(), x) - v.begin());
+}
+
+int validate(const mope_tables_desc* t, const mope_model_desc* m) {
+    if (!t || !m) return fail(MOPE_E_INVALID, "null description");
+    if (t->F < 2 || t->n_gens < 2 || t->n_us < 2 || !t->drift || !t->gens || !t->us || !t->freqs)
+        return fail(MOPE_E_INVALID, "drift tables need F>=2 and a grid of at least 2x2");
+    if (t->bot && (t->n_nbs < 2 || t->n_bot_us < 2 || !t->nbs || !t->bot_us))
+        return fail(MOPE_E_INVALID, "bottleneck tables need a grid of at least 2x2");
+    for (int i = 1; i < t->n_gens; ++i) if (!(t->gens[i] > t->gens[i - 1])) return fail(MOPE_E_INVALID, "gens not ascending");
+    for (int i = 1; i < t->n_us; ++i) if (!(t->us[i] > t->us[i - 1])) return fail(MOPE_E_INVALID, "us not ascending");
+    if (m->n_var < 1 || m->n_ped < 1 || !m->peds) return fail(MOPE_E_INVALID, "model needs >=1 variable and >=1 pedigree");
+    for (int k = 0; k < m->n_ped; ++k) {
+        const mope_pedigree_desc& p = m->peds[k];
+        if (p.n_leaves < 1 || p.n_branches < 1 || p.n_loci < 0 || p.n_fam < 1 || p.n_asc < 1 || p.n_mult < 0)
+            return fail(MOPE_E_INVALID, "pedigree %d: bad sizes", k);
+        for (int b = 0; b < p.n_branches; ++b) {
+            if (p.br_parent[b] <= b || p.br_parent[b] > p.n_branches)
+                return fail(MOPE_E_INVALID, "pedigree %d: branch %d parent %d violates postorder numbering", k, b, p.br_parent[b]);
+            if (p.br_var[b] < 0 || p.br_var[b] >= m->n_var) return fail(MOPE_E_INVALID, "pedigree %d: bad var index", k);
+            if (p.br_mult[b] >= p.n_mult) return fail(MOPE_E_INVALID, "pedigree %d: bad multiplier index", k);
+            if (p.br_leaf[b] >= p.n_leaves) return fail(MOPE_E_INVALID, "pedigree %d: bad leaf index", k);
+            if (p.br_bottleneck[b] && p.br_mult[b] >= 0)
+                return fail(MOPE_E_INVALID, "pedigree %d: a multiplier on a bottleneck branch is not defined", k);
+        }
+        for (int f = 0; f < p.n_fam; ++f)
+            if (p.fam_asc[f] < 0 || p.fam_asc[f] >= p.n_asc) return fail(MOPE_E_INVALID, "pedigree %d: bad fam_asc", k);
+    }
+    return 0;
+}
+
+// Compile the branch schedule.  Slots are assigned with stack discipline over the postorder walk.
+int compile_schedule(const mope_pedigree_desc& pd, const std::vector<int>& fixed_key_of_branch,
+                     const std::vector<int>& rate_key_of_branch, Pedigree& out) {
+    const int nb = pd.n_branches, root = pd.n_branches;
+    std::vector<int> slot(nb + 1, -1), nchild(nb + 1, 0), seen(nb + 1, 0);
+    for (int b = 0; b < nb; ++b) nchild[pd.br_parent[b]]++;
+    std::vector<int> free_slots;
+    int n_slots = 0;
+    out.ops_h.clear();
+    for (int b = 0; b < nb; ++b) {
+        TreeOp op{};
+        const int par = pd.br_parent[b];
+        if (pd.br_leaf[b] >= 0) {
+            if (nchild[b] != 0) return fail(MOPE_E_INVALID, "branch %d is marked leaf but has children", b);
+            op.src_kind = 0;
+            op.src = pd.br_leaf[b];
+        } else {
+            if (nchild[b] == 0 || slot[b] < 0) return fail(MOPE_E_INVALID, "internal node %d has no children", b);
+            op.src_kind = 1;
+            op.src = slot[b];
+        }
+        op.first = (seen[par] == 0);
+        seen[par]++;
+        const bool completes_root = (par == root && seen[par] == nchild[par]);
+        op.last = completes_root ? 1 : 0;
+        if (slot[par] < 0 && !(completes_root && op.first)) {
+            if (!free_slots.empty()) { slot[par] = free_slots.back(); free_slots.pop_back(); }
+            else slot[par] = n_slots++;
+        }
+        op.dst = slot[par];
+        if (pd.br_mult[b] >= 0) { op.kind = 1; op.key = rate_key_of_branch[b]; op.mult = pd.br_mult[b]; }
+        else { op.kind = 0; op.key = fixed_key_of_branch[b]; op.mult = -1; }
+        out.ops_h.push_back(op);
+        // the child's slot is free once consumed (after this op)
+        if (op.src_kind == 1) free_slots.push_back(slot[b]);
+    }
+    if (out.ops_h.empty() || !out.ops_h.back().last) return fail(MOPE_E_INVALID, "schedule does not end at the root");
+    out.n_slots = std::max(n_slots, 1);
+    out.n_ops = (int)out.ops_h.size();
+    return 0;
+}
+
+struct ArenaPlan {
+    size_t bytes = 0;
+};
+
+// lays out (or just sizes) everything that lives in the arena
+int layout_arena(mope_ctx* c, const mope_tables_desc* t, const mope_model_desc* m, Bump& bump, bool dry) {
+    const size_t FF = (size_t)t->F * t->F;
+    size_t ntab = (size_t)t->n_gens * t->n_us * FF + (t->bot ? (size_t)t->n_nbs * t->n_bot_us * FF : 0);
+    double* tab = bump.take<double>(ntab);
+    double* gd = bump.take<double>(t->n_gens);
+    if (!dry) { c->tables = tab; c->gens_dev = gd; c->bot_base = (int64_t)t->n_gens * t->n_us * FF; }
+    const int Fp = round_up_i(t->F, 16);
+    for (int k = 0; k < m->n_ped; ++k) {
+        const mope_pedigree_desc& pd = m->peds[k];
+        const int R = pd.n_loci + 2 * pd.n_asc;
+        const int R_pad = round_up_i(std::max(R, 1), TM);
+        double* E = bump.take<double>((size_t)pd.n_leaves * R_pad * Fp);
+        double* mu = bump.take<double>((size_t)std::max(pd.n_mult, 1) * R_pad);
+        int32_t* fa = bump.take<int32_t>(pd.n_fam);
+        double* fc = bump.take<double>(pd.n_fam);
+        double* fl = bump.take<double>(pd.n_fam);
+        TreeOp* ops = bump.take<TreeOp>(pd.n_branches);
+        if (!dry) {
+            Pedigree& P = c->peds[k];
+            P.E = E; P.mult = mu; P.fam_asc = fa; P.fam_count = fc; P.fam_lgamma = fl; P.ops = ops;
+        }
+    }
+    // transient inputs of the emission kernel live at the arena tail; they are dead after create().
+    // Size it with the same take() sequence create() uses (each take is 256-byte aligned).
+    size_t max_cells = 1;
+    for (int k = 0; k < m->n_ped; ++k) max_cells = std::max(max_cells, (size_t)m->peds[k].n_loci * m->peds[k].n_leaves);
+    if (dry) {
+        bump.take<double>(max_cells);
+        bump.take<double>(max_cells);
+        bump.take<double>(t->F);
+        bump.take<double>(t->F);
+        bump.take<int8_t>(t->F);
+        bump.take<int8_t>(t->F);
+        bump.take<int8_t>(t->F);
+    }
+    return 0;
+}
+
+template <int NTW>
+int launch_tree_t(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(tree_kernel<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<NTW>::SMEM_BYTES));
+        attr_set = true;
+    }
+    tree_kernel<NTW><<<grid, NTHREADS, TileCfg<NTW>::SMEM_BYTES, st>>>(tp);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int launch_tree(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) {
+    switch (c->tree_variant) {
+        case 5: return launch_tree_t<5>(c, tp, grid, st);
+        case 8: return launch_tree_t<8>(c, tp, grid, st);
+        default: return launch_tree_t<13>(c, tp, grid, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-walker interpolation plan
+// ------------------------------------------------------------------------------------------------
+struct WalkerPlan {
+    int32_t status = 0;
+    size_t n_blocks = 0;  // matrix blocks this walker needs in the pool
+};
+
+struct PlanOut {
+    std::vector<InterpJob> jobs;   // dst offsets relative to the chunk pool
+    std::vector<int64_t> mat_off;  // [Wc][n_mat]
+    std::vector<RateInfo> rate;    // [Wc][n_rate]
+};
+
+// range checks of one non-rate key (transition_data_2d.py:158-173, transition_data_bottleneck.py:118-129)
+int32_t status_fixed(const mope_ctx* c, bool bott, double len, double mut) {
+    int32_t st = 0;
+    if (bott) {
+        if (!c->has_bot) return MOPE_ST_NO_BOTTLENECK_TABLE;
+        if (std::isnan(len) || std::isnan(mut)) st |= MOPE_ST_NOT_FINITE;
+        if (len < c->min_nb) st |= MOPE_ST_NB_TOO_SMALL;
+        if (len > c->max_nb) st |= MOPE_ST_NB_TOO_LARGE;
+        if (mut < c->min_bmut) st |= MOPE_ST_MUT_TOO_SMALL;
+        if (mut > c->max_bmut) st |= MOPE_ST_MUT_TOO_LARGE;
+    } else {
+        if (!std::isfinite(len) || !std::isfinite(mut)) st |= MOPE_ST_NOT_FINITE;
+        if (len > c->max_coal) st |= MOPE_ST_TIME_TOO_LARGE;
+        if (mut < c->min_mut) st |= MOPE_ST_MUT_TOO_SMALL;
+        if (mut > c->max_mut) st |= MOPE_ST_MUT_TOO_LARGE;
+    }
+    return st;
+}
+
+// range checks of a rate key: times are mult*len, monotone in mult, so the extreme multipliers decide
+int32_t status_rate(const mope_ctx* c, double min_mult, double max_mult, double len, double mut) {
+    int32_t st = 0;
+    const double tmax = max_mult * len, tmin = min_mult * len;
+    if (!std::isfinite(tmax) || !std::isfinite(tmin) || !std::isfinite(mut)) st |= MOPE_ST_NOT_FINITE;
+    if (tmax > c->max_coal) st |= MOPE_ST_TIME_TOO_LARGE;
+    if (mut < c->min_mut) st |= MOPE_ST_MUT_TOO_SMALL;
+    if (mut > c->max_mut) st |= MOPE_ST_MUT_TOO_LARGE;
+    return st;
+}
+
+// generation-grid range [glo, ghi] a rate key needs; false when every row takes the identity short-cut
+bool rate_range(const mope_ctx* c, double min_mult, double max_mult, double len, int& glo, int& ghi) {
+    const double gmax = c->N * (max_mult * len), gmin = c->N * (min_mult * len);
+    if (gmax < c->gens[0]) return false;
+    ghi = std::min(lower_bound_idx(c->gens, gmax), c->n_gens - 1);
+    glo = (gmin < c->gens[0]) ? 0 : std::max(std::min(lower_bound_idx(c->gens, gmin), c->n_gens - 1) - 1, 0);
+    return true;
+}
+
+// one non-rate matrix with exact (len, mut); b = block index inside the chunk pool
+void emit_fixed_job(const mope_ctx* c, bool bott, double len, double mut, size_t& b, PlanOut& out) {
+    const size_t FF = (size_t)c->F * c->F;
+    const size_t blk = (size_t)c->Fp * c->Fp + c->Fp;
+    InterpJob jb{};
+    jb.dst = (int64_t)(b * blk);
+    out.mat_off.push_back(jb.dst);
+    ++b;
+    if (bott) {
+        // transition_data_bottleneck.py:138-171
+        const int nbn = c->n_nbs, nun = c->n_bot_us;
+        int bi = std::min(lower_bound_idx(c->nbs, len), nbn - 1);
+        const double u = mut / (2.0 * c->N);
+        int ui = std::min(lower_bound_idx(c->bot_us, u), nun - 1);
+        const int b1 = bi > 0 ? bi - 1 : nbn - 1, u1i = ui > 0 ? ui - 1 : nun - 1;  // python's index -1 wraps
+        const double t = len, t1 = c->nbs[b1], t2 = c->nbs[bi], u1 = c->bot_us[u1i], u2 = c->bot_us[ui];
+        const double denom = (t2 - t1) * (u2 - u1);
+        jb.w[0] = (t2 - t) * (u2 - u) / denom;  // w11
+        jb.w[2] = (t - t1) * (u2 - u) / denom;  // w21
+        jb.w[1] = (t2 - t) * (u - u1) / denom;  // w12
+        jb.w[3] = (t - t1) * (u - u1) / denom;  // w22
+        jb.src[0] = c->bot_base + (int64_t)(((size_t)b1 * nun + u1i) * FF);
+        jb.src[1] = c->bot_base + (int64_t)(((size_t)b1 * nun + ui) * FF);
+        jb.src[2] = c->bot_base + (int64_t)(((size_t)bi * nun + u1i) * FF);
+        jb.src[3] = c->bot_base + (int64_t)(((size_t)bi * nun + ui) * FF);
+        jb.flags = 0;
+    } else {
+        // transition_data_2d.py:183-224
+        const double t = c->N * len;
+        if (t < c->gens[0]) {
+            jb.flags = 2;
+        } else {
+            const int G = c->n_gens, U = c->n_us;
+            const int gi = std::min(lower_bound_idx(c->gens, t), G - 1);
+            const double xd = mut / (2.0 * c->N);
+            const int xi = std::min(lower_bound_idx(c->us, xd), U - 1);
+            const int g1 = gi > 0 ? gi - 1 : G - 1, x1i = xi > 0 ? xi - 1 : U - 1;
+            const double t1 = c->gens[g1], t2 = c->gens[gi], x1 = c->us[x1i], x2 = c->us[xi];
+            const double denom = (t2 - t1) * (x2 - x1);
+            jb.w[0] = (t2 - t) * (x2 - xd) / denom;
+            jb.w[2] = (t - t1) * (x2 - xd) / denom;
+            jb.w[1] = (t2 - t) * (xd - x1) / denom;
+            jb.w[3] = (t - t1) * (xd - x1) / denom;
+            jb.src[0] = (int64_t)(((size_t)g1 * U + x1i) * FF);
+            jb.src[1] = (int64_t)(((size_t)g1 * U + xi) * FF);
+            jb.src[2] = (int64_t)(((size_t)gi * U + x1i) * FF);
+            jb.src[3] = (int64_t)(((size_t)gi * U + xi) * FF);
+            jb.flags = 1;
+        }
+    }
+    out.jobs.push_back(jb);
+}
+
+// the mutation-axis blends A_g = bx*Q[g,x1] + cx*Q[g,x2] for every generation-grid index a rate key touches;
+// the time-axis blend is per row and happens inside the tree kernel
+void emit_rate_jobs(const mope_ctx* c, double min_mult, double max_mult, double len, double mut, size_t& b, PlanOut& out) {
+    const size_t FF = (size_t)c->F * c->F;
+    const size_t blk = (size_t)c->Fp * c->Fp + c->Fp;
+    RateInfo ri{};
+    ri.len = len;
+    ri.off = (int64_t)(b * blk);
+    ri.gbase = 0;
+    ri.gcount = 0;
+    int glo, ghi;
+    if (rate_range(c, min_mult, max_mult, len, glo, ghi)) {
+        const int U = c->n_us;
+        const double xd = mut / (2.0 * c->N);
+        const int xi = std::min(lower_bound_idx(c->us, xd), U - 1);
+        const int x1i = xi > 0 ? xi - 1 : U - 1;
+        const double x1 = c->us[x1i], x2 = c->us[xi];
+        const double bx = (x2 - xd) / (x2 - x1), cx = (xd - x1) / (x2 - x1);
+        ri.gbase = glo;
+        ri.gcount = ghi - glo + 1;
+        for (int g = glo; g <= ghi; ++g) {
+            InterpJob jb{};
+            jb.dst = (int64_t)(b * blk);
+            ++b;
+            jb.src[0] = (int64_t)(((size_t)g * U + x1i) * FF);
+            jb.src[1] = (int64_t)(((size_t)g * U + xi) * FF);
+            jb.src[2] = jb.src[0];
+            jb.src[3] = jb.src[1];
+            jb.w[0] = bx; jb.w[1] = cx; jb.w[2] = 0; jb.w[3] = 0;
+            jb.flags = 4;  // two-term blend; the clamp/renormalisation is applied per row in the tree kernel
+            out.jobs.push_back(jb);
+        }
+    }
+    out.rate.push_back(ri);
+}
+
+// status + number of blocks for one walker (no jobs yet)
+void plan_walker_size(const mope_ctx* c, const double* x, WalkerPlan& wp) {
+    wp.status = 0;
+    wp.n_blocks = 0;
+    const int nv = c->n_var;
+    for (const FixedKey& k : c->fixed_keys) {
+        wp.status |= status_fixed(c, k.bott != 0, std::pow(10.0, x[k.var]), std::pow(10.0, x[nv + k.var]));
+        wp.n_blocks += 1;
+    }
+    for (const RateKey& k : c->rate_keys) {
+        const double len = std::pow(10.0, x[k.var]);
+        const int32_t st = status_rate(c, k.min_mult, k.max_mult, len, std::pow(10.0, x[nv + k.var]));
+        wp.status |= st;
+        int glo, ghi;
+        if (!st && rate_range(c, k.min_mult, k.max_mult, len, glo, ghi)) wp.n_blocks += (size_t)(ghi - glo + 1);
+    }
+}
+
+// emit jobs for one (valid) walker; block0 is the walker's first block inside the chunk pool
+void plan_walker_jobs(const mope_ctx* c, const double* x, size_t block0, PlanOut& out) {
+    const int nv = c->n_var;
+    size_t b = block0;
+    for (const FixedKey& k : c->fixed_keys)
+        emit_fixed_job(c, k.bott != 0, std::pow(10.0, x[k.var]), std::pow(10.0, x[nv + k.var]), b, out);
+    for (const RateKey& k : c->rate_keys)
+        emit_rate_jobs(c, k.min_mult, k.max_mult, std::pow(10.0, x[k.var]), std::pow(10.0, x[nv + k.var]), b, out);
+}
+
+// fixed (walker-independent) part of the eval workspace
+struct WsFixed {
+    size_t scratch_doubles, out_ll, out_root, out_asc;
+};
+
+size_t per_walker_bytes(const mope_ctx* c, size_t n_blocks) {
+    const size_t blk = ((size_t)c->Fp * c->Fp + c->Fp) * sizeof(double);
+    size_t b = n_blocks * (blk + sizeof(InterpJob));
+    b += c->fixed_keys.size() * sizeof(int64_t) + c->rate_keys.size() * sizeof(RateInfo);
+    b += (size_t)c->Fp * sizeof(double);                 // stat
+    b += (size_t)c->max_tiles * sizeof(double);          // tile_ll
+    b += (size_t)c->max_asc2 * sizeof(double);           // asc_dot
+    return b + 64;
+}
+
+size_t fixed_ws_bytes(const mope_ctx* c, int W) {
+    size_t b = (size_t)c->num_sms * c->max_slots * TM * c->Fp * sizeof(double);  // scratch
+    b += (size_t)W * sizeof(double) * (1 + c->n_ped);                             // out_ll, out_root
+    b += (size_t)W * c->asc_total * sizeof(double);                               // out_log_asc
+    b += (size_t)W * sizeof(int32_t);                                             // walker index
+    return b + 16 * 256 + 4096;
+}
+
+size_t max_blocks_per_walker(const mope_ctx* c) {
+    return c->fixed_keys.size() + c->rate_keys.size() * (size_t)c->n_gens;
+}
+
+// the core: evaluate walkers whose params are on the host; stat may be a host or device pointer
+int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_on_device, int W, void* workspace,
+              size_t ws_bytes, cudaStream_t st, double* out_ll, bool out_on_device, int32_t* out_status,
+              double* out_root_ll, double* out_log_asc) {
+    if (!c || !params || !stat || !out_ll || W < 0) return fail(MOPE_E_INVALID, "eval: null argument");
+    if (W == 0) return 0;
+    if (!workspace) return fail(MOPE_E_INVALID, "eval: null workspace");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int ndim = c->ndim, Fp = c->Fp, F = c->F;
+    const int n_mat = (int)c->fixed_keys.size(), n_rate = (int)c->rate_keys.size();
+
+    // 1. plan sizes / statuses
+    std::vector<WalkerPlan> plans(W);
+    std::vector<int> good;
+    good.reserve(W);
+    for (int w = 0; w < W; ++w) {
+        plan_walker_size(c, params + (size_t)w * ndim, plans[w]);
+        if (out_status) out_status[w] = plans[w].status;
+        if (plans[w].status == 0) good.push_back(w);
+    }
+    const int Wg = (int)good.size();
+
+    // 2. carve the walker-independent part of the workspace
+    Bump ws;
+    ws.base = (char*)workspace;
+    ws.cap = ws_bytes;
+    double* scratch = ws.take<double>((size_t)c->num_sms * c->max_slots * TM * Fp);
+    double* d_out_ll = out_on_device ? out_ll : ws.take<double>(W);
+    double* d_out_root = out_root_ll ? ws.take<double>((size_t)W * c->n_ped) : nullptr;
+    double* d_out_asc = out_log_asc ? ws.take<double>((size_t)W * c->asc_total) : nullptr;
+    if (!ws.ok()) return fail(MOPE_E_NOMEM, "workspace too small: %zu bytes, need more than %zu", ws_bytes, ws.used);
+    const size_t fixed_used = ws.used;
+
+    // outputs of invalid walkers: NaN (the host wrapper raises ValueError like the reference)
+    {
+        // fill everything with NaN once; valid walkers overwrite
+        std::vector<double> nanv(W, std::numeric_limits<double>::quiet_NaN());
+        size_t need = (size_t)W * sizeof(double);
+        if (ensure_pinned(c, need)) return MOPE_E_CUDA;
+        // (pinned buffer is re-used below; this copy is ordered on the stream before any kernel)
+        std::memcpy(c->pinned, nanv.data(), need);
+        CUDA_TRY(cudaMemcpyAsync(d_out_ll, c->pinned, need, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+
+    // 3. chunk the valid walkers
+    size_t gi0 = 0;
+    // staging size upper bound for one chunk is computed per chunk
+    while (gi0 < (size_t)Wg) {
+        size_t avail = ws_bytes - align_up(fixed_used, 256);
+        size_t used = 16 * 256;  // alignment slack of the per-chunk carve
+        size_t n_blocks = 0;
+        size_t gi1 = gi0;
+        while (gi1 < (size_t)Wg) {
+            const size_t nb = plans[good[gi1]].n_blocks;
+            const size_t add = per_walker_bytes(c, nb);
+            if (used + add > avail) break;
+            used += add;
+            n_blocks += nb;
+            ++gi1;
+        }
+        if (gi1 == gi0) return fail(MOPE_E_NOMEM, "workspace too small for a single walker: %zu bytes available, %zu needed",
+                                    avail, used + per_walker_bytes(c, plans[good[gi0]].n_blocks));
+        const int Wc = (int)(gi1 - gi0);
+
+        PlanOut po;
+        po.jobs.reserve(n_blocks);
+        po.mat_off.reserve((size_t)Wc * n_mat);
+        po.rate.reserve((size_t)Wc * n_rate);
+        size_t b0 = 0;
+        std::vector<int32_t> widx(Wc);
+        for (int i = 0; i < Wc; ++i) {
+            const int w = good[gi0 + i];
+            widx[i] = w;
+            plan_walker_jobs(c, params + (size_t)w * ndim, b0, po);
+            b0 += plans[w].n_blocks;
+        }
+        if (po.jobs.size() != n_blocks) return fail(MOPE_E_INVALID, "internal: plan size mismatch (%zu vs %zu)", po.jobs.size(), n_blocks);
+
+        // carve the chunk part
+        Bump cw = ws;
+        cw.used = fixed_used;
+        const size_t blk = (size_t)Fp * Fp + Fp;
+        InterpJob* d_jobs = cw.take<InterpJob>(std::max<size_t>(n_blocks, 1));
+        int64_t* d_mat_off = cw.take<int64_t>(std::max<size_t>((size_t)Wc * n_mat, 1));
+        RateInfo* d_rate = cw.take<RateInfo>(std::max<size_t>((size_t)Wc * n_rate, 1));
+        int32_t* d_widx = cw.take<int32_t>(Wc);
+        double* d_stat = cw.take<double>((size_t)Wc * Fp);
+        double* d_pool = cw.take<double>(std::max<size_t>(n_blocks, 1) * blk);
+        double* d_tile_ll = cw.take<double>((size_t)Wc * c->max_tiles);
+        double* d_asc_dot = cw.take<double>((size_t)Wc * std::max(c->max_asc2, 2));
+        if (!cw.ok()) return fail(MOPE_E_NOMEM, "internal: chunk carve exceeded the workspace (%zu > %zu)", cw.used, cw.cap);
+
+        // stage host -> device
+        const size_t sz_jobs = n_blocks * sizeof(InterpJob), sz_mo = (size_t)Wc * n_mat * sizeof(int64_t),
+                     sz_rate = (size_t)Wc * n_rate * sizeof(RateInfo), sz_widx = (size_t)Wc * sizeof(int32_t),
+                     sz_stat = (size_t)Wc * Fp * sizeof(double);
+        const size_t stage_bytes = align_up(sz_jobs, 64) + align_up(sz_mo, 64) + align_up(sz_rate, 64) + align_up(sz_widx, 64) +
+                                   (stat_on_device ? 0 : align_up(sz_stat, 64));
+        CUDA_TRY(cudaStreamSynchronize(st));  // previous chunk's staging is consumed
+        if (ensure_pinned(c, stage_bytes)) return MOPE_E_CUDA;
+        char* hp = c->pinned;
+        auto push = [&](void* dptr, const void* src, size_t bytes) -> int {
+            if (bytes == 0) return 0;
+            std::memcpy(hp, src, bytes);
+            CUDA_TRY(cudaMemcpyAsync(dptr, hp, bytes, cudaMemcpyHostToDevice, st));
+            hp += align_up(bytes, 64);
+            return 0;
+        };
+        if (push(d_jobs, po.jobs.data(), sz_jobs)) return MOPE_E_CUDA;
+        if (push(d_mat_off, po.mat_off.data(), sz_mo)) return MOPE_E_CUDA;
+        if (push(d_rate, po.rate.data(), sz_rate)) return MOPE_E_CUDA;
+        if (push(d_widx, widx.data(), sz_widx)) return MOPE_E_CUDA;
+        if (!stat_on_device) {
+            double* hs = reinterpret_cast<double*>(hp);
+            for (int i = 0; i < Wc; ++i) {
+                const double* src = stat + (size_t)widx[i] * F;
+                std::memcpy(hs + (size_t)i * Fp, src, (size_t)F * sizeof(double));
+                for (int f = F; f < Fp; ++f) hs[(size_t)i * Fp + f] = 0.0;
+            }
+            CUDA_TRY(cudaMemcpyAsync(d_stat, hs, sz_stat, cudaMemcpyHostToDevice, st));
+        } else {
+            // gather + pad rows on the device
+            const long long total = (long long)Wc * Fp;
+            gather_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(stat, d_widx, d_stat, Wc, F, Fp);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+        }
+
+        // interpolation
+        if (n_blocks > 0) {
+            const int wpb = 8;
+            const long long rows = (long long)n_blocks * Fp;
+            const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+            interp_kernel<<<grid, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_jobs, (int)n_blocks, c->tables, d_pool, F, Fp);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+        }
+
+        // pruning + finalize per pedigree
+        for (int k = 0; k < c->n_ped; ++k) {
+            const Pedigree& P = c->peds[k];
+            TreeParams tp{};
+            tp.E = P.E;
+            tp.E_leaf_stride = (int64_t)P.R_pad * Fp;
+            tp.scratch = scratch;
+            tp.ops = P.ops;
+            tp.n_ops = P.n_ops;
+            tp.n_slots = c->max_slots;
+            tp.R = P.R; tp.L = P.L; tp.R_pad = P.R_pad; tp.Fp = Fp; tp.F = F; tp.NT = c->NT; tp.n_tiles = P.n_tiles; tp.W = Wc;
+            tp.pool = d_pool;
+            tp.mat_off = d_mat_off;
+            tp.n_mat = n_mat; tp.n_rate = n_rate;
+            tp.rate = d_rate;
+            tp.mult = P.mult;
+            tp.gens = c->gens_dev;
+            tp.n_gens = c->n_gens;
+            tp.Npop = c->N;
+            tp.stat = d_stat;
+            tp.tile_ll = d_tile_ll;
+            tp.asc_dot = d_asc_dot;
+            tp.Yout = nullptr;
+            const long long items = (long long)Wc * P.n_tiles;
+            const int grid = (int)std::min<long long>(items, c->num_sms);
+            if (launch_tree(c, tp, grid, st)) return MOPE_E_CUDA;
+
+            FinalizeParams fp{};
+            fp.tile_ll = d_tile_ll; fp.asc_dot = d_asc_dot;
+            fp.fam_asc = P.fam_asc; fp.fam_count = P.fam_count; fp.fam_lgamma = P.fam_lgamma;
+            fp.out_ll = d_out_ll; fp.out_root_ll = d_out_root; fp.out_log_asc = d_out_asc;
+            fp.widx = d_widx;
+            fp.n_tiles = P.n_tiles; fp.n_asc = P.n_asc; fp.n_fam = P.n_fam; fp.W = Wc;
+            fp.ped_index = k; fp.ped_stride = c->n_ped; fp.asc_offset = P.asc_offset; fp.asc_stride = c->asc_total;
+            fp.accumulate = (k > 0);
+            fp.log_genome = std::log(c->genome);
+            fp.penalty = c->penalty;
+            finalize_kernel<<<Wc, 256, 0, st>>>(fp);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+        }
+        gi0 = gi1;
+    }
+
+    if (!out_on_device) {
+        // device -> host
+        size_t need = (size_t)W * sizeof(double) * (1 + (out_root_ll ? c->n_ped : 0) + (out_log_asc ? c->asc_total : 0));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (ensure_pinned(c, need)) return MOPE_E_CUDA;
+        char* hp = c->pinned;
+        CUDA_TRY(cudaMemcpyAsync(hp, d_out_ll, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, st));
+        char* hp_root = hp + (size_t)W * sizeof(double);
+        char* hp_asc = hp_root + (out_root_ll ? (size_t)W * c->n_ped * sizeof(double) : 0);
+        if (out_root_ll) CUDA_TRY(cudaMemcpyAsync(hp_root, d_out_root, (size_t)W * c->n_ped * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (out_log_asc) CUDA_TRY(cudaMemcpyAsync(hp_asc, d_out_asc, (size_t)W * c->asc_total * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        std::memcpy(out_ll, hp, (size_t)W * sizeof(double));
+        if (out_root_ll) std::memcpy(out_root_ll, hp_root, (size_t)W * c->n_ped * sizeof(double));
+        if (out_log_asc) std::memcpy(out_log_asc, hp_asc, (size_t)W * c->asc_total * sizeof(double));
+        const double qnan = std::numeric_limits<double>::quiet_NaN();
+        for (int w = 0; w < W; ++w) {
+            if (plans[w].status) {
+                out_ll[w] = qnan;
+                if (out_root_ll) for (int k = 0; k < c->n_ped; ++k) out_root_ll[(size_t)w * c->n_ped + k] = qnan;
+                if (out_log_asc) for (int u = 0; u < c->asc_total; ++u) out_log_asc[(size_t)w * c->asc_total + u] = qnan;
+            }
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* mope_b200_last_error(void) { return g_err.c_str(); }
+const char* mope_b200_version(void) { return "mope_b200 0.1 (sm_100a, fp64 DMMA)"; }
+
+int mope_b200_arena_bytes(const mope_tables_desc* tables, const mope_model_desc* model, size_t* out_bytes) {
+    if (!out_bytes) return fail(MOPE_E_INVALID, "null out_bytes");
+    if (int rc = validate(tables, model)) return rc;
+    Bump b;
+    b.dry = true;
+    layout_arena(nullptr, tables, model, b, true);
+    *out_bytes = align_up(b.used, 256) + 4096;
+    return 0;
+}
+
+int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int device, void* arena, size_t arena_bytes,
+                     void* stream, mope_ctx** out) {
+    if (!out) return fail(MOPE_E_INVALID, "null out");
+    *out = nullptr;
+    if (int rc = validate(t, m)) return rc;
+    if (!arena) return fail(MOPE_E_INVALID, "null arena");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device || device < 0)
+        return fail(MOPE_E_NODEVICE, "CUDA device %d not available (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(MOPE_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    cudaStream_t st = (cudaStream_t)stream;
+
+    mope_ctx* c = new mope_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->F = t->F;
+    c->Fp = round_up_i(t->F, 16);
+    c->NT = (t->F + 7) / 8;
+    c->tree_variant = c->Fp <= 80 ? 5 : (c->Fp <= 128 ? 8 : 13);
+    c->n_gens = t->n_gens; c->n_us = t->n_us;
+    c->has_bot = t->bot != nullptr;
+    c->n_nbs = c->has_bot ? t->n_nbs : 0;
+    c->n_bot_us = c->has_bot ? t->n_bot_us : 0;
+    c->N = t->N;
+    c->gens.assign(t->gens, t->gens + t->n_gens);
+    c->us.assign(t->us, t->us + t->n_us);
+    c->freqs.assign(t->freqs, t->freqs + t->F);
+    if (c->has_bot) { c->nbs.assign(t->nbs, t->nbs + t->n_nbs); c->bot_us.assign(t->bot_us, t->bot_us + t->n_bot_us); }
+    // transition_data_2d.py:105-108, transition_data_bottleneck.py:90-93
+    c->min_coal = c->gens.front() / c->N; c->max_coal = c->gens.back() / c->N;
+    c->min_mut = c->us.front() * 2 * c->N; c->max_mut = c->us.back() * 2 * c->N;
+    if (c->has_bot) {
+        c->min_nb = c->nbs.front(); c->max_nb = c->nbs.back();
+        c->min_bmut = c->bot_us.front() * 2 * c->N; c->max_bmut = c->bot_us.back() * 2 * c->N;
+    }
+    c->n_var = m->n_var; c->ndim = 2 * m->n_var + 2; c->n_ped = m->n_ped;
+    c->min_phred = m->min_phred_score; c->min_freq = m->min_freq; c->genome = m->genome_size; c->penalty = m->poisson_like_penalty;
+    c->peds.resize(m->n_ped);
+
+    // matrix keys shared by all pedigrees
+    std::vector<std::vector<int>> fk(m->n_ped), rk(m->n_ped);
+    for (int k = 0; k < m->n_ped; ++k) {
+        const mope_pedigree_desc& pd = m->peds[k];
+        fk[k].assign(pd.n_branches, -1);
+        rk[k].assign(pd.n_branches, -1);
+        for (int b = 0; b < pd.n_branches; ++b) {
+            const int v = pd.br_var[b];
+            if (pd.br_mult[b] < 0) {
+                const int bott = pd.br_bottleneck[b] ? 1 : 0;
+                int idx = -1;
+                for (size_t i = 0; i < c->fixed_keys.size(); ++i) if (c->fixed_keys[i].var == v && c->fixed_keys[i].bott == bott) idx = (int)i;
+                if (idx < 0) { c->fixed_keys.push_back({v, bott}); idx = (int)c->fixed_keys.size() - 1; }
+                fk[k][b] = idx;
+            } else {
+                double mn = std::numeric_limits<double>::infinity(), mx = -mn;
+                const int mc = pd.br_mult[b];
+                for (int r = 0; r < pd.n_loci; ++r) { double v2 = pd.row_mult[(size_t)mc * pd.n_loci + r]; mn = std::min(mn, v2); mx = std::max(mx, v2); }
+                for (int u = 0; u < pd.n_asc; ++u) { double v2 = pd.asc_mult[(size_t)mc * pd.n_asc + u]; mn = std::min(mn, v2); mx = std::max(mx, v2); }
+                int idx = -1;
+                for (size_t i = 0; i < c->rate_keys.size(); ++i) if (c->rate_keys[i].var == v) idx = (int)i;
+                if (idx < 0) { c->rate_keys.push_back({v, mn, mx}); idx = (int)c->rate_keys.size() - 1; }
+                else { c->rate_keys[idx].min_mult = std::min(c->rate_keys[idx].min_mult, mn); c->rate_keys[idx].max_mult = std::max(c->rate_keys[idx].max_mult, mx); }
+                rk[k][b] = idx;
+            }
+        }
+    }
+
+    Bump bump;
+    bump.base = (char*)arena;
+    bump.cap = arena_bytes;
+    layout_arena(c, t, m, bump, false);
+    if (!bump.ok()) { delete c; return fail(MOPE_E_NOMEM, "arena too small: %zu bytes, need %zu", arena_bytes, bump.used); }
+
+    auto cleanup_fail = [&](int rc) { delete c; return rc; };
+#define CUDA_TRY_C(expr)                                                                                        \
+    do {                                                                                                        \
+        cudaError_t e__ = (expr);                                                                               \
+        if (e__ != cudaSuccess)                                                                                 \
+            return cleanup_fail(fail(MOPE_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+    } while (0)
+
+    // tables
+    const size_t FF = (size_t)t->F * t->F;
+    CUDA_TRY_C(cudaMemcpyAsync(c->tables, t->drift, (size_t)t->n_gens * t->n_us * FF * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (c->has_bot)
+        CUDA_TRY_C(cudaMemcpyAsync(c->tables + c->bot_base, t->bot, (size_t)t->n_nbs * t->n_bot_us * FF * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY_C(cudaMemcpyAsync(c->gens_dev, t->gens, (size_t)t->n_gens * sizeof(double), cudaMemcpyHostToDevice, st));
+
+    // per-frequency emission constants on the host with libm (mope/_binom.pyx:76-91)
+    const int F = t->F, Fp = c->Fp;
+    std::vector<double> logp(F), log1mp(F);
+    std::vector<int8_t> pclass(F), e0(F), eN(F);
+    const double perr = (m->min_phred_score != -1.0) ? std::pow(10.0, -1.0 * m->min_phred_score / 10.0) : 0.0;
+    for (int f = 0; f < F; ++f) {
+        const double fr = t->freqs[f];
+        const double p = (1.0 - perr) * fr + (perr / 3.0) * (1.0 - fr);
+        pclass[f] = (p == 0.0) ? 1 : ((p == 1.0) ? 2 : 0);
+        logp[f] = (p > 0.0) ? std::log(p) : 0.0;
+        log1mp[f] = (p < 1.0) ? std::log1p(-p) : 0.0;
+        e0[f] = fr < m->min_freq;         // ascertainment.py:178-183
+        eN[f] = fr > 1 - m->min_freq;
+    }
+
+    int asc_off = 0;
+    for (int k = 0; k < m->n_ped; ++k) {
+        const mope_pedigree_desc& pd = m->peds[k];
+        Pedigree& P = c->peds[k];
+        P.n_leaves = pd.n_leaves; P.n_branches = pd.n_branches; P.L = pd.n_loci; P.n_fam = pd.n_fam; P.n_mult = pd.n_mult; P.n_asc = pd.n_asc;
+        P.R = pd.n_loci + 2 * pd.n_asc;
+        P.R_pad = round_up_i(std::max(P.R, 1), TM);
+        P.n_tiles = P.R_pad / TM;
+        P.asc_offset = asc_off;
+        asc_off += pd.n_asc;
+        if (int rc = compile_schedule(pd, fk[k], rk[k], P)) return cleanup_fail(rc);
+        c->max_slots = std::max(c->max_slots, P.n_slots);
+        c->max_tiles = std::max(c->max_tiles, P.n_tiles);
+        c->max_asc2 = std::max(c->max_asc2, 2 * P.n_asc);
+
+        // multipliers per row (real rows then ascertainment pairs, np.repeat(..., 2): ascertainment.py:205-206)
+        std::vector<double> mult((size_t)std::max(pd.n_mult, 1) * P.R_pad, 0.0);
+        for (int mc = 0; mc < pd.n_mult; ++mc) {
+            for (int r = 0; r < pd.n_loci; ++r) mult[(size_t)mc * P.R_pad + r] = pd.row_mult[(size_t)mc * pd.n_loci + r];
+            for (int u = 0; u < pd.n_asc; ++u) {
+                mult[(size_t)mc * P.R_pad + pd.n_loci + 2 * u] = pd.asc_mult[(size_t)mc * pd.n_asc + u];
+                mult[(size_t)mc * P.R_pad + pd.n_loci + 2 * u + 1] = pd.asc_mult[(size_t)mc * pd.n_asc + u];
+            }
+        }
+        CUDA_TRY_C(cudaMemcpyAsync(P.mult, mult.data(), mult.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY_C(cudaMemcpyAsync(P.fam_asc, pd.fam_asc, (size_t)pd.n_fam * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_TRY_C(cudaMemcpyAsync(P.fam_count, pd.fam_count, (size_t)pd.n_fam * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY_C(cudaMemcpyAsync(P.fam_lgamma, pd.fam_lgamma, (size_t)pd.n_fam * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY_C(cudaMemcpyAsync(P.ops, P.ops_h.data(), (size_t)P.n_ops * sizeof(TreeOp), cudaMemcpyHostToDevice, st));
+
+        // emissions: transient inputs at the arena tail
+        Bump tail = bump;
+        const size_t cells = (size_t)pd.n_loci * pd.n_leaves;
+        double* d_counts = tail.take<double>(std::max<size_t>(cells, 1));
+        double* d_cov = tail.take<double>(std::max<size_t>(cells, 1));
+        double* d_logp = tail.take<double>(F);
+        double* d_log1mp = tail.take<double>(F);
+        int8_t* d_cls = tail.take<int8_t>(F);
+        int8_t* d_e0 = tail.take<int8_t>(F);
+        int8_t* d_eN = tail.take<int8_t>(F);
+        if (!tail.ok()) return cleanup_fail(fail(MOPE_E_NOMEM, "arena too small for the emission inputs"));
+        if (cells) {
+            CUDA_TRY_C(cudaMemcpyAsync(d_counts, pd.counts, cells * sizeof(double), cudaMemcpyHostToDevice, st));
+            CUDA_TRY_C(cudaMemcpyAsync(d_cov, pd.coverage, cells * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        CUDA_TRY_C(cudaMemcpyAsync(d_logp, logp.data(), F * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY_C(cudaMemcpyAsync(d_log1mp, log1mp.data(), F * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY_C(cudaMemcpyAsync(d_cls, pclass.data(), F, cudaMemcpyHostToDevice, st));
+        CUDA_TRY_C(cudaMemcpyAsync(d_e0, e0.data(), F, cudaMemcpyHostToDevice, st));
+        CUDA_TRY_C(cudaMemcpyAsync(d_eN, eN.data(), F, cudaMemcpyHostToDevice, st));
+        EmissionParams ep{};
+        ep.counts = d_counts; ep.coverage = d_cov; ep.logp = d_logp; ep.log1mp = d_log1mp; ep.pclass = d_cls;
+        ep.asc_e0 = d_e0; ep.asc_eN = d_eN; ep.E = P.E;
+        ep.L = P.L; ep.S = P.n_leaves; ep.R = P.R; ep.R_pad = P.R_pad; ep.F = F; ep.Fp = Fp;
+        const long long warps = (long long)P.n_leaves * P.R_pad;
+        const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+        emission_kernel<<<grid, 256, 0, st>>>(ep);
+        CUDA_TRY_C(cudaGetLastError());
+        c->launches++;
+        CUDA_TRY_C(cudaStreamSynchronize(st));  // host vectors above go out of scope per pedigree
+    }
+    c->asc_total = asc_off;
+    CUDA_TRY_C(cudaStreamSynchronize(st));
+#undef CUDA_TRY_C
+    *out = c;
+    return 0;
+}
+
+int mope_b200_destroy(mope_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->opbuf) cudaFree(c->opbuf);
+    delete c;
+    return 0;
+}
+
+int mope_b200_workspace_bytes(const mope_ctx* c, int W, size_t* out_min, size_t* out_full) {
+    if (!c || W < 1) return fail(MOPE_E_INVALID, "workspace_bytes: bad argument");
+    const size_t fixed = fixed_ws_bytes(c, W);
+    const size_t pw = per_walker_bytes(c, max_blocks_per_walker(c));
+    if (out_min) *out_min = fixed + pw + 8192;
+    if (out_full) *out_full = fixed + (size_t)W * pw + 8192;
+    return 0;
+}
+
+int mope_b200_eval(mope_ctx* c, const double* params, const double* stat, int W, void* workspace, size_t ws_bytes,
+                   void* stream, double* out_ll, int32_t* out_status, double* out_root_ll, double* out_log_asc) {
+    return eval_impl(c, params, stat, false, W, workspace, ws_bytes, (cudaStream_t)stream, out_ll, false, out_status, out_root_ll, out_log_asc);
+}
+
+int mope_b200_eval_device(mope_ctx* c, const double* params_host, const double* stat_dev, int W, void* workspace,
+                          size_t ws_bytes, void* stream, double* out_ll_dev, int32_t* out_status_host) {
+    return eval_impl(c, params_host, stat_dev, true, W, workspace, ws_bytes, (cudaStream_t)stream, out_ll_dev, true, out_status_host, nullptr, nullptr);
+}
+
+int64_t mope_b200_launch_count(const mope_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// operator-level entry points
+// ------------------------------------------------------------------------------------------------
+int mope_b200_transition_matrix(mope_ctx* c, int bottleneck, double x, double scaled_mut, void* stream, double* out_P,
+                                int32_t* out_status) {
+    if (!c || !out_P || !out_status) return fail(MOPE_E_INVALID, "transition_matrix: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    WalkerPlan wp;
+    wp.status = status_fixed(c, bottleneck != 0, x, scaled_mut);
+    *out_status = wp.status;
+    if (wp.status) return 0;
+    PlanOut po;
+    size_t b0 = 0;
+    emit_fixed_job(c, bottleneck != 0, x, scaled_mut, b0, po);
+    const int F = c->F, Fp = c->Fp;
+    const size_t blk = (size_t)Fp * Fp + Fp;
+    const size_t need = align_up(sizeof(InterpJob), 256) + blk * sizeof(double) + (size_t)F * F * sizeof(double) + 1024;
+    if (ensure_opbuf(c, need)) return MOPE_E_CUDA;
+    InterpJob* d_job = reinterpret_cast<InterpJob*>(c->opbuf);
+    double* d_blk = reinterpret_cast<double*>(c->opbuf + align_up(sizeof(InterpJob), 256));
+    double* d_out = d_blk + blk;
+    CUDA_TRY(cudaMemcpyAsync(d_job, po.jobs.data(), sizeof(InterpJob), cudaMemcpyHostToDevice, st));
+    const int wpb = 8;
+    interp_kernel<<<(Fp + wpb - 1) / wpb, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_job, 1, c->tables, d_blk, F, Fp);
+    CUDA_TRY(cudaGetLastError());
+    const long long total = (long long)F * F;
+    unpad_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_blk, d_out, F, F, Fp);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(out_P, d_out, (size_t)F * F * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mope_b200_leaf_likelihoods(mope_ctx* c, const double* counts, const double* coverage, int L, int S, const double* freqs,
+                               int F, double min_phred, void* stream, double* out) {
+    if (!c || !counts || !coverage || !freqs || !out || L < 0 || S < 1 || F < 1) return fail(MOPE_E_INVALID, "leaf_likelihoods: bad argument");
+    if (L == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Fp = round_up_i(F, 16);
+    const int R_pad = round_up_i(L, TM);
+    std::vector<double> logp(F), log1mp(F);
+    std::vector<int8_t> pclass(F), zeros(F, 0);
+    const double perr = (min_phred != -1.0) ? std::pow(10.0, -1.0 * min_phred / 10.0) : 0.0;
+    for (int f = 0; f < F; ++f) {
+        const double p = (1.0 - perr) * freqs[f] + (perr / 3.0) * (1.0 - freqs[f]);
+        pclass[f] = (p == 0.0) ? 1 : ((p == 1.0) ? 2 : 0);
+        logp[f] = (p > 0.0) ? std::log(p) : 0.0;
+        log1mp[f] = (p < 1.0) ? std::log1p(-p) : 0.0;
+    }
+    Bump b;
+    b.dry = true;
+    auto carve = [&](Bump& bb, double*& dc, double*& dn, double*& dl, double*& dl1, int8_t*& cls, int8_t*& z, double*& E, double*& o) {
+        dc = bb.take<double>((size_t)L * S); dn = bb.take<double>((size_t)L * S);
+        dl = bb.take<double>(F); dl1 = bb.take<double>(F); cls = bb.take<int8_t>(F); z = bb.take<int8_t>(F);
+        E = bb.take<double>((size_t)S * R_pad * Fp); o = bb.take<double>((size_t)L * S * F);
+    };
+    double *dc, *dn, *dl, *dl1, *E, *o; int8_t *cls, *z;
+    carve(b, dc, dn, dl, dl1, cls, z, E, o);
+    if (ensure_opbuf(c, b.used + 256)) return MOPE_E_CUDA;
+    Bump r;
+    r.base = c->opbuf; r.cap = c->opbuf_cap;
+    carve(r, dc, dn, dl, dl1, cls, z, E, o);
+    CUDA_TRY(cudaMemcpyAsync(dc, counts, (size_t)L * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dn, coverage, (size_t)L * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dl, logp.data(), F * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dl1, log1mp.data(), F * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(cls, pclass.data(), F, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(z, zeros.data(), F, cudaMemcpyHostToDevice, st));
+    EmissionParams ep{};
+    ep.counts = dc; ep.coverage = dn; ep.logp = dl; ep.log1mp = dl1; ep.pclass = cls; ep.asc_e0 = z; ep.asc_eN = z; ep.E = E;
+    ep.L = L; ep.S = S; ep.R = L; ep.R_pad = R_pad; ep.F = F; ep.Fp = Fp;
+    const long long warps = (long long)S * R_pad;
+    emission_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(ep);
+    CUDA_TRY(cudaGetLastError());
+    // [S][R_pad][Fp] -> [L][S][F]
+    const long long total = (long long)L * S * F;
+    emission_to_lsf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(E, o, L, S, F, Fp, R_pad);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(out, o, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* parent, int n_rows, const double* lengths,
+                            double scaled_mut, void* stream, int32_t* out_status) {
+    if (!c || !child || !parent || !lengths || !out_status || n_rows < 0 || kind < 0 || kind > 2)
+        return fail(MOPE_E_INVALID, "branch_update: bad argument");
+    *out_status = 0;
+    if (n_rows == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = c->F, Fp = c->Fp;
+    const int R_pad = round_up_i(n_rows, TM);
+    const size_t blk = (size_t)Fp * Fp + Fp;
+
+    // plan
+    PlanOut po;
+    RateInfo ri{};
+    int32_t status = 0;
+    size_t b0 = 0;
+    if (kind == 1) {
+        double mn = lengths[0], mx = lengths[0];
+        for (int r = 1; r < n_rows; ++r) { mn = std::min(mn, lengths[r]); mx = std::max(mx, lengths[r]); }
+        // lengths enter as multipliers of a unit branch length (mult * 1.0 is exact)
+        status = status_rate(c, mn, mx, 1.0, scaled_mut);
+        if (!status) { emit_rate_jobs(c, mn, mx, 1.0, scaled_mut, b0, po); ri = po.rate[0]; }
+    } else {
+        status = status_fixed(c, kind == 2, lengths[0], scaled_mut);
+        if (!status) emit_fixed_job(c, kind == 2, lengths[0], scaled_mut, b0, po);
+    }
+    *out_status = status;
+    if (status) return 0;
+    const size_t n_blocks = po.jobs.size();
+
+    Bump b;
+    b.dry = true;
+    struct Ptrs { InterpJob* jobs; int64_t* mo; RateInfo* rate; double *pool, *E, *Y, *par, *mult, *raw; TreeOp* op; } P{};
+    auto carve = [&](Bump& bb) {
+        P.jobs = bb.take<InterpJob>(std::max<size_t>(n_blocks, 1));
+        P.mo = bb.take<int64_t>(1);
+        P.rate = bb.take<RateInfo>(1);
+        P.op = bb.take<TreeOp>(1);
+        P.pool = bb.take<double>(std::max<size_t>(n_blocks, 1) * blk);
+        P.E = bb.take<double>((size_t)R_pad * Fp);
+        P.Y = bb.take<double>((size_t)R_pad * Fp);
+        P.par = bb.take<double>((size_t)n_rows * F);
+        P.raw = bb.take<double>((size_t)n_rows * F);
+        P.mult = bb.take<double>(R_pad);
+    };
+    carve(b);
+    if (ensure_opbuf(c, b.used + 256)) return MOPE_E_CUDA;
+    Bump r;
+    r.base = c->opbuf; r.cap = c->opbuf_cap;
+    carve(r);
+
+    if (n_blocks) CUDA_TRY(cudaMemcpyAsync(P.jobs, po.jobs.data(), n_blocks * sizeof(InterpJob), cudaMemcpyHostToDevice, st));
+    const int64_t zero_off = 0;
+    CUDA_TRY(cudaMemcpyAsync(P.mo, &zero_off, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(P.rate, &ri, sizeof(RateInfo), cudaMemcpyHostToDevice, st));
+    TreeOp op{};
+    op.src_kind = 0; op.src = 0; op.dst = -1; op.first = 1; op.kind = (kind == 1) ? 1 : 0; op.key = 0; op.mult = 0; op.last = 0;
+    CUDA_TRY(cudaMemcpyAsync(P.op, &op, sizeof(TreeOp), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(P.raw, child, (size_t)n_rows * F * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(P.par, parent, (size_t)n_rows * F * sizeof(double), cudaMemcpyHostToDevice, st));
+    {
+        std::vector<double> mu(R_pad, 0.0);
+        if (kind == 1) for (int i = 0; i < n_rows; ++i) mu[i] = lengths[i];
+        CUDA_TRY(cudaMemcpyAsync(P.mult, mu.data(), (size_t)R_pad * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    const long long tot = (long long)R_pad * Fp;
+    pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P.raw, P.E, n_rows, F, Fp, R_pad);
+    CUDA_TRY(cudaGetLastError());
+    if (n_blocks) {
+        const int wpb = 8;
+        const long long rows = (long long)n_blocks * Fp;
+        interp_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(P.jobs, (int)n_blocks, c->tables, P.pool, F, Fp);
+        CUDA_TRY(cudaGetLastError());
+    }
+    TreeParams tp{};
+    tp.E = P.E; tp.E_leaf_stride = (int64_t)R_pad * Fp; tp.scratch = P.Y /*unused*/; tp.ops = P.op; tp.n_ops = 1; tp.n_slots = 0;
+    tp.R = n_rows; tp.L = n_rows; tp.R_pad = R_pad; tp.Fp = Fp; tp.F = F; tp.NT = c->NT; tp.n_tiles = R_pad / TM; tp.W = 1;
+    tp.pool = P.pool; tp.mat_off = P.mo; tp.n_mat = 1; tp.n_rate = 1; tp.rate = P.rate; tp.mult = P.mult; tp.gens = c->gens_dev;
+    tp.n_gens = c->n_gens; tp.Npop = c->N; tp.stat = nullptr; tp.tile_ll = nullptr; tp.asc_dot = nullptr; tp.Yout = P.Y;
+    if (launch_tree(c, tp, std::min(tp.n_tiles, c->num_sms), st)) return MOPE_E_CUDA;
+    const long long tot2 = (long long)n_rows * F;
+    mul_unpad_kernel<<<(unsigned)((tot2 + 255) / 256), 256, 0, st>>>(P.Y, P.par, n_rows, F, Fp);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 3;
+    CUDA_TRY(cudaMemcpyAsync(parent, P.par, (size_t)n_rows * F * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mope_b200_non_asc_probs(mope_ctx* c, const double* qualities, const int64_t* qual_off, int n_sets, const double* freqs, int F,
+                            double min_freq, void* stream, double* out) {
+    if (!c || !qualities || !qual_off || !freqs || !out || n_sets < 0 || F < 1) return fail(MOPE_E_INVALID, "non_asc_probs: bad argument");
+    if (n_sets == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nq = qual_off[n_sets];
+    for (int s = 0; s < n_sets; ++s) {
+        if (qual_off[s + 1] < qual_off[s]) return fail(MOPE_E_INVALID, "non_asc_probs: offsets not ascending");
+        const int K = (int)std::ceil(min_freq * (double)(qual_off[s + 1] - qual_off[s]));
+        if (K > PB_MAXK) return fail(MOPE_E_INVALID, "non_asc_probs: ceil(min_freq*nreads) = %d exceeds the supported %d", K, PB_MAXK);
+    }
+    Bump b;
+    b.dry = true;
+    double *dq, *df, *dout; int64_t* doff; int* dflag;
+    auto carve = [&](Bump& bb) {
+        dq = bb.take<double>(std::max<int64_t>(nq, 1)); doff = bb.take<int64_t>(n_sets + 1); df = bb.take<double>(F);
+        dout = bb.take<double>((size_t)n_sets * F); dflag = bb.take<int>(1);
+    };
+    carve(b);
+    if (ensure_opbuf(c, b.used + 256)) return MOPE_E_CUDA;
+    Bump r;
+    r.base = c->opbuf; r.cap = c->opbuf_cap;
+    carve(r);
+    if (nq) CUDA_TRY(cudaMemcpyAsync(dq, qualities, (size_t)nq * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(doff, qual_off, (size_t)(n_sets + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(df, freqs, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(dflag, 0, sizeof(int), st));
+    pb_kernel<<<n_sets, 128, 0, st>>>(dq, doff, df, F, min_freq, dout, dflag);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)n_sets * F * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

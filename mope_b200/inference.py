@@ -1,0 +1,304 @@
+"""Host-side mirror of the reference's inference API for the log-likelihood path.
+
+Same names, argument meaning and error behaviour as mope/inference.py for: the module-level trampolines
+`logl` / `logp` / `post_clone` reading the global `inf_data` (:45-60), `Inference(...)` (:263-738, count data,
+non-selection model), `Inference.loglike` (:770-910), `like_obj` (:766), `inf_bound_like_obj` (:1008-1015),
+`logprior` (:1055-1110), `log_posterior` (:1132-1161) and the prior box of `_get_likelihood_limits` (:154-258).
+The likelihood itself runs on the GPU through mope_b200.engine.Engine; the batched entry points
+(`loglike_batch`, `log_posterior_batch`) are what `GpuPool.map` uses so that one emcee half-step is one
+device call.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import model as _model
+from . import tables as _tables
+from .engine import Engine, OutOfTableError, status_message
+from .stationary import stationary_distribution_batch
+
+inf_data = None
+
+
+def logl(x):
+    global inf_data
+    return -1.0 * inf_data.inf_bound_like_obj(x)
+
+
+def logp(x):
+    global inf_data
+    return inf_data.logprior(x)
+
+
+def post_clone(x):
+    global inf_data
+    return inf_data.log_posterior(x)
+
+
+def _get_valid_start_from(sf_str):
+    for v in ("prior", "true", "map"):
+        if sf_str == v:
+            return v
+    warnings.warn("getting starting position from heuristic guess")
+    return "initguess"
+
+
+class Inference(object):
+    def __init__(self, data_files, tree_files, age_files, transitions_file, true_parameters=None, start_from="prior",
+                 data_are_freqs=False, genome_size=16569, bottleneck_file=None, poisson_like_penalty=1.0, min_freq=0.001,
+                 transition_copy=None, transition_buf=None, transition_shape=None, print_debug=False,
+                 log_unif_drift=False, inverse_bot_priors=False, post_is_prior=False, lower_drift_limit=1e-3,
+                 upper_drift_limit=3, min_phred_score=None, selection_model=False, device=0, workspace_bytes=None,
+                 _inputs_are_text=False):
+        if selection_model:
+            raise NotImplementedError("the selection model is outside the GPU log-likelihood path")
+        if data_are_freqs:
+            raise NotImplementedError("frequency-format data (get_nearest_likelihoods_cython) is outside the GPU "
+                                      "log-likelihood path; use allele counts")
+        if true_parameters:
+            raise NotImplementedError("--true-parameters is not supported by the GPU path")
+        self.data_files, self.tree_files, self.age_files = list(data_files), list(tree_files), list(age_files)
+        if not (len(self.data_files) == len(self.tree_files) == len(self.age_files)) or not self.data_files:
+            raise ValueError("need one data file, one tree file and one ages file per pedigree type")
+        self.data_are_freqs = data_are_freqs
+        self.genome_size = genome_size
+        self.transitions_file = transitions_file
+        self.start_from = _get_valid_start_from(start_from)
+        self.bottleneck_file = bottleneck_file
+        self.poisson_like_penalty = poisson_like_penalty
+        self.min_freq = min_freq
+        self.print_debug = print_debug
+        self.log_unif_drift = log_unif_drift
+        self.inverse_bot_priors = inverse_bot_priors
+        self.post_is_prior = post_is_prior
+        self.lower_drift_limit = lower_drift_limit
+        self.upper_drift_limit = upper_drift_limit
+        self.min_phred_score = min_phred_score
+        self.selection_model = False
+        self.true_params = None
+        self.true_loglike = None
+
+        # tables (inference.py:741-763)
+        self.transition_data = _tables.load(transitions_file, bottleneck_file)
+        self.bottleneck_data = self.transition_data if self.transition_data.bot is not None else None
+        self.freqs = self.transition_data.get_bin_frequencies()
+        self.num_freqs = self.freqs.shape[0]
+        self.breaks = self.transition_data.get_breaks()
+        self.transition_N = self.transition_data.get_N()
+
+        # pedigrees
+        self.tree_strings, self.peds = [], []
+        for dat_fn, tree_fn, age_fn in zip(self.data_files, self.tree_files, self.age_files):
+            if _inputs_are_text:
+                tree_str = tree_fn.strip()
+            else:
+                with open(tree_fn) as fin:
+                    tree_str = fin.read().strip()
+            self.tree_strings.append(tree_str)
+            datp = _model.read_table(dat_fn, _inputs_are_text)
+            agep = _model.read_table(age_fn, _inputs_are_text)
+            self.peds.append(_model.compile_pedigree(datp, tree_str, agep))
+
+        self.leaf_names = [p.leaf_names for p in self.peds]
+        self.branch_names = [p.branch_names for p in self.peds]
+        self.multiplierdict = [p.multiplier_of for p in self.peds]
+        self.varnamedict = [p.varname_of for p in self.peds]
+        self.multipliernames = [p.multipliernames for p in self.peds]
+        self.is_bottleneck = {}
+        for p in self.peds:
+            for v, b in p.bottleneck_of_var.items():
+                if v in self.is_bottleneck and self.is_bottleneck[v] != b:
+                    raise ValueError("nodes with the same variable name must have the same status as bottlenecks in all trees")
+                self.is_bottleneck[v] = b
+        self.varnames = sorted(self.is_bottleneck.keys())
+        self.num_varnames = len(self.varnames)
+        self.var_indices = {v: i for i, v in enumerate(self.varnames)}
+        self.num_branches = [len(b) for b in self.branch_names]
+        self.branch_indices = [{br: i for i, br in enumerate(b)} for b in self.branch_names]
+        self.leaf_indices = [{br: i for i, br in enumerate(b)} for b in self.leaf_names]
+        nv = self.num_varnames
+        self.translate_indices = []
+        for p in self.peds:
+            li = [self.var_indices[p.varname_of[b]] for b in p.branch_names]
+            self.translate_indices.append(np.array(li + [nv + i for i in li] + [2 * nv, 2 * nv + 1], dtype=np.int32))
+        self.asc_ages = [p.ages for p in self.peds]
+        self.num_asc_combs = [p.n_fam for p in self.peds]
+        self.num_loci = [p.num_loci for p in self.peds]
+        if any(self.is_bottleneck.values()) and self.bottleneck_data is None:
+            # the reference raises at the first evaluation (likelihoods.py:381-382)
+            warnings.warn("tree has bottleneck branches but no bottleneck tables were given")
+
+        self.min_mults, self.max_mults = self.get_min_max_mults()
+        self.header = "\t".join(["ll"] + [v + "_l" for v in self.varnames] + [v + "_m" for v in self.varnames]
+                                + ["log10ab", "log10polyprob"])
+        self.lower, self.upper, self.ndim = self._get_likelihood_limits()
+
+        self.engine = Engine(self.transition_data, self.peds, [self.var_indices] * len(self.peds), nv, min_phred_score,
+                             min_freq, genome_size, poisson_like_penalty, device=device, workspace_bytes=workspace_bytes)
+
+    # ------------------------------------------------------------------------------------------
+    def get_min_max_mults(self):
+        """inference.py:1018-1052."""
+        mins = {v: [] for v in self.varnames}
+        maxes = {v: [] for v in self.varnames}
+        for p in self.peds:
+            for br in p.branch_names:
+                v, m = p.varname_of[br], p.multiplier_of[br]
+                if m:
+                    vals = p.ages[m].values
+                    mins[v].append(np.nanmin(vals))
+                    maxes[v].append(np.nanmax(vals))
+                else:
+                    mins[v].append(1)
+                    maxes[v].append(1)
+        return (np.array([min(mins[v]) for v in self.varnames]), np.array([max(maxes[v]) for v in self.varnames]))
+
+    def _get_likelihood_limits(self):
+        """inference.py:154-258, non-selection branch."""
+        nv = self.num_varnames
+        td = self.transition_data
+        min_allowed_len = 0.1 * max(td.get_min_coal_time(), self.lower_drift_limit)
+        max_allowed_len = min(td.get_max_coal_time(), self.upper_drift_limit)
+        lower_len = min_allowed_len / self.min_mults
+        upper_len = max_allowed_len / self.max_mults
+        isb = np.array([self.is_bottleneck[v] for v in self.varnames], dtype=bool)
+        self.is_bottleneck_arr = isb
+        lower_len[isb] = 2
+        upper_len[isb] = 500
+        lower_len, upper_len = np.log10(lower_len), np.log10(upper_len)
+        min_mut = max(-8, np.log10(td.get_min_mutsel_rate()))
+        max_mut = min(-1, np.log10(td.get_max_mutsel_rate()))
+        lower = np.concatenate((lower_len, np.repeat(min_mut, nv), (-9, -9)))
+        upper = np.concatenate((upper_len, np.repeat(max_mut, nv), (0, 0)))
+        return lower, upper, 2 * nv + 2
+
+    # ------------------------------------------------------------------------------------------
+    # likelihood
+    # ------------------------------------------------------------------------------------------
+    def stationary_distributions(self, X: np.ndarray) -> np.ndarray:
+        ab = 10 ** X[:, -2]
+        pp = 10 ** X[:, -1]
+        return stationary_distribution_batch(self.breaks, self.transition_N, ab, pp)
+
+    def loglike_batch(self, X, raise_on_error: bool = True, return_status: bool = False):
+        """Inference.loglike for every row of X [W, ndim] in one device call."""
+        X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
+        if X.shape[1] != self.ndim:
+            raise ValueError("expected parameter vectors of length {}".format(self.ndim))
+        stat = self.stationary_distributions(X)
+        ll, status = self.engine.loglike(X, stat)
+        if raise_on_error and status.any():
+            w = int(np.nonzero(status)[0][0])
+            raise OutOfTableError("walker {}: {}".format(w, status_message(int(status[w]))))
+        return (ll, status) if return_status else ll
+
+    def loglike_components(self, X):
+        X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
+        stat = self.stationary_distributions(X)
+        ll, status, root, lasc = self.engine.loglike(X, stat, want_components=True)
+        out, o = [], 0
+        for k, p in enumerate(self.peds):
+            u = lasc[:, o:o + p.n_asc]
+            o += p.n_asc
+            out.append(dict(root_ll=root[:, k], log_asc=u[:, p.fam_asc]))
+        return ll, status, out
+
+    def loglike(self, orig_params):
+        return float(self.loglike_batch(np.asarray(orig_params, dtype=np.float64)[None, :])[0])
+
+    def like_obj(self, varparams):
+        return -self.loglike(varparams)
+
+    def inf_bound_like_obj(self, x):
+        if self.print_debug and np.any(x < self.lower):
+            print("inf:", x)
+            return np.inf
+        if self.print_debug and np.any(x > self.upper):
+            print("inf:", x)
+            return np.inf
+        return self.like_obj(x)
+
+    # ------------------------------------------------------------------------------------------
+    # prior / posterior
+    # ------------------------------------------------------------------------------------------
+    def logprior(self, x):
+        """inference.py:1055-1110.  (The reference's uniform-drift branch cannot run as written: it subtracts a
+        length-ndim vector from the length-n_var drift part, :1079-1080; the drift slice is used here.)"""
+        x = np.asarray(x, dtype=np.float64)
+        nv = self.num_varnames
+        if np.any(x < self.lower):
+            return -np.inf
+        if np.any(x > self.upper):
+            return -np.inf
+        if self.log_unif_drift:
+            return np.sum(np.log(1.0 / (self.upper - self.lower)))
+        u, l = self.upper, self.lower
+        drift_x = x[:nv]
+        drift_part_arr = drift_x * 2.3025850929940459 + 0.834032445247956 - np.log(10 ** u[:nv] - 10 ** l[:nv])
+        mut_part = np.sum(np.log(1.0 / (u[nv:2 * nv] - l[nv:2 * nv])))
+        root_part = np.sum(np.log(1.0 / (u[2 * nv:] - l[2 * nv:])))
+        if self.inverse_bot_priors:
+            isb = self.is_bottleneck_arr
+            l_b, u_b, x_b = l[:nv][isb], u[:nv][isb], drift_x[isb]
+            drift_part_arr[isb] = np.log(l_b) + np.log(u_b) + -np.log(u_b - l_b) - 2 * np.log(x_b)
+        return np.sum(drift_part_arr) + mut_part + root_part
+
+    def fold(self, X):
+        """Sign folding of log_posterior (inference.py:1140-1145)."""
+        X = np.array(X, dtype=np.float64, copy=True)
+        nv = self.num_varnames
+        X[..., nv:2 * nv] = -1.0 * np.abs(X[..., nv:2 * nv])
+        X[..., -2:] = -np.abs(X[..., -2:])
+        return X
+
+    def log_posterior_batch(self, X):
+        X = self.fold(np.atleast_2d(np.asarray(X, dtype=np.float64)))
+        pr = np.array([self.logprior(x) for x in X])
+        v = pr.copy()
+        if not self.post_is_prior:
+            ok = np.isfinite(pr)
+            like = np.full(X.shape[0], -np.inf)
+            if ok.any():
+                like[ok] = self.loglike_batch(X[ok])
+            v = pr + like
+        v[np.isnan(v)] = -np.inf
+        return v
+
+    def log_posterior(self, x):
+        v = float(self.log_posterior_batch(np.asarray(x, dtype=np.float64)[None, :])[0])
+        if self.print_debug:
+            print("@@", v, self.logprior(self.fold(x)))
+        return v
+
+    def close(self):
+        self.engine.close()
+
+
+class GpuPool(object):
+    """Drop-in for the `pool` argument of Inference.run_mcmc / emcee.EnsembleSampler (inference.py:1322-1356):
+    `map(func, iterable)` recognises the module-level trampolines by identity and evaluates the whole iterable
+    in one device call; anything else is mapped serially."""
+
+    def __init__(self, inf: Inference):
+        self.inf = inf
+
+    def map(self, func, iterable):
+        xs = [np.asarray(x, dtype=np.float64) for x in iterable]
+        if not xs:
+            return []
+        name = getattr(func, "__name__", None)
+        mod = getattr(func, "__module__", "")
+        if mod.endswith("inference") and name in ("post_clone", "logl", "logp"):
+            X = np.stack(xs)
+            if name == "post_clone":
+                return list(self.inf.log_posterior_batch(X))
+            if name == "logp":
+                return [self.inf.logprior(x) for x in X]
+            return list(self.inf.loglike_batch(X))  # logl = -inf_bound_like_obj = +loglike
+        return [func(x) for x in xs]
+
+    def close(self):
+        pass

@@ -1,0 +1,157 @@
+"""Host model compiler: data + tree + ages -> flat arrays for the C ABI.
+
+Mirrors the init-time logic of the reference's Inference.__init__ (mope/inference.py:331-352 file reading,
+:385-451 branch/variable index maps, :456-459 removal of fixed loci, :504-525 family counts and multiplier
+columns) and flattens the result into the mope_pedigree_desc layout of include/mope_b200.h.
+"""
+from __future__ import annotations
+
+import io
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+from scipy.special import gammaln
+
+from . import newick
+
+
+def read_table(path_or_text, is_text: bool = False) -> pd.DataFrame:
+    """TSV reader with the reference's options (inference.py:332-333, :510)."""
+    src = io.StringIO(path_or_text) if is_text else path_or_text
+    return pd.read_csv(src, sep="\t", comment="#", na_values=["NA"], header=0)
+
+
+def is_fixed(X: np.ndarray, n: np.ndarray) -> np.ndarray:
+    """mope/data.py:219-228 for count data."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ps = X / n
+    freqsums = np.nansum(ps, axis=1).astype(np.float64)
+    return np.isclose(freqsums, X.shape[1]) | (freqsums == 0.0)
+
+
+@dataclass
+class PedigreeModel:
+    tree: newick.Node
+    leaf_names: List[str]
+    branch_names: List[str]
+    varname_of: Dict[str, str]
+    multiplier_of: Dict[str, Optional[str]]
+    bottleneck_of_var: Dict[str, bool]
+    multipliernames: List[str]
+    # data after init-time processing
+    counts: np.ndarray        # [L, S]
+    coverage: np.ndarray      # [L, S]
+    family: np.ndarray        # [L]
+    ages: pd.DataFrame        # the ages table with a 'count' column (asc_ages in the reference)
+    row_mult: np.ndarray      # [M, L]
+    asc_mult: np.ndarray      # [M, U]
+    fam_asc: np.ndarray       # [n_fam] int32
+    fam_count: np.ndarray     # [n_fam] float64
+    # schedule
+    br_parent: np.ndarray
+    br_leaf: np.ndarray
+    br_mult: np.ndarray
+    br_bottleneck: np.ndarray
+
+    @property
+    def num_loci(self) -> int:
+        return int(self.counts.shape[0])
+
+    @property
+    def n_fam(self) -> int:
+        return int(self.fam_asc.shape[0])
+
+    @property
+    def n_asc(self) -> int:
+        return int(self.asc_mult.shape[1])
+
+
+def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame) -> PedigreeModel:
+    tree = newick.loads(tree_str)[0]
+    nodes = [nd for nd in tree.postorder() if nd is not tree]
+    leaf_names = [nd.name for nd in nodes if nd.is_leaf]
+    branch_names = [nd.name for nd in nodes]
+    if len(set(branch_names)) != len(branch_names):
+        raise ValueError("node names must be unique in each tree")
+    for nd in nodes:
+        if nd.varname is None:
+            raise ValueError("every non-root node needs a length parameter name (node {})".format(nd.name))
+    varname_of = {nd.name: nd.varname for nd in nodes}
+    multiplier_of = {nd.name: nd.multipliername for nd in nodes}
+    bott = {}
+    for nd in nodes:
+        if nd.varname in bott and bott[nd.varname] != nd.is_bottleneck:
+            raise ValueError("nodes with the same variable name must have the same status as bottlenecks in all trees")
+        bott[nd.varname] = nd.is_bottleneck
+    multipliernames = sorted({m for m in multiplier_of.values() if m is not None})
+
+    data = data.copy()
+    for col in data.columns:
+        if col not in ("family", "position"):
+            data[col] = data[col].astype(np.float64)
+    missing = [c for c in leaf_names + [l + "_n" for l in leaf_names] if c not in data.columns]
+    if missing:
+        raise ValueError("data file lacks columns for tree leaves: {}".format(missing))
+    X = data.loc[:, leaf_names].values.astype(np.float64)
+    n = data.loc[:, [l + "_n" for l in leaf_names]].values.astype(np.float64)
+    keep = ~is_fixed(X, n)
+    data = data.loc[keep, :].reset_index(drop=True)
+    X, n = np.ascontiguousarray(X[keep]), np.ascontiguousarray(n[keep])
+    family = data["family"].values
+
+    ages = ages.copy()
+    fam_ids = ages["family"].values
+    counts = np.array([(family == f).sum() for f in fam_ids], dtype=np.int64)
+    ages["count"] = counts
+    for m in multipliernames:
+        if m not in ages.columns:
+            raise ValueError("multiplier column {} not found in the ages file".format(m))
+    M, L = len(multipliernames), X.shape[0]
+    row_mult = np.zeros((M, L))
+    first_row_of = {}
+    for i, f in enumerate(fam_ids):
+        first_row_of.setdefault(f, i)
+    for j, m in enumerate(multipliernames):
+        if m in data.columns:
+            row_mult[j] = data[m].values.astype(np.float64)
+        else:
+            col = ages[m].values.astype(np.float64)
+            row_mult[j] = [col[first_row_of[f]] for f in family]   # .iloc[0] of the matching rows
+    # distinct ascertainment row pairs: the pruning of the pseudo-rows depends on the family only through its
+    # multiplier values, so equal multiplier tuples share one pair (bit-identical results, fewer rows)
+    fam_mult = np.zeros((M, len(fam_ids)))
+    for j, m in enumerate(multipliernames):
+        fam_mult[j] = ages[m].values.astype(np.float64)
+    if M == 0:
+        asc_mult = np.zeros((0, 1))
+        fam_asc = np.zeros(len(fam_ids), dtype=np.int32)
+    else:
+        keys, fam_asc_l, uniq = {}, [], []
+        for i in range(len(fam_ids)):
+            k = fam_mult[:, i].tobytes()
+            if k not in keys:
+                keys[k] = len(uniq)
+                uniq.append(fam_mult[:, i])
+            fam_asc_l.append(keys[k])
+        asc_mult = np.ascontiguousarray(np.array(uniq).T)
+        fam_asc = np.array(fam_asc_l, dtype=np.int32)
+
+    idx_of = {id(nd): i for i, nd in enumerate(nodes)}
+    idx_of[id(tree)] = len(nodes)
+    br_parent = np.array([idx_of[id(nd.parent)] for nd in nodes], dtype=np.int32)
+    br_leaf = np.array([leaf_names.index(nd.name) if nd.is_leaf else -1 for nd in nodes], dtype=np.int32)
+    br_mult = np.array([multipliernames.index(nd.multipliername) if nd.multipliername is not None else -1 for nd in nodes],
+                       dtype=np.int32)
+    br_bott = np.array([1 if nd.is_bottleneck else 0 for nd in nodes], dtype=np.int32)
+    return PedigreeModel(tree=tree, leaf_names=leaf_names, branch_names=branch_names, varname_of=varname_of,
+                         multiplier_of=multiplier_of, bottleneck_of_var=bott, multipliernames=multipliernames,
+                         counts=X, coverage=n, family=family, ages=ages, row_mult=np.ascontiguousarray(row_mult),
+                         asc_mult=asc_mult, fam_asc=fam_asc, fam_count=counts.astype(np.float64),
+                         br_parent=br_parent, br_leaf=br_leaf, br_mult=br_mult, br_bottleneck=br_bott)
+
+
+def fam_lgamma(counts: np.ndarray) -> np.ndarray:
+    """gammaln(count + 1) of inference.py:1126."""
+    return np.ascontiguousarray(gammaln(np.asarray(counts, dtype=np.float64) + 1), dtype=np.float64)

@@ -1,0 +1,145 @@
+"""Transition tables: the in-memory state of the reference's TransitionData(memory=True) /
+TransitionDataBottleneck(memory=True) (mope/transition_data_2d.py:78-111,
+mope/transition_data_bottleneck.py:74-96) as dense sorted grids."""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+
+@dataclass
+class TransitionTables:
+    drift: np.ndarray            # [G, U, F, F]
+    gens: np.ndarray             # [G] float64 ascending
+    us: np.ndarray               # [U] float64 ascending
+    N: float
+    freqs: np.ndarray            # [F]
+    breaks: np.ndarray           # [F] int
+    bot: Optional[np.ndarray] = None      # [NB, UB, F, F]
+    nbs: Optional[np.ndarray] = None      # [NB]
+    bot_us: Optional[np.ndarray] = None   # [UB]
+
+    def __post_init__(self):
+        self.drift = np.ascontiguousarray(self.drift, dtype=np.float64)
+        self.gens = np.ascontiguousarray(self.gens, dtype=np.float64)
+        self.us = np.ascontiguousarray(self.us, dtype=np.float64)
+        self.freqs = np.ascontiguousarray(self.freqs, dtype=np.float64)
+        self.breaks = np.asarray(self.breaks)
+        if self.breaks.ndim == 0:
+            # tables written with --breaks unset store 0 here; the reference's root prior cannot use them
+            # (np.add.reduceat raises, likelihoods.py:59)
+            raise ValueError("un-binned transition tables (breaks=0) cannot be used for inference")
+        self.N = float(self.N)
+        G, U, F, F2 = self.drift.shape
+        if F != F2 or self.gens.shape != (G,) or self.us.shape != (U,) or self.freqs.shape != (F,):
+            raise ValueError("inconsistent drift table shapes")
+        if np.any(np.diff(self.gens) <= 0) or np.any(np.diff(self.us) <= 0):
+            raise ValueError("grid axes must be strictly ascending")
+        if self.bot is not None:
+            self.bot = np.ascontiguousarray(self.bot, dtype=np.float64)
+            self.nbs = np.ascontiguousarray(self.nbs, dtype=np.float64)
+            self.bot_us = np.ascontiguousarray(self.bot_us, dtype=np.float64)
+            if self.bot.shape != (self.nbs.shape[0], self.bot_us.shape[0], F, F):
+                raise ValueError("inconsistent bottleneck table shapes")
+        # the clamp of _util.check_transition_matrix (mope/_util.pyx:140-143) is a no-op on blends of
+        # matrices whose entries lie in [0,1]; the device path relies on that for age-scaled branches
+        if self.drift.min() < 0.0 or self.drift.max() > 1.0:
+            raise ValueError("drift tables hold entries outside [0, 1]")
+
+    @property
+    def F(self) -> int:
+        return int(self.freqs.shape[0])
+
+    # reference accessors (transition_data_2d.py:330-356)
+    def get_bin_frequencies(self):
+        return self.freqs
+
+    def get_breaks(self):
+        return self.breaks
+
+    def get_N(self):
+        return self.N
+
+    def get_min_coal_time(self):
+        return self.gens.min() / self.N
+
+    def get_max_coal_time(self):
+        return self.gens.max() / self.N
+
+    def get_min_mutsel_rate(self):
+        return self.us.min() * 2 * self.N
+
+    def get_max_mutsel_rate(self):
+        return self.us.max() * 2 * self.N
+
+    def save(self, path: str) -> None:
+        d = dict(drift=self.drift, gens=self.gens, us=self.us, N=np.float64(self.N), freqs=self.freqs, breaks=self.breaks)
+        if self.bot is not None:
+            d.update(bot=self.bot, nbs=self.nbs, bot_us=self.bot_us)
+        np.savez(path, **d)
+
+
+def load_npz(path: str) -> TransitionTables:
+    z = np.load(path)
+    kw = dict(drift=z["drift"], gens=z["gens"], us=z["us"], N=float(z["N"]), freqs=z["freqs"], breaks=z["breaks"])
+    if "bot" in z.files:
+        kw.update(bot=z["bot"], nbs=z["nbs"], bot_us=z["bot_us"])
+    return TransitionTables(**kw)
+
+
+def _grid_from_h5(path: str, axis_attr: str, xkey: str = "u"):
+    """Read a mope master HDF5 file (datasets with attrs N, gen|Nb, u; file attrs frequencies, breaks)."""
+    import h5py  # gated: not part of this image; present wherever the reference runs
+
+    mats, N = {}, None
+    with h5py.File(path, "r") as f:
+        for name in f:
+            ds = f[name]
+            a = ds.attrs
+            if N is None:
+                N = a["N"]
+            elif a["N"] != N:
+                raise Exception("Found multiple population sizes in master file's datasets")
+            key = (float(a[axis_attr]), float(a[xkey]))
+            if key in mats:
+                raise Exception("Found duplicate grid point in matrices: {}".format(key))
+            mats[key] = np.array(ds[:, :], dtype=np.float64)
+        freqs = np.array(f.attrs["frequencies"])
+        breaks = np.array(f.attrs["breaks"])
+    ax = np.array(sorted({k[0] for k in mats}))
+    xs = np.array(sorted({k[1] for k in mats}))
+    missing = [(g, x) for g in ax for x in xs if (g, x) not in mats]
+    if missing:
+        raise ValueError("incomplete transition probability grid")
+    F = freqs.shape[0]
+    dense = np.empty((ax.shape[0], xs.shape[0], F, F))
+    for i, g in enumerate(ax):
+        for j, x in enumerate(xs):
+            dense[i, j] = mats[(g, x)]
+    return dense, ax, xs, float(N), freqs, breaks
+
+
+def load(transitions_file, bottleneck_file=None) -> TransitionTables:
+    """`transitions_file` / `bottleneck_file` as given to `mope run`: HDF5 master files, or one .npz
+    holding both grids (written by TransitionTables.save), or an already-built TransitionTables."""
+    if isinstance(transitions_file, TransitionTables):
+        return transitions_file
+    if str(transitions_file).endswith(".npz"):
+        tb = load_npz(transitions_file)
+        if bottleneck_file is not None and str(bottleneck_file).endswith(".npz") and \
+                os.path.abspath(bottleneck_file) != os.path.abspath(transitions_file):
+            zb = np.load(bottleneck_file)
+            tb.bot, tb.nbs, tb.bot_us = zb["bot"], zb["nbs"], zb["bot_us"]
+            tb.__post_init__()
+        elif bottleneck_file is None:
+            tb.bot = tb.nbs = tb.bot_us = None
+        return tb
+    drift, gens, us, N, freqs, breaks = _grid_from_h5(transitions_file, "gen")
+    kw = dict(drift=drift, gens=gens, us=us, N=N, freqs=freqs, breaks=breaks)
+    if bottleneck_file is not None:
+        bot, nbs, bus, _, _, _ = _grid_from_h5(bottleneck_file, "Nb")
+        kw.update(bot=bot, nbs=nbs, bot_us=bus)
+    return TransitionTables(**kw)

@@ -1,0 +1,199 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the reference-generated golden vectors
+and against the CPU oracle on seeded inputs.  Bar: |ll_gpu - ll_ref| / |ll_ref| <= 1e-10 per walker (fp64)."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TB = H.load_tables()
+CASES = H.load_cases()
+OUT = H.load_outputs()
+RTOL_LL = 1e-10
+
+
+def _tables():
+    from mope_b200 import TransitionTables
+    return TransitionTables(drift=TB["drift"], gens=TB["gens"], us=TB["us"], N=float(TB["N"]), freqs=TB["freqs"],
+                            breaks=TB["breaks"], bot=TB["bot"], nbs=TB["nbs"], bot_us=TB["bot_us"])
+
+
+def _inference(case, **kw):
+    from mope_b200 import Inference
+    opts = dict(log_unif_drift=True)
+    opts.update(case.get("opts", {}))
+    opts.update(kw)
+    peds = case["peds"]
+    return Inference([p["data"] for p in peds], [p["tree"] for p in peds], [p["ages"] for p in peds], _tables(),
+                     _inputs_are_text=True, **opts)
+
+
+@pytest.fixture(scope="module")
+def inf_both():
+    I = _inference(CASES["example_both"])
+    yield I
+    I.close()
+
+
+def test_transition_matrices_match_reference(inf_both):
+    from mope_b200 import OutOfTableError
+    E = inf_both.engine
+    for t, m, P in zip(OUT["unit/drift_t"], OUT["unit/drift_m"], OUT["unit/drift_P"]):
+        np.testing.assert_allclose(E.transition_matrix(t, m), P, rtol=1e-15, atol=0)
+    for nb, m, P in zip(OUT["unit/bot_nb"], OUT["unit/bot_m"], OUT["unit/bot_P"]):
+        np.testing.assert_allclose(E.transition_matrix(nb, m, bottleneck=True), P, rtol=1e-15, atol=0)
+    with pytest.raises(OutOfTableError):
+        E.transition_matrix(TB["gens"].max() / float(TB["N"]) * 1.01, 0.01)
+    with pytest.raises(OutOfTableError):
+        E.transition_matrix(0.1, 1e-30)
+    with pytest.raises(OutOfTableError):
+        E.transition_matrix(1.5, 0.01, bottleneck=True)
+    with pytest.raises(OutOfTableError):
+        E.transition_matrix(600, 0.01, bottleneck=True)
+
+
+def test_leaf_likelihoods_match_reference(inf_both):
+    E = inf_both.engine
+    X, n = OUT["unit/binom_X"], OUT["unit/binom_n"]
+    for key, phred in (("unit/binom_like", -1.0), ("unit/binom_like_phred20", 20.0)):
+        got = E.leaf_likelihoods(X, n, TB["freqs"], phred)
+        ref = OUT[key]
+        # lnchoose is a difference of lgamma(n+1) ~ n log n values: element parity is bounded by a few ulp of those
+        tol = 8 * np.finfo(np.float64).eps * np.maximum(n, 10)[:, :, None] * np.log(np.maximum(n, 10))[:, :, None]
+        assert np.all(np.abs(got - ref) <= tol * ref + 1e-300)
+        assert np.array_equal(got == 0, ref == 0)
+        assert np.array_equal(got == 1, ref == 1)
+
+
+def test_branch_updates_match_reference(inf_both):
+    E = inf_both.engine
+    child = OUT["unit/branch_child"]
+    p = OUT["unit/branch_parent_in"].copy()
+    E.branch_update(0, child, p, 0.37, 0.004)
+    np.testing.assert_allclose(p, OUT["unit/branch_length_out"], rtol=1e-13)
+    p = OUT["unit/branch_parent_in"].copy()
+    E.branch_update(1, child, p, OUT["unit/branch_lengths"], 0.004)
+    np.testing.assert_allclose(p, OUT["unit/branch_rate_out"], rtol=1e-13)
+    p = OUT["unit/branch_parent_in"].copy()
+    E.branch_update(2, child, p, 33.3, 0.004)
+    np.testing.assert_allclose(p, OUT["unit/branch_bottleneck_out"], rtol=1e-13)
+
+
+def test_branch_update_ragged_and_identity(inf_both):
+    """Row counts around the 64-row tile, times below the first generation (identity short-cut) and exact grid hits,
+    against the oracle."""
+    from oracle import mope_oracle as orc
+    E = inf_both.engine
+    drift, bot = H.oracle_tables(TB)
+    rng = np.random.RandomState(2)
+    F = TB["freqs"].shape[0]
+    N = float(TB["N"])
+    for nrows in (1, 63, 64, 65, 130):
+        child = rng.uniform(0, 1, (nrows, F))
+        par = rng.uniform(0, 1, (nrows, F))
+        lens = 10 ** rng.uniform(-4.5, np.log10(TB["gens"].max() / N), nrows)
+        lens[0] = 1e-6                      # identity
+        if nrows > 2:
+            lens[1] = TB["gens"][0] / N     # exact hit of the first grid generation
+            lens[2] = TB["gens"][4] / N     # exact interior grid hit
+        ref = par.copy()
+        drift.clear_cache()
+        orc.compute_rate_transition_likelihood(child, ref, lens, 0.02, drift)
+        got = par.copy()
+        E.branch_update(1, child, got, lens, 0.02)
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-300)
+        ref = par.copy()
+        orc.compute_length_transition_likelihood(child, ref, 1e-6, 0.02, drift)   # identity matrix
+        got = par.copy()
+        E.branch_update(0, child, got, 1e-6, 0.02)
+        np.testing.assert_allclose(got, ref, rtol=1e-14)
+
+
+def test_poisson_binomial_matches_reference(inf_both):
+    E = inf_both.engine
+    sets = [OUT["unit/pb_q_%d" % k] for k in range(4)]
+    for k in range(4):
+        got = E.non_asc_probs([sets[k]], TB["freqs"], float(OUT["unit/pb_minfreq_%d" % k]))[0]
+        np.testing.assert_allclose(got, OUT["unit/pb_out_%d" % k], rtol=1e-12, atol=1e-300)
+    # ragged batch in one call (same min_freq), incl. an empty read set
+    got = E.non_asc_probs([sets[1], np.zeros(0), sets[0][:7]], TB["freqs"], 0.02)
+    from oracle import mope_oracle as orc
+    np.testing.assert_allclose(got[0], OUT["unit/pb_out_1"], rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(got[2], orc.get_non_asc_probs(sets[0][:7], TB["freqs"], 0.02), rtol=1e-12, atol=1e-300)
+    assert np.all(got[1] == 0)
+
+
+@pytest.mark.parametrize("name", sorted(CASES.keys()))
+def test_full_likelihood_matches_reference(name):
+    I = _inference(CASES[name])
+    try:
+        np.testing.assert_allclose(I.lower, OUT[name + "/lower"], rtol=1e-15)
+        np.testing.assert_allclose(I.upper, OUT[name + "/upper"], rtol=1e-15)
+        assert I.header == CASES[name]["header"]
+        X = OUT[name + "/X"]
+        ll, status, comps = I.loglike_components(X)
+        assert not status.any()
+        ref = OUT[name + "/loglike"]
+        rel = H.relerr(ll, ref)
+        assert rel.max() <= RTOL_LL, (name, rel.max())
+        for k, c in enumerate(comps):
+            assert H.relerr(c["root_ll"], OUT[name + "/root_ll"][:, k]).max() <= RTOL_LL
+            np.testing.assert_allclose(c["log_asc"], OUT[name + "/log_asc_%d" % k], rtol=1e-9, atol=1e-14)
+        # single-vector entry points and the posterior (sign folding + prior)
+        assert H.relerr(I.loglike(X[0]), ref[0]) <= RTOL_LL
+        nv = I.num_varnames
+        Xs = X.copy()
+        Xs[:, nv:2 * nv] *= np.where(np.arange(nv) % 2 == 0, -1.0, 1.0)
+        Xs[:, -1] *= -1.0
+        lp = I.log_posterior_batch(Xs)
+        assert H.relerr(lp, OUT[name + "/log_posterior"]).max() <= RTOL_LL
+        assert H.relerr(I.log_posterior(Xs[1]), OUT[name + "/log_posterior"][1]) <= RTOL_LL
+        for i in (0, X.shape[0] - 1):
+            assert H.relerr(I.logprior(X[i]), OUT[name + "/logprior"][i]) <= 1e-14
+    finally:
+        I.close()
+
+
+def test_out_of_prior_and_out_of_table(inf_both):
+    from mope_b200 import OutOfTableError
+    I = inf_both
+    x = OUT["example_both/X"][0].copy()
+    bad = x.copy()
+    bad[0] = I.upper[0] + 0.5
+    assert I.log_posterior(bad) == -np.inf          # prior short-circuits, likelihood never evaluated
+    far = x.copy()
+    far[I.num_varnames] = 3.0                       # mutation rate beyond the table
+    with pytest.raises(OutOfTableError):
+        I.loglike(far)
+    ll, status = I.loglike_batch(np.stack([x, far, x]), raise_on_error=False, return_status=True)
+    assert status[0] == 0 and status[2] == 0 and status[1] != 0
+    assert np.isnan(ll[1]) and ll[0] == ll[2]
+    assert H.relerr(ll[0], OUT["example_both/loglike"][0]) <= RTOL_LL
+
+
+def test_small_workspace_chunks_walkers():
+    """A workspace that only fits a few walkers gives identical results (chunked evaluation)."""
+    case = CASES["example_both"]
+    X = OUT["example_both/X"][:24]
+    I1 = _inference(case)
+    ll_full = I1.loglike_batch(X)
+    I1.close()
+    I2 = _inference(case, workspace_bytes=1)        # clamps to the minimum: one walker per chunk
+    ll_small = I2.loglike_batch(X)
+    I2.close()
+    np.testing.assert_array_equal(ll_full, ll_small)
+
+
+def test_gpu_pool_map(inf_both):
+    from mope_b200 import GpuPool
+    from mope_b200 import inference as minf
+    minf.inf_data = inf_both
+    pool = GpuPool(inf_both)
+    X = OUT["example_both/X"][:5]
+    got = pool.map(minf.post_clone, list(X))
+    assert H.relerr(got, [inf_both.log_posterior(x) for x in X]).max() == 0
+    got = pool.map(minf.logl, list(X))
+    assert H.relerr(got, OUT["example_both/loglike"][:5]).max() <= RTOL_LL
+    assert pool.map(minf.logp, list(X)) == [inf_both.logprior(x) for x in X]
+    assert pool.map(lambda v: float(v.sum()), list(X)) == [float(x.sum()) for x in X]

@@ -1,0 +1,107 @@
+"""CPU tests of the host side of mope_b200 (no CUDA calls): parser, model compiler, prior box, root prior,
+and that the C-ABI library loads and exports every symbol include/mope_b200.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from mope_b200 import _lib, model, newick, stationary, tables
+from oracle import mope_oracle as orc
+from tests import helpers as H
+
+TB = H.load_tables()
+CASES = H.load_cases()
+OUT = H.load_outputs()
+
+
+def test_library_exports_every_declared_symbol():
+    _lib.build()
+    hdr = open(os.path.join(H.GOLDEN, "..", "..", "include", "mope_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mope_b200_[a-z_]+)\s*\(", hdr)))
+    assert declared == sorted(_lib.SYMBOLS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in _lib.lib().mope_b200_version()
+
+
+def test_newick_matches_oracle_parser():
+    for case in CASES.values():
+        for ped in case["peds"]:
+            a = newick.loads(ped["tree"])[0]
+            b = orc.parse_newick(ped["tree"])
+            la = [(n.name, n.varname, n.multipliername, n.is_bottleneck, len(n.children)) for n in a.postorder()]
+            lb = [(n.name, n.varname, n.multipliername, n.is_bottleneck, len(n.children)) for n in b.postorder()]
+            assert la == lb
+
+
+def test_newick_errors():
+    with pytest.raises(ValueError):
+        newick.loads("((a:x,b:y)c:z;")
+    with pytest.raises(ValueError):
+        newick.loads("(a:x*y*z,b:y)r;")
+    t = newick.loads("(a:x^,b:y*age)r;")[0]
+    assert [(n.name, n.varname, n.multipliername, n.is_bottleneck) for n in t.postorder()] == \
+        [("a", "x", None, True), ("b", "y", "age", False), ("r", None, None, False)]
+
+
+@pytest.mark.parametrize("name", sorted(CASES.keys()))
+def test_model_compile_matches_reference(name):
+    case = CASES[name]
+    for k, ped in enumerate(case["peds"]):
+        pm = model.compile_pedigree(model.read_table(ped["data"], True), ped["tree"], model.read_table(ped["ages"], True))
+        assert pm.branch_names == case["branch_names"][k]
+        assert pm.leaf_names == case["leaf_names"][k]
+        assert pm.num_loci == int(OUT[name + "/num_loci_%d" % k])
+        np.testing.assert_array_equal(pm.fam_count.astype(np.int64), OUT[name + "/counts_%d" % k])
+        # parents come after children, the root is node n_branches
+        assert np.all(pm.br_parent > np.arange(len(pm.branch_names)))
+        assert pm.br_parent.max() == len(pm.branch_names)
+        # ascertainment pairs are the distinct multiplier tuples
+        assert pm.asc_mult.shape[1] == len({tuple(pm.asc_mult[:, pm.fam_asc[f]]) for f in range(pm.n_fam)})
+        o = H.oracle_inference(case, TB).peds[k]
+        for j, m in enumerate(pm.multipliernames):
+            np.testing.assert_array_equal(pm.row_mult[j], o.row_mult[m])
+            np.testing.assert_array_equal(pm.asc_mult[j][pm.fam_asc], np.asarray(o.ages[m], dtype=np.float64))
+
+
+def test_stationary_distribution_bit_identical_to_reference():
+    abpp = OUT["unit/stat_abpp"]
+    got = stationary.stationary_distribution_batch(TB["breaks"], int(TB["N"]), abpp[:, 0], abpp[:, 1])
+    np.testing.assert_array_equal(got, OUT["unit/stat_dist"])
+    # and against the oracle restatement on random draws over the whole prior box
+    rng = np.random.RandomState(5)
+    ab, pp = 10 ** rng.uniform(-9, 0, 40), 10 ** rng.uniform(-9, 0, 40)
+    got = stationary.stationary_distribution_batch(TB["breaks"], int(TB["N"]), ab, pp)
+    for i in range(40):
+        np.testing.assert_array_equal(got[i], orc.get_stationary_distribution_double_beta(TB["breaks"], int(TB["N"]), ab[i], pp[i]))
+
+
+def test_tables_validation(tmp_path):
+    tb = tables.TransitionTables(drift=TB["drift"], gens=TB["gens"], us=TB["us"], N=float(TB["N"]), freqs=TB["freqs"],
+                                 breaks=TB["breaks"], bot=TB["bot"], nbs=TB["nbs"], bot_us=TB["bot_us"])
+    p = str(tmp_path / "t.npz")
+    tb.save(p)
+    tb2 = tables.load(p, p)
+    np.testing.assert_array_equal(tb2.drift, tb.drift)
+    assert tb2.get_max_coal_time() == TB["gens"].max() / float(TB["N"])
+    assert tables.load(p, None).bot is None
+    with pytest.raises(ValueError):
+        tables.TransitionTables(drift=TB["drift"], gens=TB["gens"][::-1], us=TB["us"], N=1000, freqs=TB["freqs"], breaks=TB["breaks"])
+    with pytest.raises(ValueError):
+        tables.TransitionTables(drift=TB["drift"], gens=TB["gens"], us=TB["us"], N=1000, freqs=TB["freqs"], breaks=np.int64(0))
+
+
+def test_engine_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from mope_b200 import Inference
+    case = CASES["test_simple"]
+    tb = tables.TransitionTables(drift=TB["drift"], gens=TB["gens"], us=TB["us"], N=float(TB["N"]), freqs=TB["freqs"],
+                                 breaks=TB["breaks"], bot=TB["bot"], nbs=TB["nbs"], bot_us=TB["bot_us"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Inference([case["peds"][0]["data"]], [case["peds"][0]["tree"]], [case["peds"][0]["ages"]], tb,
+                  log_unif_drift=True, _inputs_are_text=True)
