@@ -145,6 +145,14 @@ int mope_b200_eval_device(mope_ctx* ctx, const double* params_host, const double
 /* Number of kernels this library launched since the context was created. */
 int64_t mope_b200_launch_count(const mope_ctx* ctx);
 
+/* Measurement support (bench.py).  With profiling on, every pruning-kernel launch is bracketed by CUDA events on
+ * its stream; mope_b200_kernel_times synchronises, returns the accumulated device time (ms) and launch count of the
+ * pruning kernel and of the interpolation kernel since the last call, and resets the accumulators. */
+int mope_b200_set_profiling(mope_ctx* ctx, int on);
+int mope_b200_kernel_times(mope_ctx* ctx, double* tree_ms, int64_t* tree_launches, double* interp_ms, int64_t* interp_launches);
+/* fp64 tensor-pipe ceiling: register-only mma.sync.m8n8k4.f64 loop for about `millis` ms on `stream`; TFLOP/s out. */
+int mope_b200_fp64_peak(mope_ctx* ctx, double millis, void* stream, double* out_tflops);
+
 /* Operator-level entry points (parity tests mirror the reference's operator contracts). */
 
 /* P = get_transition_probabilities_2d(x, scaled_mut): bottleneck=0 -> drift tables, x = scaled time,

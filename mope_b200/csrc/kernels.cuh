@@ -640,4 +640,19 @@ __global__ void mul_unpad_kernel(const double* __restrict__ Y, double* __restric
     parent[idx] *= Y[(size_t)r * Fp + f];
 }
 
+// register-only DMMA loop: the fp64 tensor-pipe ceiling the tree kernel is measured against
+__global__ void dmma_peak_kernel(double* out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x * 1e-9; c[i][1] = i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+
 }  // namespace mope

@@ -104,6 +104,10 @@ struct mope_ctx {
     size_t opbuf_cap = 0;
     int64_t launches = 0;
     int tree_variant = 13;
+    // profiling
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_tree, ev_interp;
+    std::vector<cudaEvent_t> ev_pool;
 };
 
 namespace {
@@ -248,6 +252,23 @@ int layout_arena(mope_ctx* c, const mope_tables_desc* t, const mope_model_desc* 
     return 0;
 }
 
+cudaEvent_t get_event(mope_ctx* c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ScopedTimer {
+    mope_ctx* c; cudaStream_t st; std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* sink; cudaEvent_t e0 = nullptr;
+    ScopedTimer(mope_ctx* c_, cudaStream_t st_, std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* sink_) : c(c_), st(st_), sink(sink_) {
+        if (c->profiling) { e0 = get_event(c); cudaEventRecord(e0, st); }
+    }
+    ~ScopedTimer() {
+        if (e0) { cudaEvent_t e1 = get_event(c); cudaEventRecord(e1, st); sink->push_back({e0, e1}); }
+    }
+};
+
 template <int NTW>
 int launch_tree_t(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) {
     static bool attr_set = false;
@@ -255,7 +276,10 @@ int launch_tree_t(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) 
         CUDA_TRY(cudaFuncSetAttribute(tree_kernel<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<NTW>::SMEM_BYTES));
         attr_set = true;
     }
-    tree_kernel<NTW><<<grid, NTHREADS, TileCfg<NTW>::SMEM_BYTES, st>>>(tp);
+    {
+        ScopedTimer timer(c, st, &c->ev_tree);
+        tree_kernel<NTW><<<grid, NTHREADS, TileCfg<NTW>::SMEM_BYTES, st>>>(tp);
+    }
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return 0;
@@ -600,7 +624,10 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
             const int wpb = 8;
             const long long rows = (long long)n_blocks * Fp;
             const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-            interp_kernel<<<grid, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_jobs, (int)n_blocks, c->tables, d_pool, F, Fp);
+            {
+                ScopedTimer timer(c, st, &c->ev_interp);
+                interp_kernel<<<grid, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_jobs, (int)n_blocks, c->tables, d_pool, F, Fp);
+            }
             CUDA_TRY(cudaGetLastError());
             c->launches++;
         }
@@ -875,6 +902,9 @@ int mope_b200_destroy(mope_ctx* c) {
     cudaSetDevice(c->device);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->opbuf) cudaFree(c->opbuf);
+    for (auto& pr : c->ev_tree) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& pr : c->ev_interp) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
     delete c;
     return 0;
 }
@@ -899,6 +929,67 @@ int mope_b200_eval_device(mope_ctx* c, const double* params_host, const double* 
 }
 
 int64_t mope_b200_launch_count(const mope_ctx* c) { return c ? c->launches : 0; }
+
+int mope_b200_set_profiling(mope_ctx* c, int on) {
+    if (!c) return fail(MOPE_E_INVALID, "null ctx");
+    c->profiling = on != 0;
+    return 0;
+}
+
+int mope_b200_kernel_times(mope_ctx* c, double* tree_ms, int64_t* tree_launches, double* interp_ms, int64_t* interp_launches) {
+    if (!c) return fail(MOPE_E_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    auto drain = [&](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v, double* ms, int64_t* n) {
+        double tot = 0;
+        for (auto& pr : v) {
+            float m = 0;
+            cudaEventElapsedTime(&m, pr.first, pr.second);
+            tot += m;
+            c->ev_pool.push_back(pr.first);
+            c->ev_pool.push_back(pr.second);
+        }
+        if (ms) *ms = tot;
+        if (n) *n = (int64_t)v.size();
+        v.clear();
+    };
+    drain(c->ev_tree, tree_ms, tree_launches);
+    drain(c->ev_interp, interp_ms, interp_launches);
+    return 0;
+}
+
+int mope_b200_fp64_peak(mope_ctx* c, double millis, void* stream, double* out_tflops) {
+    if (!c || !out_tflops) return fail(MOPE_E_INVALID, "fp64_peak: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ensure_opbuf(c, 4096)) return MOPE_E_CUDA;
+    double* out = reinterpret_cast<double*>(c->opbuf);
+    const int grid = c->num_sms * 2, threads = 512, iters = 20000;
+    const double flop_per_launch = 2.0 * 256 * 8 * (double)iters * ((double)grid * threads / 32);
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    dmma_peak_kernel<<<grid, threads, 0, st>>>(out, iters, 1.0000001, 1e-9);  // warm-up
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int reps = 0;
+    double total_ms = 0;
+    CUDA_TRY(cudaEventRecord(e0, st));
+    do {
+        dmma_peak_kernel<<<grid, threads, 0, st>>>(out, iters, 1.0000001, 1e-9);
+        ++reps;
+        c->launches++;
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        total_ms = ms;
+    } while (total_ms < millis && reps < 10000);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *out_tflops = flop_per_launch * reps / (total_ms * 1e-3) * 1e-12;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // operator-level entry points

@@ -168,6 +168,23 @@ class Engine:
         _lib.check(rc, "mope_b200_eval_device")
         return status
 
+    # measurement support ------------------------------------------------------------------------
+    def set_profiling(self, on: bool) -> None:
+        _lib.check(self.lib.mope_b200_set_profiling(self.ctx, int(bool(on))), "mope_b200_set_profiling")
+
+    def kernel_times(self):
+        """(tree_ms, tree_launches, interp_ms, interp_launches) accumulated since the last call; synchronises."""
+        tm, im = C.c_double(0), C.c_double(0)
+        tn, in_ = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.lib.mope_b200_kernel_times(self.ctx, C.byref(tm), C.byref(tn), C.byref(im), C.byref(in_)),
+                   "mope_b200_kernel_times")
+        return tm.value, tn.value, im.value, in_.value
+
+    def fp64_peak_tflops(self, millis: float = 300.0) -> float:
+        out = C.c_double(0)
+        _lib.check(self.lib.mope_b200_fp64_peak(self.ctx, float(millis), self._stream(), C.byref(out)), "mope_b200_fp64_peak")
+        return out.value
+
     # operator-level entry points ------------------------------------------------------------------
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
