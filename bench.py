@@ -303,6 +303,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1) / args.steps
     launches = (eng.launch_count() - launches0) // max(args.steps, 1)
     tree_ms, tree_n, interp_ms, interp_n = eng.kernel_times()
+    gemm_ops, identity_ops = eng.last_eval_stats()
     eng.set_profiling(False)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -331,7 +332,9 @@ def run_ours(args):
 
     if rank == 0:
         # ---- roofline of the dominant kernel (the fused pruning kernel), fp64 tensor pipe ----
-        flops_per_launch = 2.0 * F * F * R * B * W
+        # algorithmic flops of the GEMMs the kernel actually executes: 2 F^2 per (row, branch), minus the branches
+        # that take the reference's identity short-cut (those are forwarded without a product)
+        flops_per_launch = 2.0 * F * F * R * gemm_ops
         tree_avg_ms = tree_ms / max(tree_n, 1)
         achieved = flops_per_launch / (tree_avg_ms * 1e-3) * 1e-12
         peak = eng.fp64_peak_tflops(300.0)
@@ -348,7 +351,8 @@ def run_ours(args):
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": "fp64 DMMA register-only loop measured live in this run (MEASURED_PEAKS.json has no fp64 entry; "
                                    "its dense-bf16 figure does not bound an fp64 kernel)",
-                    "flops_per_launch": flops_per_launch, "avg_launch_ms": tree_avg_ms, "launches_timed": int(tree_n),
+                    "flops_per_launch": flops_per_launch, "branch_gemms_per_launch": int(gemm_ops),
+                    "identity_branches_per_launch": int(identity_ops), "avg_launch_ms": tree_avg_ms, "launches_timed": int(tree_n),
                     "share_of_step": tree_avg_ms * (tree_n / max(args.steps, 1)) / ms,
                     "hbm_frac_if_memory_bound": (alg_bytes / (tree_avg_ms * 1e-3) * 1e-9 / hbm) if hbm else None,
                     "interp_avg_ms": interp_ms / max(interp_n, 1)}

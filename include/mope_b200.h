@@ -145,6 +145,11 @@ int mope_b200_eval_device(mope_ctx* ctx, const double* params_host, const double
 /* Number of kernels this library launched since the context was created. */
 int64_t mope_b200_launch_count(const mope_ctx* ctx);
 
+/* Branch updates of the last eval, counted per (walker, branch): GEMMs executed, and branches that took the
+ * reference's identity short-cut (N*t below the first table generation, transition_data_2d.py:184-187), for which
+ * the message is forwarded without a GEMM.  For age-scaled branches every (walker, branch) counts as one GEMM. */
+int mope_b200_last_eval_stats(const mope_ctx* ctx, int64_t* gemm_ops, int64_t* identity_ops);
+
 /* Measurement support (bench.py).  With profiling on, every pruning-kernel launch is bracketed by CUDA events on
  * its stream; mope_b200_kernel_times synchronises, returns the accumulated device time (ms) and launch count of the
  * pruning kernel and of the interpolation kernel since the last call, and resets the accumulators. */

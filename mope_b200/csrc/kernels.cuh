@@ -24,15 +24,18 @@ constexpr int LDSM = KC + 4;  // smem row stride in doubles: 20 -> conflict-free
 constexpr int NSTAGE = 4;     // cp.async pipeline depth
 constexpr int NTHREADS = 256; // 8 warps: 4 along M (16 rows each) x 2 along N
 
+// One branch of the tree: Y = P . (product of the child messages of the node below the branch).
 struct TreeOp {
-    int32_t src_kind;  // 0 leaf emissions, 1 scratch slot
-    int32_t src;       // leaf column or slot id
-    int32_t dst;       // parent scratch slot (-1 when the parent is the root and this is its only/last use)
-    int32_t first;     // 1: parent = Y, 0: parent *= Y
-    int32_t kind;      // 0 shared matrix (fixed length or bottleneck), 1 per-row times (rate)
-    int32_t key;       // kind 0: matrix key index; kind 1: rate key index
-    int32_t mult;      // kind 1: multiplier column
-    int32_t last;      // 1: parent is the root and is complete after this op -> root reduction
+    int32_t nsrc;         // 1 or 2 operands, multiplied element-wise while the A fragments are read
+    int32_t src_kind[2];  // 0 leaf emissions (leaf branches, nsrc = 1), 1 scratch slot
+    int32_t src[2];       // leaf column or slot id
+    int32_t dst;          // scratch slot receiving the message Y (-1 for the op that completes the root)
+    int32_t first;        // 1: dst = Y; 0: dst *= Y (third and later children of a node fold into an existing message)
+    int32_t kind;         // 0 shared matrix (fixed length or bottleneck), 1 per-row times (rate)
+    int32_t key;          // kind 0: matrix key index; kind 1: rate key index
+    int32_t mult;         // kind 1: multiplier column
+    int32_t last;         // 1: this message completes the root -> root reduction instead of a store
+    int32_t sib[2];       // last: slots of the root's other messages (-1 = none)
 };
 
 struct RateInfo {
@@ -57,8 +60,9 @@ struct TreeParams {
     const TreeOp* ops;
     int32_t n_ops, n_slots;
     int32_t R, L, R_pad, Fp, F, NT, n_tiles, W;
+    int32_t tile_block;      // tiles per L2 block of the item order
     const double* pool;      // per-launch matrix pool
-    const int64_t* mat_off;  // [W][n_mat] offsets (doubles) into pool
+    const int64_t* mat_off;  // [W][n_mat] offsets (doubles) into pool; negative = identity matrix (GEMM skipped)
     int32_t n_mat, n_rate;
     const RateInfo* rate;    // [W][n_rate]
     const double* mult;      // [n_mult][R_pad]
@@ -220,6 +224,14 @@ __global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* t
 
 // ------------------------------------------------------------------------------------------------
 // fused pruning pass
+//
+// One CTA owns a 64-row tile of one walker and walks the whole branch schedule for it.  Every branch is a
+// GEMM tile Y[64 x F] = V[64 x F] . P^T on the fp64 tensor pipe (mma.sync.m8n8k4.f64), where V is the
+// element-wise product of the (at most two) child messages of the node below the branch -- the product is
+// taken while the A fragments are read from shared memory, so no epilogue ever has to read-modify-write a
+// parent tile.  Messages live in a per-CTA scratch ring that stays L2 resident.  K is streamed in 16-wide
+// chunks through a 4-stage cp.async pipeline; the P chunks of the next branch are prefetched under the
+// epilogue of the current one.
 // ------------------------------------------------------------------------------------------------
 struct TreeSmem {
     double rowdot[2][TM];
@@ -231,76 +243,88 @@ struct TreeSmem {
 template <int NTW>
 struct TileCfg {
     static constexpr int PROWS = 2 * NTW * 8;                          // P rows staged per pass
-    static constexpr int STAGE_DOUBLES = (TM + PROWS) * LDSM;
+    static constexpr int STAGE_DOUBLES = (2 * TM + PROWS) * LDSM;      // V0 | V1 | P
     static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_DOUBLES * sizeof(double) + sizeof(TreeSmem);
 };
 
-// issue the cp.async copies of one K chunk: V rows [0,TM) and P rows [0,prow_count)
-template <int NTW>
-__device__ __forceinline__ void load_chunk(double* stage, const double* __restrict__ Vsrc, const double* __restrict__ Psrc,
-                                           int Fp, int kc, int prow_count) {
+// cp.async copies of one K chunk of P rows [0, prow_count) into the stage
+__device__ __forceinline__ void load_P_chunk(double* stage, const double* __restrict__ Psrc, int Fp, int kc, int prow_count) {
     const int koff = kc * KC;
-    const int total = (TM + prow_count) * (KC / 2);  // 16-byte pieces
+    double* dstb = stage + 2 * TM * LDSM;
+    const int total = prow_count * (KC / 2);
     for (int idx = threadIdx.x; idx < total; idx += NTHREADS) {
         const int r = idx >> 3, piece = idx & 7;
-        const double* g = (r < TM) ? (Vsrc + (size_t)r * Fp + koff + piece * 2)
-                                   : (Psrc + (size_t)(r - TM) * Fp + koff + piece * 2);
+        cp_async16(dstb + r * LDSM + piece * 2, Psrc + (size_t)r * Fp + koff + piece * 2);
+    }
+}
+// cp.async copies of one K chunk of the (one or two) V operands
+template <int NSRC>
+__device__ __forceinline__ void load_V_chunk(double* stage, const double* __restrict__ V0, const double* __restrict__ V1, int Fp, int kc) {
+    const int koff = kc * KC;
+    constexpr int total = NSRC * TM * (KC / 2);
+    for (int idx = threadIdx.x; idx < total; idx += NTHREADS) {
+        const int r = idx >> 3, piece = idx & 7;
+        const double* g = (NSRC == 1 || r < TM) ? (V0 + (size_t)r * Fp + koff + piece * 2)
+                                                : (V1 + (size_t)(r - TM) * Fp + koff + piece * 2);
         cp_async16(stage + r * LDSM + piece * 2, g);
     }
 }
 
-// acc += V[64 x K] * P[rows x K]^T for this warp's 16 rows x (ntw valid) n-tiles.  wt (may be null): per-row
-// scale of V in shared memory (rate segments).
-template <int NTW>
-__device__ __forceinline__ void gemm_pass(double (&acc)[2][NTW][2], double* stages, const double* __restrict__ Vsrc,
-                                          const double* __restrict__ Psrc, int Fp, int prow_count, int ntw_valid,
-                                          const double* wt, int seg_for_wt, const TreeSmem* ts) {
+// acc += (V0 .* V1 .* w)[64 x K] * P[rows x K]^T for this warp's 16 rows x NTW n-tiles.
+// p_prefetched: the P chunks of the first NSTAGE-1 stages were already issued (previous epilogue).
+template <int NTW, int NSRC, bool SCALED>
+__device__ __forceinline__ void gemm_pass(double (&acc)[2][NTW][2], double* stages, const double* __restrict__ V0,
+                                          const double* __restrict__ V1, const double* __restrict__ Psrc, int Fp, int prow_count,
+                                          bool p_prefetched, double w0, double w1) {
     using Cfg = TileCfg<NTW>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp & 3, wn = warp >> 2;
     const int nchunks = Fp / KC;
-    // prologue
 #pragma unroll
     for (int s = 0; s < NSTAGE - 1; ++s) {
-        if (s < nchunks) load_chunk<NTW>(stages + (size_t)s * Cfg::STAGE_DOUBLES, Vsrc, Psrc, Fp, s, prow_count);
+        if (s < nchunks) {
+            double* stg = stages + (size_t)s * Cfg::STAGE_DOUBLES;
+            if (!p_prefetched) load_P_chunk(stg, Psrc, Fp, s, prow_count);
+            load_V_chunk<NSRC>(stg, V0, V1, Fp, s);
+        }
         cp_async_commit();
     }
-    double w0 = 1.0, w1 = 1.0;
-    if (wt != nullptr) {
-        // per-row weight of this segment: a if seg == gi-1, d if seg == gi
-        const int r0 = wm * 16 + (lane >> 2), r1 = r0 + 8;
-        const int g0 = ts->row_g[r0], g1 = ts->row_g[r1];
-        w0 = (g0 >= 0) ? ((seg_for_wt == g0 - 1 ? ts->row_a[r0] : 0.0) + (seg_for_wt == g0 ? ts->row_d[r0] : 0.0)) : 0.0;
-        w1 = (g1 >= 0) ? ((seg_for_wt == g1 - 1 ? ts->row_a[r1] : 0.0) + (seg_for_wt == g1 ? ts->row_d[r1] : 0.0)) : 0.0;
-    }
+    const int a_off = (wm * 16 + (lane >> 2)) * LDSM + (lane & 3);
+    const int b_off = (2 * TM + wn * NTW * 8 + (lane >> 2)) * LDSM + (lane & 3);
     for (int c = 0; c < nchunks; ++c) {
         cp_async_wait<NSTAGE - 2>();
         __syncthreads();
         {
             const int nc = c + NSTAGE - 1;
-            if (nc < nchunks) load_chunk<NTW>(stages + (size_t)(nc % NSTAGE) * Cfg::STAGE_DOUBLES, Vsrc, Psrc, Fp, nc, prow_count);
+            if (nc < nchunks) {
+                double* stg = stages + (size_t)(nc % NSTAGE) * Cfg::STAGE_DOUBLES;
+                load_P_chunk(stg, Psrc, Fp, nc, prow_count);
+                load_V_chunk<NSRC>(stg, V0, V1, Fp, nc);
+            }
             cp_async_commit();
         }
         const double* st = stages + (size_t)(c % NSTAGE) * Cfg::STAGE_DOUBLES;
-        const double* As = st + (wm * 16 + (lane >> 2)) * LDSM + (lane & 3);
-        const double* Bs = st + (TM + wn * NTW * 8 + (lane >> 2)) * LDSM + (lane & 3);
+        const double* As = st + a_off;
+        const double* Bs = st + b_off;
 #pragma unroll
         for (int q = 0; q < KC / 4; ++q) {
             double a0 = As[q * 4];
             double a1 = As[8 * LDSM + q * 4];
-            if (wt != nullptr) { a0 *= w0; a1 *= w1; }
+            if (NSRC == 2) {
+                a0 *= As[TM * LDSM + q * 4];
+                a1 *= As[(TM + 8) * LDSM + q * 4];
+            }
+            if (SCALED) { a0 *= w0; a1 *= w1; }
 #pragma unroll
             for (int j = 0; j < NTW; ++j) {
-                if (j < ntw_valid) {
-                    const double b = Bs[j * 8 * LDSM + q * 4];
-                    dmma(acc[0][j][0], acc[0][j][1], a0, b);
-                    dmma(acc[1][j][0], acc[1][j][1], a1, b);
-                }
+                const double b = Bs[j * 8 * LDSM + q * 4];
+                dmma(acc[0][j][0], acc[0][j][1], a0, b);
+                dmma(acc[1][j][0], acc[1][j][1], a1, b);
             }
         }
     }
     cp_async_wait<0>();
-    __syncthreads();  // all warps done with the stages before the next pass refills them
+    __syncthreads();  // all warps done with the stages before they are refilled
 }
 
 template <int NTW>
@@ -315,24 +339,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
     const int Fp = p.Fp;
     double* my_scratch = p.scratch + (size_t)blockIdx.x * p.n_slots * TM * Fp;
     const int npass = (p.NT + 2 * NTW - 1) / (2 * NTW);
+    const int nchunks = Fp / KC;
     const long long n_items = (long long)p.W * p.n_tiles;
+    const size_t blk = (size_t)Fp * Fp + Fp;
+    const int rA = wm * 16 + (lane >> 2);  // tile-local rows of acc[0], acc[1] = rA, rA + 8
 
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int w = (int)(item / p.n_tiles);
-        const int tile = (int)(item % p.n_tiles);
+        // item order: tile blocks outermost, then walkers, then the tiles of the block, so that a block of
+        // emission tiles is re-used by every walker while it is L2 resident
+        int w, tile;
+        {
+            const long long per_block = (long long)p.W * p.tile_block;
+            const int tb = (int)(item / per_block);
+            const int t_first = tb * p.tile_block;
+            const int t_count = min(p.tile_block, p.n_tiles - t_first);
+            const long long rem = item - (long long)tb * per_block;
+            w = (int)(rem / t_count);
+            tile = t_first + (int)(rem % t_count);
+        }
         const int row0 = tile * TM;
+        bool p_prefetched = false;
 
         for (int oi = 0; oi < p.n_ops; ++oi) {
             const TreeOp op = p.ops[oi];
-            const double* Vsrc = (op.src_kind == 0)
-                                     ? p.E + (size_t)op.src * p.E_leaf_stride + (size_t)row0 * Fp
-                                     : my_scratch + (size_t)op.src * TM * Fp;
+            const double* V0 = (op.src_kind[0] == 0) ? p.E + (size_t)op.src[0] * p.E_leaf_stride + (size_t)row0 * Fp
+                                                     : my_scratch + (size_t)op.src[0] * TM * Fp;
+            const double* V1 = (op.nsrc == 2) ? my_scratch + (size_t)op.src[1] * TM * Fp : V0;
             double* dst = (op.dst >= 0) ? my_scratch + (size_t)op.dst * TM * Fp : nullptr;
 
             const double* Pbase = nullptr;
             const RateInfo* ri = nullptr;
+            bool identity = false;
             if (op.kind == 0) {
-                Pbase = p.pool + p.mat_off[(size_t)w * p.n_mat + op.key];
+                const int64_t off = p.mat_off[(size_t)w * p.n_mat + op.key];
+                identity = off < 0;  // N*t below the first generation: P = I, Y = V exactly (transition_data_2d.py:184-187)
+                Pbase = p.pool + (identity ? 0 : off);
             } else {
                 ri = &p.rate[(size_t)w * p.n_rate + op.key];
                 // per-row generation index and time weights (transition_data_2d.py:183-224)
@@ -362,15 +403,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                     ts->row_a[threadIdx.x] = a;
                     ts->row_d[threadIdx.x] = d;
                 }
-                __syncthreads();
             }
-            if (op.last) {
-                if (threadIdx.x < 2 * TM) (&ts->rowdot[0][0])[threadIdx.x] = 0.0;
-                // visibility to the epilogue is ordered by the __syncthreads inside gemm_pass
+            if (op.last && threadIdx.x < 2 * TM) (&ts->rowdot[0][0])[threadIdx.x] = 0.0;
+            // messages written by the previous epilogue (and the row tables above) become visible here
+            __syncthreads();
+
+            if (identity && !op.last && p.Yout == nullptr) {
+                // Identity short-cut for the whole branch: the message is the operand product itself.  Streamed with
+                // independent 16-byte accesses (the generic epilogue would serialise one L2 round trip per fragment).
+                const int n2 = TM * Fp / 2;
+                const double2* a2 = reinterpret_cast<const double2*>(V0);
+                const double2* b2 = reinterpret_cast<const double2*>(V1);
+                double2* d2 = reinterpret_cast<double2*>(dst);
+#pragma unroll 4
+                for (int idx = threadIdx.x; idx < n2; idx += NTHREADS) {
+                    double2 v = a2[idx];
+                    if (op.nsrc == 2) { const double2 u = b2[idx]; v.x *= u.x; v.y *= u.y; }
+                    if (!op.first) { const double2 u = d2[idx]; v.x *= u.x; v.y *= u.y; }
+                    d2[idx] = v;
+                }
+                // P prefetch for the next op (nothing was staged by this one)
+                p_prefetched = false;
+                if (oi + 1 < p.n_ops) {
+                    const TreeOp nx = p.ops[oi + 1];
+                    if (nx.kind == 0) {
+                        const int64_t off = p.mat_off[(size_t)w * p.n_mat + nx.key];
+                        if (off >= 0) {
+#pragma unroll
+                            for (int s = 0; s < NSTAGE - 1; ++s)
+                                if (s < nchunks) load_P_chunk(stages + (size_t)s * Cfg::STAGE_DOUBLES, p.pool + off, Fp, s, min(Cfg::PROWS, Fp));
+                            p_prefetched = true;
+                        }
+                    }
+                }
+                continue;
             }
 
             for (int pass = 0; pass < npass; ++pass) {
-                const int t0 = pass * 2 * NTW;                       // first n-tile of the pass
+                const int t0 = pass * 2 * NTW;  // first n-tile of the pass
                 const int prow_count = min(Cfg::PROWS, Fp - t0 * 8);
                 int ntw_valid = p.NT - (t0 + wn * NTW);
                 ntw_valid = ntw_valid < 0 ? 0 : (ntw_valid > NTW ? NTW : ntw_valid);
@@ -380,18 +450,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                 for (int j = 0; j < NTW; ++j) { acc[0][j][0] = acc[0][j][1] = acc[1][j][0] = acc[1][j][1] = 0.0; }
 
                 if (op.kind == 0) {
-                    gemm_pass<NTW>(acc, stages, Vsrc, Pbase + (size_t)t0 * 8 * Fp, Fp, prow_count, ntw_valid, nullptr, 0, ts);
+                    if (!identity) {
+                        const double* Pp = Pbase + (size_t)t0 * 8 * Fp;
+                        if (op.nsrc == 2) gemm_pass<NTW, 2, false>(acc, stages, V0, V1, Pp, Fp, prow_count, p_prefetched, 1.0, 1.0);
+                        else gemm_pass<NTW, 1, false>(acc, stages, V0, V1, Pp, Fp, prow_count, p_prefetched, 1.0, 1.0);
+                    }
                 } else {
                     const int slo = ts->seg_lo, shi = ts->seg_hi;
-                    const size_t blk = (size_t)Fp * Fp + Fp;
+                    const int g0 = ts->row_g[rA], g1 = ts->row_g[rA + 8];
                     for (int seg = slo; seg <= shi; ++seg) {
+                        // per-row weight of this segment: a if seg == gi-1, d if seg == gi
+                        const double w0 = (g0 >= 0) ? ((seg == g0 - 1 ? ts->row_a[rA] : 0.0) + (seg == g0 ? ts->row_d[rA] : 0.0)) : 0.0;
+                        const double w1 = (g1 >= 0) ? ((seg == g1 - 1 ? ts->row_a[rA + 8] : 0.0) + (seg == g1 ? ts->row_d[rA + 8] : 0.0)) : 0.0;
                         const double* Pseg = p.pool + ri->off + (size_t)(seg - ri->gbase) * blk + (size_t)t0 * 8 * Fp;
-                        gemm_pass<NTW>(acc, stages, Vsrc, Pseg, Fp, prow_count, ntw_valid, ts->row_a, seg, ts);
+                        if (op.nsrc == 2) gemm_pass<NTW, 2, true>(acc, stages, V0, V1, Pseg, Fp, prow_count, false, w0, w1);
+                        else gemm_pass<NTW, 1, true>(acc, stages, V0, V1, Pseg, Fp, prow_count, false, w0, w1);
+                    }
+                }
+                p_prefetched = false;
+
+                // ---- prefetch the P chunks of the next GEMM unit under this epilogue (stages are free) ----
+                {
+                    const double* Pn = nullptr;
+                    int prow_n = 0;
+                    if (pass + 1 < npass) {
+                        if (op.kind == 0 && !identity) { Pn = Pbase + (size_t)(t0 + 2 * NTW) * 8 * Fp; prow_n = min(Cfg::PROWS, Fp - (t0 + 2 * NTW) * 8); }
+                    } else if (oi + 1 < p.n_ops) {
+                        const TreeOp nx = p.ops[oi + 1];
+                        if (nx.kind == 0) {
+                            const int64_t off = p.mat_off[(size_t)w * p.n_mat + nx.key];
+                            if (off >= 0) { Pn = p.pool + off; prow_n = min(Cfg::PROWS, Fp); }
+                        }
+                    }
+                    if (Pn != nullptr) {
+#pragma unroll
+                        for (int s = 0; s < NSTAGE - 1; ++s)
+                            if (s < nchunks) load_P_chunk(stages + (size_t)s * Cfg::STAGE_DOUBLES, Pn, Fp, s, prow_n);
+                        p_prefetched = true;  // joins the first commit group of the next gemm_pass
                     }
                 }
 
                 // ---------------- epilogue ----------------
-                const int rA = wm * 16 + (lane >> 2);  // tile-local rows of acc[0], acc[1] = rA, rA + 8
                 double dot0 = 0.0, dot1 = 0.0;
 #pragma unroll
                 for (int j = 0; j < NTW; ++j) {
@@ -401,34 +500,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                         for (int mi = 0; mi < 2; ++mi) {
                             const int rl = rA + 8 * mi;
                             double y0 = acc[mi][j][0], y1 = acc[mi][j][1];
-                            if (op.kind == 1) {
-                                const int gi = ts->row_g[rl];
-                                if (gi < 0) {  // identity short-cut (or padding row): Y = V
-                                    const double2 v = *reinterpret_cast<const double2*>(Vsrc + (size_t)rl * Fp + col);
-                                    y0 = v.x; y1 = v.y;
-                                } else {
-                                    // row renormalisation of the blended matrix (_util.pyx:138-147)
-                                    const size_t blk = (size_t)Fp * Fp + Fp;
-                                    const double* s2 = p.pool + ri->off + (size_t)(gi - ri->gbase) * blk + (size_t)Fp * Fp;
-                                    const double a = ts->row_a[rl], d = ts->row_d[rl];
-                                    double den0 = d * s2[col], den1 = d * s2[col + 1];
-                                    if (gi > 0 && a != 0.0) {
-                                        const double* s1 = s2 - blk;
-                                        den0 += a * s1[col]; den1 += a * s1[col + 1];
-                                    }
-                                    if (den0 > 1.0) y0 /= den0;
-                                    if (den1 > 1.0) y1 /= den1;
+                            const bool row_ident = identity || (op.kind == 1 && ts->row_g[rl] < 0);
+                            if (row_ident) {  // identity short-cut (or padding row): Y = V
+                                double2 v = *reinterpret_cast<const double2*>(V0 + (size_t)rl * Fp + col);
+                                if (op.nsrc == 2) {
+                                    const double2 v1 = *reinterpret_cast<const double2*>(V1 + (size_t)rl * Fp + col);
+                                    v.x *= v1.x; v.y *= v1.y;
                                 }
+                                y0 = v.x; y1 = v.y;
+                            } else if (op.kind == 1) {
+                                // row renormalisation of the blended matrix (_util.pyx:138-147)
+                                const int gi = ts->row_g[rl];
+                                const double* s2 = p.pool + ri->off + (size_t)(gi - ri->gbase) * blk + (size_t)Fp * Fp;
+                                const double a = ts->row_a[rl], d = ts->row_d[rl];
+                                double den0 = d * s2[col], den1 = d * s2[col + 1];
+                                if (gi > 0 && a != 0.0) {
+                                    const double* s1 = s2 - blk;
+                                    den0 += a * s1[col]; den1 += a * s1[col + 1];
+                                }
+                                if (den0 > 1.0) y0 /= den0;
+                                if (den1 > 1.0) y1 /= den1;
                             }
                             if (p.Yout != nullptr) {
                                 *reinterpret_cast<double2*>(p.Yout + ((size_t)w * p.R_pad + row0 + rl) * Fp + col) = make_double2(y0, y1);
                                 continue;
                             }
-                            if (!op.first) {
+                            if (!op.first) {  // only nodes with more than two children fold a message into an existing one
                                 const double2 pv = *reinterpret_cast<const double2*>(dst + (size_t)rl * Fp + col);
                                 y0 *= pv.x; y1 *= pv.y;
                             }
                             if (op.last) {
+                                for (int sidx = 0; sidx < 2; ++sidx) {
+                                    if (op.sib[sidx] >= 0) {
+                                        const double2 sv = *reinterpret_cast<const double2*>(my_scratch + (size_t)op.sib[sidx] * TM * Fp + (size_t)rl * Fp + col);
+                                        y0 *= sv.x; y1 *= sv.y;
+                                    }
+                                }
                                 const double2 sv = *reinterpret_cast<const double2*>(p.stat + (size_t)w * Fp + col);
                                 if (mi == 0) dot0 += y0 * sv.x + y1 * sv.y;
                                 else dot1 += y0 * sv.x + y1 * sv.y;
@@ -449,16 +556,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                     }
                 }
             }  // pass
-            // zero the K-padding columns [8*NT, Fp) of the parent tile once (first write), so that it is a
-            // valid V operand later
+            // zero the K-padding columns [8*NT, Fp) of a fresh message so that it is a valid V operand later
             if (p.Yout == nullptr && !op.last && op.first && 8 * p.NT < Fp) {
                 const int padw = Fp - 8 * p.NT;
                 for (int idx = threadIdx.x; idx < TM * padw; idx += NTHREADS)
                     dst[(size_t)(idx / padw) * Fp + 8 * p.NT + (idx % padw)] = 0.0;
             }
-            __syncthreads();  // parent tile visible to the whole CTA before it is read as an operand
 
             if (op.last && p.Yout == nullptr) {
+                __syncthreads();
                 // root reduction (_likes.pyx:312-322, 426-442): real rows -> sum of logs in fixed order;
                 // ascertainment rows -> raw dot products
                 if (warp == 0) {
@@ -474,9 +580,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
                     if (lane == 0) p.tile_ll[(size_t)w * p.n_tiles + tile] = part;
                 }
-                __syncthreads();
             }
         }  // ops
+        __syncthreads();  // the next item re-uses the scratch ring and the row tables
     }      // items
 }
 

@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <vector>
@@ -104,6 +105,8 @@ struct mope_ctx {
     size_t opbuf_cap = 0;
     int64_t launches = 0;
     int tree_variant = 13;
+    // statistics of the last eval: branch GEMMs executed / skipped by the identity short-cut (per walker x branch)
+    int64_t last_gemm_ops = 0, last_identity_ops = 0;
     // profiling
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_tree, ev_interp;
@@ -167,11 +170,15 @@ int validate(const mope_tables_desc* t, const mope_model_desc* m) {
     return 0;
 }
 
-// Compile the branch schedule.  Slots are assigned with stack discipline over the postorder walk.
+// Compile the branch schedule.  Every branch b produces a message Y_b = P_b . content(b); content(b) is the
+// element-wise product of the messages of b's children (or the leaf emissions).  A node keeps at most two
+// pending messages: the third and later children fold into the second one (read-modify-write), so that a
+// consumer never multiplies more than two operands.  Slots are recycled as soon as they are consumed.
 int compile_schedule(const mope_pedigree_desc& pd, const std::vector<int>& fixed_key_of_branch,
                      const std::vector<int>& rate_key_of_branch, Pedigree& out) {
     const int nb = pd.n_branches, root = pd.n_branches;
-    std::vector<int> slot(nb + 1, -1), nchild(nb + 1, 0), seen(nb + 1, 0);
+    std::vector<int> nchild(nb + 1, 0), seen(nb + 1, 0);
+    std::vector<std::vector<int>> pending(nb + 1);  // message slots waiting at a node
     for (int b = 0; b < nb; ++b) nchild[pd.br_parent[b]]++;
     std::vector<int> free_slots;
     int n_slots = 0;
@@ -179,29 +186,44 @@ int compile_schedule(const mope_pedigree_desc& pd, const std::vector<int>& fixed
     for (int b = 0; b < nb; ++b) {
         TreeOp op{};
         const int par = pd.br_parent[b];
+        op.sib[0] = op.sib[1] = -1;
         if (pd.br_leaf[b] >= 0) {
             if (nchild[b] != 0) return fail(MOPE_E_INVALID, "branch %d is marked leaf but has children", b);
-            op.src_kind = 0;
-            op.src = pd.br_leaf[b];
+            op.nsrc = 1;
+            op.src_kind[0] = 0;
+            op.src[0] = pd.br_leaf[b];
+            op.src_kind[1] = 0;
+            op.src[1] = 0;
         } else {
-            if (nchild[b] == 0 || slot[b] < 0) return fail(MOPE_E_INVALID, "internal node %d has no children", b);
-            op.src_kind = 1;
-            op.src = slot[b];
+            if (nchild[b] == 0 || pending[b].empty()) return fail(MOPE_E_INVALID, "internal node %d has no children", b);
+            op.nsrc = (int)pending[b].size();
+            for (int i = 0; i < op.nsrc; ++i) { op.src_kind[i] = 1; op.src[i] = pending[b][i]; }
+            if (op.nsrc == 1) { op.src_kind[1] = 1; op.src[1] = op.src[0]; }
         }
-        op.first = (seen[par] == 0);
         seen[par]++;
         const bool completes_root = (par == root && seen[par] == nchild[par]);
         op.last = completes_root ? 1 : 0;
-        if (slot[par] < 0 && !(completes_root && op.first)) {
-            if (!free_slots.empty()) { slot[par] = free_slots.back(); free_slots.pop_back(); }
-            else slot[par] = n_slots++;
+        if (completes_root) {
+            op.dst = -1;
+            op.first = 1;
+            for (size_t i = 0; i < pending[par].size(); ++i) op.sib[i] = pending[par][i];
+        } else if (pending[par].size() < 2) {
+            int s;
+            if (!free_slots.empty()) { s = free_slots.back(); free_slots.pop_back(); }
+            else s = n_slots++;
+            // never hand out a slot this op is still reading
+            op.dst = s;
+            op.first = 1;
+            pending[par].push_back(s);
+        } else {
+            op.dst = pending[par][1];
+            op.first = 0;
         }
-        op.dst = slot[par];
         if (pd.br_mult[b] >= 0) { op.kind = 1; op.key = rate_key_of_branch[b]; op.mult = pd.br_mult[b]; }
         else { op.kind = 0; op.key = fixed_key_of_branch[b]; op.mult = -1; }
         out.ops_h.push_back(op);
-        // the child's slot is free once consumed (after this op)
-        if (op.src_kind == 1) free_slots.push_back(slot[b]);
+        // the operands are free once this op has run
+        if (pd.br_leaf[b] < 0) for (int sl : pending[b]) free_slots.push_back(sl);
     }
     if (out.ops_h.empty() || !out.ops_h.back().last) return fail(MOPE_E_INVALID, "schedule does not end at the root");
     out.n_slots = std::max(n_slots, 1);
@@ -350,6 +372,11 @@ bool rate_range(const mope_ctx* c, double min_mult, double max_mult, double len,
 void emit_fixed_job(const mope_ctx* c, bool bott, double len, double mut, size_t& b, PlanOut& out) {
     const size_t FF = (size_t)c->F * c->F;
     const size_t blk = (size_t)c->Fp * c->Fp + c->Fp;
+    if (!bott && c->N * len < c->gens[0]) {
+        // identity short-cut (transition_data_2d.py:184-187): nothing to interpolate, the kernel skips the GEMM
+        out.mat_off.push_back(-1);
+        return;
+    }
     InterpJob jb{};
     jb.dst = (int64_t)(b * blk);
     out.mat_off.push_back(jb.dst);
@@ -375,9 +402,7 @@ void emit_fixed_job(const mope_ctx* c, bool bott, double len, double mut, size_t
     } else {
         // transition_data_2d.py:183-224
         const double t = c->N * len;
-        if (t < c->gens[0]) {
-            jb.flags = 2;
-        } else {
+        {
             const int G = c->n_gens, U = c->n_us;
             const int gi = std::min(lower_bound_idx(c->gens, t), G - 1);
             const double xd = mut / (2.0 * c->N);
@@ -441,8 +466,9 @@ void plan_walker_size(const mope_ctx* c, const double* x, WalkerPlan& wp) {
     wp.n_blocks = 0;
     const int nv = c->n_var;
     for (const FixedKey& k : c->fixed_keys) {
-        wp.status |= status_fixed(c, k.bott != 0, std::pow(10.0, x[k.var]), std::pow(10.0, x[nv + k.var]));
-        wp.n_blocks += 1;
+        const double len = std::pow(10.0, x[k.var]);
+        wp.status |= status_fixed(c, k.bott != 0, len, std::pow(10.0, x[nv + k.var]));
+        if (k.bott || !(c->N * len < c->gens[0])) wp.n_blocks += 1;
     }
     for (const RateKey& k : c->rate_keys) {
         const double len = std::pow(10.0, x[k.var]);
@@ -535,6 +561,8 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
         CUDA_TRY(cudaStreamSynchronize(st));
     }
 
+    c->last_gemm_ops = 0;
+    c->last_identity_ops = 0;
     // 3. chunk the valid walkers
     size_t gi0 = 0;
     // staging size upper bound for one chunk is computed per chunk
@@ -635,6 +663,13 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
         // pruning + finalize per pedigree
         for (int k = 0; k < c->n_ped; ++k) {
             const Pedigree& P = c->peds[k];
+            for (const TreeOp& op : P.ops_h) {
+                if (op.kind != 0) { c->last_gemm_ops += Wc; continue; }
+                for (int i = 0; i < Wc; ++i) {
+                    if (po.mat_off[(size_t)i * n_mat + op.key] < 0) c->last_identity_ops++;
+                    else c->last_gemm_ops++;
+                }
+            }
             TreeParams tp{};
             tp.E = P.E;
             tp.E_leaf_stride = (int64_t)P.R_pad * Fp;
@@ -643,6 +678,8 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
             tp.n_ops = P.n_ops;
             tp.n_slots = c->max_slots;
             tp.R = P.R; tp.L = P.L; tp.R_pad = P.R_pad; tp.Fp = Fp; tp.F = F; tp.NT = c->NT; tp.n_tiles = P.n_tiles; tp.W = Wc;
+            tp.tile_block = std::max(1, std::min(P.n_tiles, c->num_sms / 4));
+            if (const char* e = getenv("MOPE_TILE_BLOCK")) tp.tile_block = std::max(1, std::min(P.n_tiles, atoi(e)));  // tuning knob
             tp.pool = d_pool;
             tp.mat_off = d_mat_off;
             tp.n_mat = n_mat; tp.n_rate = n_rate;
@@ -930,6 +967,13 @@ int mope_b200_eval_device(mope_ctx* c, const double* params_host, const double* 
 
 int64_t mope_b200_launch_count(const mope_ctx* c) { return c ? c->launches : 0; }
 
+int mope_b200_last_eval_stats(const mope_ctx* c, int64_t* gemm_ops, int64_t* identity_ops) {
+    if (!c) return fail(MOPE_E_INVALID, "null ctx");
+    if (gemm_ops) *gemm_ops = c->last_gemm_ops;
+    if (identity_ops) *identity_ops = c->last_identity_ops;
+    return 0;
+}
+
 int mope_b200_set_profiling(mope_ctx* c, int on) {
     if (!c) return fail(MOPE_E_INVALID, "null ctx");
     c->profiling = on != 0;
@@ -1007,6 +1051,10 @@ int mope_b200_transition_matrix(mope_ctx* c, int bottleneck, double x, double sc
     size_t b0 = 0;
     emit_fixed_job(c, bottleneck != 0, x, scaled_mut, b0, po);
     const int F = c->F, Fp = c->Fp;
+    if (po.jobs.empty()) {  // identity short-cut (transition_data_2d.py:184-187)
+        for (int i = 0; i < F; ++i) for (int j = 0; j < F; ++j) out_P[(size_t)i * F + j] = (i == j) ? 1.0 : 0.0;
+        return 0;
+    }
     const size_t blk = (size_t)Fp * Fp + Fp;
     const size_t need = align_up(sizeof(InterpJob), 256) + blk * sizeof(double) + (size_t)F * F * sizeof(double) + 1024;
     if (ensure_opbuf(c, need)) return MOPE_E_CUDA;
@@ -1131,11 +1179,12 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
     carve(r);
 
     if (n_blocks) CUDA_TRY(cudaMemcpyAsync(P.jobs, po.jobs.data(), n_blocks * sizeof(InterpJob), cudaMemcpyHostToDevice, st));
-    const int64_t zero_off = 0;
-    CUDA_TRY(cudaMemcpyAsync(P.mo, &zero_off, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    const int64_t mat_off0 = po.mat_off.empty() ? 0 : po.mat_off[0];  // -1: identity short-cut
+    CUDA_TRY(cudaMemcpyAsync(P.mo, &mat_off0, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(P.rate, &ri, sizeof(RateInfo), cudaMemcpyHostToDevice, st));
     TreeOp op{};
-    op.src_kind = 0; op.src = 0; op.dst = -1; op.first = 1; op.kind = (kind == 1) ? 1 : 0; op.key = 0; op.mult = 0; op.last = 0;
+    op.nsrc = 1; op.src_kind[0] = 0; op.src[0] = 0; op.src_kind[1] = 0; op.src[1] = 0; op.dst = -1; op.first = 1;
+    op.kind = (kind == 1) ? 1 : 0; op.key = 0; op.mult = 0; op.last = 0; op.sib[0] = op.sib[1] = -1;
     CUDA_TRY(cudaMemcpyAsync(P.op, &op, sizeof(TreeOp), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(P.raw, child, (size_t)n_rows * F * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(P.par, parent, (size_t)n_rows * F * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1157,6 +1206,7 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
     TreeParams tp{};
     tp.E = P.E; tp.E_leaf_stride = (int64_t)R_pad * Fp; tp.scratch = P.Y /*unused*/; tp.ops = P.op; tp.n_ops = 1; tp.n_slots = 0;
     tp.R = n_rows; tp.L = n_rows; tp.R_pad = R_pad; tp.Fp = Fp; tp.F = F; tp.NT = c->NT; tp.n_tiles = R_pad / TM; tp.W = 1;
+    tp.tile_block = tp.n_tiles;
     tp.pool = P.pool; tp.mat_off = P.mo; tp.n_mat = 1; tp.n_rate = 1; tp.rate = P.rate; tp.mult = P.mult; tp.gens = c->gens_dev;
     tp.n_gens = c->n_gens; tp.Npop = c->N; tp.stat = nullptr; tp.tile_ll = nullptr; tp.asc_dot = nullptr; tp.Yout = P.Y;
     if (launch_tree(c, tp, std::min(tp.n_tiles, c->num_sms), st)) return MOPE_E_CUDA;

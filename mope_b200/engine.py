@@ -172,6 +172,12 @@ class Engine:
     def set_profiling(self, on: bool) -> None:
         _lib.check(self.lib.mope_b200_set_profiling(self.ctx, int(bool(on))), "mope_b200_set_profiling")
 
+    def last_eval_stats(self):
+        """(gemm_ops, identity_ops) of the last evaluation, counted per (walker, branch)."""
+        g, i = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.lib.mope_b200_last_eval_stats(self.ctx, C.byref(g), C.byref(i)), "mope_b200_last_eval_stats")
+        return g.value, i.value
+
     def kernel_times(self):
         """(tree_ms, tree_launches, interp_ms, interp_launches) accumulated since the last call; synchronises."""
         tm, im = C.c_double(0), C.c_double(0)
