@@ -12,6 +12,7 @@
 //                     and Poisson terms                               (inference.py:872-894,1113-1129)
 //   pb_kernel         Poisson-binomial non-ascertainment probabilities (_poisson_binom.pyx:18-90)
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -20,8 +21,6 @@ namespace mope {
 
 constexpr int TM = 64;        // rows (loci) per tile
 constexpr int KC = 16;        // K chunk in doubles (128 B per row)
-constexpr int LDSM = KC + 4;  // smem row stride in doubles: 20 -> conflict-free 8 B fragment loads
-constexpr int NSTAGE = 4;     // cp.async pipeline depth
 constexpr int NTHREADS = 256; // 8 warps: 4 along M (16 rows each) x 2 along N
 
 // One branch of the tree: Y = P . (product of the child messages of the node below the branch).
@@ -54,6 +53,9 @@ struct InterpJob {
 };
 
 struct TreeParams {
+    CUtensorMap tmapE;      // emissions as 2-D [n_leaves*R_pad][Fp], box 16 x 64, 128 B swizzle
+    CUtensorMap tmapS;      // scratch ring as 2-D [grid*n_slots*64][Fp], box 16 x 64
+    CUtensorMap tmapP;      // matrix pool as 2-D [n_blocks*(Fp+1)][Fp], box 16 x PROWS
     const double* E;        // [n_leaves][R_pad][Fp]
     int64_t E_leaf_stride;  // R_pad * Fp
     double* scratch;        // [gridDim.x][n_slots][TM][Fp]
@@ -73,6 +75,7 @@ struct TreeParams {
     double* tile_ll;         // [W][n_tiles]
     double* asc_dot;         // [W][R - L]
     double* Yout;            // operator-level mode (single op): Y rows go to Yout[w][row][Fp] instead of a slot
+    int32_t debug;           // measurement only: 1 = skip the MMAs (data movement only), 2 = skip the copies (MMAs only)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -226,14 +229,24 @@ __global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* t
 // fused pruning pass
 //
 // One CTA owns a 64-row tile of one walker and walks the whole branch schedule for it.  Every branch is a
-// GEMM tile Y[64 x F] = V[64 x F] . P^T on the fp64 tensor pipe (mma.sync.m8n8k4.f64), where V is the
-// element-wise product of the (at most two) child messages of the node below the branch -- the product is
-// taken while the A fragments are read from shared memory, so no epilogue ever has to read-modify-write a
-// parent tile.  Messages live in a per-CTA scratch ring that stays L2 resident.  K is streamed in 16-wide
-// chunks through a 4-stage cp.async pipeline; the P chunks of the next branch are prefetched under the
-// epilogue of the current one.
+// GEMM tile Y[64 x F] = V[64 x F] . P^T on the fp64 tensor pipe (mma.sync.m8n8k4.f64; the tcgen05 path has no
+// f64 kind), where V is the element-wise product of the (at most two) child messages of the node below the
+// branch -- the product is taken while the A fragments are read from shared memory, so no epilogue has to
+// read-modify-write a parent tile.  Messages live in a per-CTA scratch ring that stays L2 resident.
+//
+// Operand movement: K is streamed in 16-wide chunks (128 B per row) by TMA (cp.async.bulk.tensor.2d, 128-byte
+// swizzle) into a 5-stage shared-memory ring guarded by full/empty mbarriers.  One lane issues the copies three
+// chunks ahead; the eight MMA warps only wait on `full`, read fragments, issue DMMAs and arrive on `empty` --
+// there is no CTA-wide barrier in the main loop.  The first chunks of the next branch are issued while the
+// current epilogue runs.  With the 128 B swizzle the fragment reads are bank-conflict free when the four k
+// indices of an MMA step are taken as {2q, 2q+1, 2q+8, 2q+9} of the chunk (any fixed permutation of k is valid
+// as long as A and B use the same one).
 // ------------------------------------------------------------------------------------------------
+constexpr int NS = 5;   // ring stages
+constexpr int PF = 3;   // prefetch distance in chunks
+
 struct TreeSmem {
+    unsigned long long full[NS], empty[NS], epi;
     double rowdot[2][TM];
     double row_a[TM], row_d[TM];
     int32_t row_g[TM];      // generation-grid index gi of the row (rate ops); -1 = identity / padding row
@@ -242,107 +255,138 @@ struct TreeSmem {
 
 template <int NTW>
 struct TileCfg {
-    static constexpr int PROWS = 2 * NTW * 8;                          // P rows staged per pass
-    static constexpr int STAGE_DOUBLES = (2 * TM + PROWS) * LDSM;      // V0 | V1 | P
-    static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_DOUBLES * sizeof(double) + sizeof(TreeSmem);
+    static constexpr int PROWS = 2 * NTW * 8;                    // P rows staged per pass
+    static constexpr int V_BYTES = TM * KC * 8;                  // 8 KB per V operand
+    static constexpr int P_BYTES = PROWS * KC * 8;
+    static constexpr int STAGE_BYTES = 2 * V_BYTES + P_BYTES;    // V0 | V1 | P, each 1024-aligned
+    static constexpr size_t SMEM_BYTES = (size_t)NS * STAGE_BYTES + sizeof(TreeSmem) + 1024 /*alignment slack*/;
 };
 
-// cp.async copies of one K chunk of P rows [0, prow_count) into the stage
-__device__ __forceinline__ void load_P_chunk(double* stage, const double* __restrict__ Psrc, int Fp, int kc, int prow_count) {
-    const int koff = kc * KC;
-    double* dstb = stage + 2 * TM * LDSM;
-    const int total = prow_count * (KC / 2);
-    for (int idx = threadIdx.x; idx < total; idx += NTHREADS) {
-        const int r = idx >> 3, piece = idx & 7;
-        cp_async16(dstb + r * LDSM + piece * 2, Psrc + (size_t)r * Fp + koff + piece * 2);
-    }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
-// cp.async copies of one K chunk of the (one or two) V operands
-template <int NSRC>
-__device__ __forceinline__ void load_V_chunk(double* stage, const double* __restrict__ V0, const double* __restrict__ V1, int Fp, int kc) {
-    const int koff = kc * KC;
-    constexpr int total = NSRC * TM * (KC / 2);
-    for (int idx = threadIdx.x; idx < total; idx += NTHREADS) {
-        const int r = idx >> 3, piece = idx & 7;
-        const double* g = (NSRC == 1 || r < TM) ? (V0 + (size_t)r * Fp + koff + piece * 2)
-                                                : (V1 + (size_t)(r - TM) * Fp + koff + piece * 2);
-        cp_async16(stage + r * LDSM + piece * 2, g);
-    }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\nbra.uni WAIT_LOOP;\nWAIT_DONE:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// what the copy-issuing lane needs to know about one GEMM unit (branch x pass x segment)
+struct UnitDesc {
+    int32_t nsrc;
+    int32_t v_is_E;       // operand 0 comes from the emission tensor (tensor map E) instead of the scratch ring
+    int32_t v0_row, v1_row;  // row coordinates in the respective tensor map
+    int32_t p_row;        // row coordinate in the pool tensor map
+};
+
+template <int NTW>
+__device__ __forceinline__ void issue_P(const TreeParams& p, unsigned char* ring, TreeSmem* ts, const UnitDesc& u, int c, unsigned g) {
+    using Cfg = TileCfg<NTW>;
+    const unsigned s = g % NS;
+    mbar_wait(&ts->empty[s], ((g / NS) & 1u) ^ 1u);
+    mbar_expect_tx(&ts->full[s], (unsigned)(Cfg::P_BYTES + u.nsrc * Cfg::V_BYTES));
+    tma_load_2d(ring + (size_t)s * Cfg::STAGE_BYTES + 2 * Cfg::V_BYTES, &p.tmapP, c * KC, u.p_row, &ts->full[s]);
+}
+template <int NTW>
+__device__ __forceinline__ void issue_V(const TreeParams& p, unsigned char* ring, TreeSmem* ts, const UnitDesc& u, int c, unsigned g) {
+    using Cfg = TileCfg<NTW>;
+    const unsigned s = g % NS;
+    unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
+    tma_load_2d(st, u.v_is_E ? (const void*)&p.tmapE : (const void*)&p.tmapS, c * KC, u.v0_row, &ts->full[s]);
+    if (u.nsrc == 2) tma_load_2d(st + Cfg::V_BYTES, &p.tmapS, c * KC, u.v1_row, &ts->full[s]);
 }
 
-// acc += (V0 .* V1 .* w)[64 x K] * P[rows x K]^T for this warp's 16 rows x NTW n-tiles.
-// p_prefetched: the P chunks of the first NSTAGE-1 stages were already issued (previous epilogue).
+// acc += (V0 .* V1 .* w)[64 x K] * P[rows x K]^T for this warp's 16 rows x NTW n-tiles; chunks g0 .. g0+nchunks-1 of
+// the ring.  Lane 0 of warp 0 keeps the ring PF chunks ahead.
 template <int NTW, int NSRC, bool SCALED>
-__device__ __forceinline__ void gemm_pass(double (&acc)[2][NTW][2], double* stages, const double* __restrict__ V0,
-                                          const double* __restrict__ V1, const double* __restrict__ Psrc, int Fp, int prow_count,
-                                          bool p_prefetched, double w0, double w1) {
+__device__ __forceinline__ void gemm_unit(double (&acc)[2][NTW][2], const TreeParams& p, unsigned char* ring, TreeSmem* ts,
+                                          const UnitDesc& u, int nchunks, unsigned g0, double w0, double w1) {
     using Cfg = TileCfg<NTW>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp & 3, wn = warp >> 2;
-    const int nchunks = Fp / KC;
-#pragma unroll
-    for (int s = 0; s < NSTAGE - 1; ++s) {
-        if (s < nchunks) {
-            double* stg = stages + (size_t)s * Cfg::STAGE_DOUBLES;
-            if (!p_prefetched) load_P_chunk(stg, Psrc, Fp, s, prow_count);
-            load_V_chunk<NSRC>(stg, V0, V1, Fp, s);
-        }
-        cp_async_commit();
-    }
-    const int a_off = (wm * 16 + (lane >> 2)) * LDSM + (lane & 3);
-    const int b_off = (2 * TM + wn * NTW * 8 + (lane >> 2)) * LDSM + (lane & 3);
+    const int x = lane >> 2, kk = lane & 3;
+    const int z = x ^ ((kk >> 1) << 2);
+    const int h = (kk & 1) << 3;
+    const int a_base = (wm * 16 + x) * 128 + h;
+    const int b_base = 2 * Cfg::V_BYTES + (wn * NTW * 8 + x) * 128 + h;
     for (int c = 0; c < nchunks; ++c) {
-        cp_async_wait<NSTAGE - 2>();
-        __syncthreads();
-        {
-            const int nc = c + NSTAGE - 1;
-            if (nc < nchunks) {
-                double* stg = stages + (size_t)(nc % NSTAGE) * Cfg::STAGE_DOUBLES;
-                load_P_chunk(stg, Psrc, Fp, nc, prow_count);
-                load_V_chunk<NSRC>(stg, V0, V1, Fp, nc);
-            }
-            cp_async_commit();
+        const unsigned g = g0 + c;
+        if (p.debug != 2 && threadIdx.x == 0 && c + PF < nchunks) {
+            issue_P<NTW>(p, ring, ts, u, c + PF, g + PF);
+            issue_V<NTW>(p, ring, ts, u, c + PF, g + PF);
         }
-        const double* st = stages + (size_t)(c % NSTAGE) * Cfg::STAGE_DOUBLES;
-        const double* As = st + a_off;
-        const double* Bs = st + b_off;
+        __syncwarp();
+        const unsigned s = g % NS;
+        if (p.debug != 2) mbar_wait(&ts->full[s], (g / NS) & 1u);
+        const unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
+        if (p.debug != 1)
 #pragma unroll
         for (int q = 0; q < KC / 4; ++q) {
-            double a0 = As[q * 4];
-            double a1 = As[8 * LDSM + q * 4];
+            const int oq = ((q ^ z) << 4);
+            const unsigned char* pa = st + a_base + oq;
+            const unsigned char* pb = st + b_base + oq;
+            double a0 = *reinterpret_cast<const double*>(pa);
+            double a1 = *reinterpret_cast<const double*>(pa + 1024);
             if (NSRC == 2) {
-                a0 *= As[TM * LDSM + q * 4];
-                a1 *= As[(TM + 8) * LDSM + q * 4];
+                a0 *= *reinterpret_cast<const double*>(pa + Cfg::V_BYTES);
+                a1 *= *reinterpret_cast<const double*>(pa + Cfg::V_BYTES + 1024);
             }
             if (SCALED) { a0 *= w0; a1 *= w1; }
 #pragma unroll
             for (int j = 0; j < NTW; ++j) {
-                const double b = Bs[j * 8 * LDSM + q * 4];
+                const double b = *reinterpret_cast<const double*>(pb + j * 1024);
                 dmma(acc[0][j][0], acc[0][j][1], a0, b);
                 dmma(acc[1][j][0], acc[1][j][1], a1, b);
             }
         }
+        __syncwarp();
+        if (p.debug != 2 && lane == 0) mbar_arrive(&ts->empty[s]);
     }
-    cp_async_wait<0>();
-    __syncthreads();  // all warps done with the stages before they are refilled
 }
 
 template <int NTW>
 __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant__ TreeParams p) {
     using Cfg = TileCfg<NTW>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* stages = reinterpret_cast<double*>(smem_raw);
-    TreeSmem* ts = reinterpret_cast<TreeSmem*>(smem_raw + (size_t)NSTAGE * Cfg::STAGE_DOUBLES * sizeof(double));
+    extern __shared__ unsigned char smem_raw[];
+    // 1024-byte alignment for the 128 B swizzle; plain pointer arithmetic keeps the shared address space visible to the
+    // compiler (fragment reads must be LDS, not generic loads)
+    unsigned char* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    TreeSmem* ts = reinterpret_cast<TreeSmem*>(ring + (size_t)NS * Cfg::STAGE_BYTES);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp & 3, wn = warp >> 2;
     const int Fp = p.Fp;
     double* my_scratch = p.scratch + (size_t)blockIdx.x * p.n_slots * TM * Fp;
+    const int scratch_row0 = blockIdx.x * p.n_slots * TM;   // row of slot 0 in the scratch tensor map
     const int npass = (p.NT + 2 * NTW - 1) / (2 * NTW);
     const int nchunks = Fp / KC;
     const long long n_items = (long long)p.W * p.n_tiles;
     const size_t blk = (size_t)Fp * Fp + Fp;
+    const int blk_rows = Fp + 1;
     const int rA = wm * 16 + (lane >> 2);  // tile-local rows of acc[0], acc[1] = rA, rA + 8
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&ts->full[s], 1); mbar_init(&ts->empty[s], NTHREADS / 32); }
+        mbar_init(&ts->epi, NTHREADS / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    unsigned g = 0;       // chunks consumed so far (ring position), identical in every thread
+    unsigned epi_n = 0;   // epilogues completed so far (phase of ts->epi)
 
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         // item order: tile blocks outermost, then walkers, then the tiles of the block, so that a block of
@@ -358,7 +402,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
             tile = t_first + (int)(rem % t_count);
         }
         const int row0 = tile * TM;
-        bool p_prefetched = false;
+        bool prologue_issued = false;   // chunks 0..PF-1 of the coming unit are already in flight
 
         for (int oi = 0; oi < p.n_ops; ++oi) {
             const TreeOp op = p.ops[oi];
@@ -367,13 +411,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
             const double* V1 = (op.nsrc == 2) ? my_scratch + (size_t)op.src[1] * TM * Fp : V0;
             double* dst = (op.dst >= 0) ? my_scratch + (size_t)op.dst * TM * Fp : nullptr;
 
-            const double* Pbase = nullptr;
+            UnitDesc u;
+            u.nsrc = op.nsrc;
+            u.v_is_E = (op.src_kind[0] == 0);
+            u.v0_row = u.v_is_E ? op.src[0] * p.R_pad + row0 : scratch_row0 + op.src[0] * TM;
+            u.v1_row = scratch_row0 + op.src[1] * TM;
+            u.p_row = 0;
+
             const RateInfo* ri = nullptr;
             bool identity = false;
+            int64_t moff = 0;
             if (op.kind == 0) {
-                const int64_t off = p.mat_off[(size_t)w * p.n_mat + op.key];
-                identity = off < 0;  // N*t below the first generation: P = I, Y = V exactly (transition_data_2d.py:184-187)
-                Pbase = p.pool + (identity ? 0 : off);
+                moff = p.mat_off[(size_t)w * p.n_mat + op.key];
+                identity = moff < 0;  // N*t below the first generation: P = I, Y = V exactly (transition_data_2d.py:184-187)
             } else {
                 ri = &p.rate[(size_t)w * p.n_rate + op.key];
                 // per-row generation index and time weights (transition_data_2d.py:183-224)
@@ -403,45 +453,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                     ts->row_a[threadIdx.x] = a;
                     ts->row_d[threadIdx.x] = d;
                 }
+                __syncthreads();
             }
-            if (op.last && threadIdx.x < 2 * TM) (&ts->rowdot[0][0])[threadIdx.x] = 0.0;
-            // messages written by the previous epilogue (and the row tables above) become visible here
-            __syncthreads();
+            if (op.last) {
+                if (threadIdx.x < 2 * TM) (&ts->rowdot[0][0])[threadIdx.x] = 0.0;
+                __syncthreads();
+            }
 
             if (identity && !op.last && p.Yout == nullptr) {
-                // Identity short-cut for the whole branch: the message is the operand product itself.  Streamed with
-                // independent 16-byte accesses (the generic epilogue would serialise one L2 round trip per fragment).
+                // Identity short-cut for the whole branch: the message is the operand product itself.  The operands
+                // were written with generic stores one or more epilogues ago; wait for the last one.
+                if (epi_n > 0) mbar_wait(&ts->epi, (epi_n - 1) & 1u);
                 const int n2 = TM * Fp / 2;
                 const double2* a2 = reinterpret_cast<const double2*>(V0);
                 const double2* b2 = reinterpret_cast<const double2*>(V1);
                 double2* d2 = reinterpret_cast<double2*>(dst);
-#pragma unroll 4
-                for (int idx = threadIdx.x; idx < n2; idx += NTHREADS) {
-                    double2 v = a2[idx];
-                    if (op.nsrc == 2) { const double2 u = b2[idx]; v.x *= u.x; v.y *= u.y; }
-                    if (!op.first) { const double2 u = d2[idx]; v.x *= u.x; v.y *= u.y; }
-                    d2[idx] = v;
-                }
-                // P prefetch for the next op (nothing was staged by this one)
-                p_prefetched = false;
-                if (oi + 1 < p.n_ops) {
-                    const TreeOp nx = p.ops[oi + 1];
-                    if (nx.kind == 0) {
-                        const int64_t off = p.mat_off[(size_t)w * p.n_mat + nx.key];
-                        if (off >= 0) {
+                for (int base = 0; base < n2; base += NTHREADS * 4) {
+                    double2 v[4], q2[4], r2[4];
 #pragma unroll
-                            for (int s = 0; s < NSTAGE - 1; ++s)
-                                if (s < nchunks) load_P_chunk(stages + (size_t)s * Cfg::STAGE_DOUBLES, p.pool + off, Fp, s, min(Cfg::PROWS, Fp));
-                            p_prefetched = true;
+                    for (int k = 0; k < 4; ++k) {
+                        const int idx = base + k * NTHREADS + threadIdx.x;
+                        if (idx < n2) {
+                            v[k] = a2[idx];
+                            if (op.nsrc == 2) q2[k] = b2[idx];
+                            if (!op.first) r2[k] = d2[idx];
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int idx = base + k * NTHREADS + threadIdx.x;
+                        if (idx < n2) {
+                            if (op.nsrc == 2) { v[k].x *= q2[k].x; v[k].y *= q2[k].y; }
+                            if (!op.first) { v[k].x *= r2[k].x; v[k].y *= r2[k].y; }
+                            d2[idx] = v[k];
                         }
                     }
                 }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ts->epi);
+                ++epi_n;
                 continue;
             }
 
             for (int pass = 0; pass < npass; ++pass) {
                 const int t0 = pass * 2 * NTW;  // first n-tile of the pass
-                const int prow_count = min(Cfg::PROWS, Fp - t0 * 8);
                 int ntw_valid = p.NT - (t0 + wn * NTW);
                 ntw_valid = ntw_valid < 0 ? 0 : (ntw_valid > NTW ? NTW : ntw_valid);
 
@@ -451,47 +507,79 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
 
                 if (op.kind == 0) {
                     if (!identity) {
-                        const double* Pp = Pbase + (size_t)t0 * 8 * Fp;
-                        if (op.nsrc == 2) gemm_pass<NTW, 2, false>(acc, stages, V0, V1, Pp, Fp, prow_count, p_prefetched, 1.0, 1.0);
-                        else gemm_pass<NTW, 1, false>(acc, stages, V0, V1, Pp, Fp, prow_count, p_prefetched, 1.0, 1.0);
+                        u.p_row = (int)(moff / Fp) + t0 * 8;
+                        if (p.debug != 2 && !prologue_issued && threadIdx.x == 0) {
+                            if (epi_n > 0) mbar_wait(&ts->epi, (epi_n - 1) & 1u);
+                            for (int c = 0; c < PF && c < nchunks; ++c) { issue_P<NTW>(p, ring, ts, u, c, g + c); issue_V<NTW>(p, ring, ts, u, c, g + c); }
+                        }
+                        if (op.nsrc == 2) gemm_unit<NTW, 2, false>(acc, p, ring, ts, u, nchunks, g, 1.0, 1.0);
+                        else gemm_unit<NTW, 1, false>(acc, p, ring, ts, u, nchunks, g, 1.0, 1.0);
+                        g += nchunks;
+                        prologue_issued = false;
                     }
                 } else {
                     const int slo = ts->seg_lo, shi = ts->seg_hi;
-                    const int g0 = ts->row_g[rA], g1 = ts->row_g[rA + 8];
+                    const int g0r = ts->row_g[rA], g1r = ts->row_g[rA + 8];
                     for (int seg = slo; seg <= shi; ++seg) {
                         // per-row weight of this segment: a if seg == gi-1, d if seg == gi
-                        const double w0 = (g0 >= 0) ? ((seg == g0 - 1 ? ts->row_a[rA] : 0.0) + (seg == g0 ? ts->row_d[rA] : 0.0)) : 0.0;
-                        const double w1 = (g1 >= 0) ? ((seg == g1 - 1 ? ts->row_a[rA + 8] : 0.0) + (seg == g1 ? ts->row_d[rA + 8] : 0.0)) : 0.0;
-                        const double* Pseg = p.pool + ri->off + (size_t)(seg - ri->gbase) * blk + (size_t)t0 * 8 * Fp;
-                        if (op.nsrc == 2) gemm_pass<NTW, 2, true>(acc, stages, V0, V1, Pseg, Fp, prow_count, false, w0, w1);
-                        else gemm_pass<NTW, 1, true>(acc, stages, V0, V1, Pseg, Fp, prow_count, false, w0, w1);
+                        const double w0 = (g0r >= 0) ? ((seg == g0r - 1 ? ts->row_a[rA] : 0.0) + (seg == g0r ? ts->row_d[rA] : 0.0)) : 0.0;
+                        const double w1 = (g1r >= 0) ? ((seg == g1r - 1 ? ts->row_a[rA + 8] : 0.0) + (seg == g1r ? ts->row_d[rA + 8] : 0.0)) : 0.0;
+                        u.p_row = (int)(ri->off / Fp) + (seg - ri->gbase) * blk_rows + t0 * 8;
+                        if (p.debug != 2 && threadIdx.x == 0) {
+                            if (epi_n > 0) mbar_wait(&ts->epi, (epi_n - 1) & 1u);
+                            for (int c = 0; c < PF && c < nchunks; ++c) { issue_P<NTW>(p, ring, ts, u, c, g + c); issue_V<NTW>(p, ring, ts, u, c, g + c); }
+                        }
+                        if (op.nsrc == 2) gemm_unit<NTW, 2, true>(acc, p, ring, ts, u, nchunks, g, w0, w1);
+                        else gemm_unit<NTW, 1, true>(acc, p, ring, ts, u, nchunks, g, w0, w1);
+                        g += nchunks;
                     }
+                    prologue_issued = false;
                 }
-                p_prefetched = false;
 
-                // ---- prefetch the P chunks of the next GEMM unit under this epilogue (stages are free) ----
-                {
-                    const double* Pn = nullptr;
-                    int prow_n = 0;
-                    if (pass + 1 < npass) {
-                        if (op.kind == 0 && !identity) { Pn = Pbase + (size_t)(t0 + 2 * NTW) * 8 * Fp; prow_n = min(Cfg::PROWS, Fp - (t0 + 2 * NTW) * 8); }
-                    } else if (oi + 1 < p.n_ops) {
-                        const TreeOp nx = p.ops[oi + 1];
-                        if (nx.kind == 0) {
-                            const int64_t off = p.mat_off[(size_t)w * p.n_mat + nx.key];
-                            if (off >= 0) { Pn = p.pool + off; prow_n = min(Cfg::PROWS, Fp); }
+                // ---- start the first chunks of the next GEMM unit under this epilogue ----
+                // P tiles right away; V tiles of a following pass too (same operands); V tiles of the next branch once
+                // every warp has published its part of this epilogue (they may be the message being written now).
+                UnitDesc un;
+                bool have_next = false, next_same_op = false;
+                if (pass + 1 < npass) {
+                    if (op.kind == 0 && !identity) { un = u; un.p_row = (int)(moff / Fp) + (t0 + 2 * NTW) * 8; have_next = true; next_same_op = true; }
+                } else if (oi + 1 < p.n_ops) {
+                    const TreeOp nx = p.ops[oi + 1];
+                    if (nx.kind == 0) {
+                        const int64_t off = p.mat_off[(size_t)w * p.n_mat + nx.key];
+                        if (off >= 0) {
+                            un.nsrc = nx.nsrc;
+                            un.v_is_E = (nx.src_kind[0] == 0);
+                            un.v0_row = un.v_is_E ? nx.src[0] * p.R_pad + row0 : scratch_row0 + nx.src[0] * TM;
+                            un.v1_row = scratch_row0 + nx.src[1] * TM;
+                            un.p_row = (int)(off / Fp);
+                            have_next = true;
                         }
                     }
-                    if (Pn != nullptr) {
-#pragma unroll
-                        for (int s = 0; s < NSTAGE - 1; ++s)
-                            if (s < nchunks) load_P_chunk(stages + (size_t)s * Cfg::STAGE_DOUBLES, Pn, Fp, s, prow_n);
-                        p_prefetched = true;  // joins the first commit group of the next gemm_pass
+                }
+                if (p.debug != 2 && have_next && threadIdx.x == 0) {
+                    for (int c = 0; c < PF && c < nchunks; ++c) issue_P<NTW>(p, ring, ts, un, c, g + c);
+                    if (next_same_op || un.v_is_E) {
+                        for (int c = 0; c < PF && c < nchunks; ++c) issue_V<NTW>(p, ring, ts, un, c, g + c);
                     }
                 }
+                __syncwarp();
 
                 // ---------------- epilogue ----------------
                 double dot0 = 0.0, dot1 = 0.0;
+                const bool plain_store = (op.kind == 0 && !identity && p.Yout == nullptr && op.first && !op.last);
+                if (plain_store) {
+                    // the common case: the message is just stored (two base pointers, immediate offsets)
+                    double* d0 = dst + (size_t)rA * Fp + (t0 + wn * NTW) * 8 + 2 * (lane & 3);
+                    double* d1 = d0 + (size_t)8 * Fp;
+#pragma unroll
+                    for (int j = 0; j < NTW; ++j) {
+                        if (j < ntw_valid) {
+                            *reinterpret_cast<double2*>(d0 + j * 8) = make_double2(acc[0][j][0], acc[0][j][1]);
+                            *reinterpret_cast<double2*>(d1 + j * 8) = make_double2(acc[1][j][0], acc[1][j][1]);
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int j = 0; j < NTW; ++j) {
                     if (j < ntw_valid) {
@@ -555,13 +643,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                         ts->rowdot[wn][rA + 8] += dot1;
                     }
                 }
+                const bool last_pass = (pass + 1 == npass);
+                if (last_pass) {
+                    // zero the K-padding columns [8*NT, Fp) of a fresh message so that it is a valid V operand later
+                    if (p.Yout == nullptr && !op.last && op.first && 8 * p.NT < Fp) {
+                        const int padw = Fp - 8 * p.NT;
+                        for (int idx = threadIdx.x; idx < TM * padw; idx += NTHREADS)
+                            dst[(size_t)(idx / padw) * Fp + 8 * p.NT + (idx % padw)] = 0.0;
+                    }
+                    // publish this warp's part of the message to the async proxy (TMA reads it next)
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ts->epi);
+                    ++epi_n;
+                }
+                if (have_next) {
+                    if (p.debug != 2 && !(next_same_op || un.v_is_E) && threadIdx.x == 0) {
+                        mbar_wait(&ts->epi, (epi_n - 1) & 1u);
+                        for (int c = 0; c < PF && c < nchunks; ++c) issue_V<NTW>(p, ring, ts, un, c, g + c);
+                    }
+                    prologue_issued = true;
+                }
+                __syncwarp();
             }  // pass
-            // zero the K-padding columns [8*NT, Fp) of a fresh message so that it is a valid V operand later
-            if (p.Yout == nullptr && !op.last && op.first && 8 * p.NT < Fp) {
-                const int padw = Fp - 8 * p.NT;
-                for (int idx = threadIdx.x; idx < TM * padw; idx += NTHREADS)
-                    dst[(size_t)(idx / padw) * Fp + 8 * p.NT + (idx % padw)] = 0.0;
-            }
 
             if (op.last && p.Yout == nullptr) {
                 __syncthreads();
@@ -569,8 +673,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                 // ascertainment rows -> raw dot products
                 if (warp == 0) {
                     double part = 0.0;
-                    for (int h = 0; h < 2; ++h) {
-                        const int rl = lane + 32 * h;
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int rl = lane + 32 * hh;
                         const int r = row0 + rl;
                         const double dt = ts->rowdot[0][rl] + ts->rowdot[1][rl];
                         if (r < p.L) part += log(dt);

@@ -70,6 +70,7 @@ struct Pedigree {
     TreeOp* ops = nullptr;
     std::vector<TreeOp> ops_h;
     int asc_offset = 0;
+    CUtensorMap tmapE;
 };
 
 struct FixedKey { int var; int bott; };
@@ -136,6 +137,42 @@ int ensure_opbuf(mope_ctx* c, size_t bytes) {
     c->opbuf_cap = cap;
     return 0;
 }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D fp64 tensor [rows][Fp] (row pitch Fp*8 bytes), box = 16 columns x box_rows rows, 128-byte swizzle
+int make_tmap(CUtensorMap* out, const double* base, uint64_t rows, int Fp, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(MOPE_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (rows == 0) rows = 1;
+    cuuint64_t gdim[2] = {(cuuint64_t)Fp, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)Fp * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MOPE_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows %llu, Fp %d, box %d)", (int)r,
+                                       (unsigned long long)rows, Fp, box_rows);
+    return 0;
+}
+
+int tree_prows(const mope_ctx* c) { return 2 * c->tree_variant * 8; }
 
 // searchsorted(side='left')
 inline int lower_bound_idx(const std::vector<double>& v, double x) {
@@ -548,6 +585,8 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
     double* d_out_asc = out_log_asc ? ws.take<double>((size_t)W * c->asc_total) : nullptr;
     if (!ws.ok()) return fail(MOPE_E_NOMEM, "workspace too small: %zu bytes, need more than %zu", ws_bytes, ws.used);
     const size_t fixed_used = ws.used;
+    CUtensorMap tmapS;
+    if (int rc = make_tmap(&tmapS, scratch, (uint64_t)c->num_sms * c->max_slots * TM, Fp, TM)) return rc;
 
     // outputs of invalid walkers: NaN (the host wrapper raises ValueError like the reference)
     {
@@ -660,6 +699,9 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
             c->launches++;
         }
 
+        CUtensorMap tmapP;
+        if (int rc = make_tmap(&tmapP, d_pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + 1), Fp, tree_prows(c))) return rc;
+
         // pruning + finalize per pedigree
         for (int k = 0; k < c->n_ped; ++k) {
             const Pedigree& P = c->peds[k];
@@ -671,6 +713,9 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
                 }
             }
             TreeParams tp{};
+            tp.tmapE = P.tmapE;
+            tp.tmapS = tmapS;
+            tp.tmapP = tmapP;
             tp.E = P.E;
             tp.E_leaf_stride = (int64_t)P.R_pad * Fp;
             tp.scratch = scratch;
@@ -692,6 +737,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
             tp.tile_ll = d_tile_ll;
             tp.asc_dot = d_asc_dot;
             tp.Yout = nullptr;
+            if (const char* e = getenv("MOPE_DEBUG_MODE")) tp.debug = atoi(e);  // measurement only (results are garbage)
             const long long items = (long long)Wc * P.n_tiles;
             const int grid = (int)std::min<long long>(items, c->num_sms);
             if (launch_tree(c, tp, grid, st)) return MOPE_E_CUDA;
@@ -926,6 +972,7 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         CUDA_TRY_C(cudaGetLastError());
         c->launches++;
         CUDA_TRY_C(cudaStreamSynchronize(st));  // host vectors above go out of scope per pedigree
+        if (int rc = make_tmap(&P.tmapE, P.E, (uint64_t)P.n_leaves * P.R_pad, Fp, TM)) return cleanup_fail(rc);
     }
     c->asc_total = asc_off;
     CUDA_TRY_C(cudaStreamSynchronize(st));
@@ -1204,6 +1251,9 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
         CUDA_TRY(cudaGetLastError());
     }
     TreeParams tp{};
+    if (int rc = make_tmap(&tp.tmapE, P.E, (uint64_t)R_pad, Fp, TM)) return rc;
+    if (int rc = make_tmap(&tp.tmapS, P.Y, (uint64_t)R_pad, Fp, TM)) return rc;   // no scratch ring in single-op mode
+    if (int rc = make_tmap(&tp.tmapP, P.pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + 1), Fp, tree_prows(c))) return rc;
     tp.E = P.E; tp.E_leaf_stride = (int64_t)R_pad * Fp; tp.scratch = P.Y /*unused*/; tp.ops = P.op; tp.n_ops = 1; tp.n_slots = 0;
     tp.R = n_rows; tp.L = n_rows; tp.R_pad = R_pad; tp.Fp = Fp; tp.F = F; tp.NT = c->NT; tp.n_tiles = R_pad / TM; tp.W = 1;
     tp.tile_block = tp.n_tiles;
