@@ -35,6 +35,7 @@ struct TreeOp {
     int32_t mult;         // kind 1: multiplier column
     int32_t last;         // 1: this message completes the root -> root reduction instead of a store
     int32_t sib[2];       // last: slots of the root's other messages (-1 = none)
+    int32_t dep_prev;     // 1: an operand is the message written by the previous op of the schedule
 };
 
 struct RateInfo {
@@ -245,8 +246,12 @@ __global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* t
 constexpr int NS = 5;   // ring stages
 constexpr int PF = 3;   // prefetch distance in chunks
 
+constexpr int MAX_OPS = 96;  // branch ops staged in shared memory (trees with more branches are rejected at create)
+
 struct TreeSmem {
     unsigned long long full[NS], empty[NS], epi;
+    long long moff[MAX_OPS];   // per item: matrix offset of every shared-matrix op of this walker (negative = identity)
+    TreeOp ops[MAX_OPS];       // the branch schedule
     double rowdot[2][TM];
     double row_a[TM], row_d[TM];
     int32_t row_g[TM];      // generation-grid index gi of the row (rate ops); -1 = identity / padding row
@@ -311,9 +316,11 @@ __device__ __forceinline__ void issue_V(const TreeParams& p, unsigned char* ring
 
 // acc += (V0 .* V1 .* w)[64 x K] * P[rows x K]^T for this warp's 16 rows x NTW n-tiles; chunks g0 .. g0+nchunks-1 of
 // the ring.  Lane 0 of warp 0 keeps the ring PF chunks ahead.
+// cross: 0 = nothing follows in the ring, 1 = the next unit's P tiles may be issued ahead, 2 = its P and V tiles.
 template <int NTW, int NSRC, bool SCALED>
 __device__ __forceinline__ void gemm_unit(double (&acc)[2][NTW][2], const TreeParams& p, unsigned char* ring, TreeSmem* ts,
-                                          const UnitDesc& u, int nchunks, unsigned g0, double w0, double w1) {
+                                          const UnitDesc& u, int nchunks, unsigned g0, double w0, double w1,
+                                          const UnitDesc& un, int cross, unsigned epi_n) {
     using Cfg = TileCfg<NTW>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp & 3, wn = warp >> 2;
@@ -324,13 +331,24 @@ __device__ __forceinline__ void gemm_unit(double (&acc)[2][NTW][2], const TreePa
     const int b_base = 2 * Cfg::V_BYTES + (wn * NTW * 8 + x) * 128 + h;
     for (int c = 0; c < nchunks; ++c) {
         const unsigned g = g0 + c;
-        if (p.debug != 2 && threadIdx.x == 0 && c + PF < nchunks) {
-            issue_P<NTW>(p, ring, ts, u, c + PF, g + PF);
-            issue_V<NTW>(p, ring, ts, u, c + PF, g + PF);
+        if (p.debug < 2 && threadIdx.x == 0) {
+            if (c + PF < nchunks) {
+                issue_P<NTW>(p, ring, ts, u, c + PF, g + PF);
+                issue_V<NTW>(p, ring, ts, u, c + PF, g + PF);
+            } else if (cross) {
+                // keep the ring full across the branch boundary: first chunks of the next unit
+                const int cn = c + PF - nchunks;
+                issue_P<NTW>(p, ring, ts, un, cn, g + PF);
+                if (cross == 2) {
+                    // its operands were published by an epilogue that every warp has normally long finished
+                    if (cn == 0 && epi_n > 0) mbar_wait(&ts->epi, (epi_n - 1) & 1u);
+                    issue_V<NTW>(p, ring, ts, un, cn, g + PF);
+                }
+            }
         }
         __syncwarp();
         const unsigned s = g % NS;
-        if (p.debug != 2) mbar_wait(&ts->full[s], (g / NS) & 1u);
+        if (p.debug < 2) mbar_wait(&ts->full[s], (g / NS) & 1u);
         const unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
         if (p.debug != 1)
 #pragma unroll
@@ -353,7 +371,7 @@ __device__ __forceinline__ void gemm_unit(double (&acc)[2][NTW][2], const TreePa
             }
         }
         __syncwarp();
-        if (p.debug != 2 && lane == 0) mbar_arrive(&ts->empty[s]);
+        if (p.debug < 2 && lane == 0) mbar_arrive(&ts->empty[s]);
     }
 }
 
@@ -385,6 +403,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
     }
     __syncthreads();
 
+    for (int i = threadIdx.x; i < p.n_ops; i += NTHREADS) ts->ops[i] = p.ops[i];
+
     unsigned g = 0;       // chunks consumed so far (ring position), identical in every thread
     unsigned epi_n = 0;   // epilogues completed so far (phase of ts->epi)
 
@@ -403,9 +423,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
         }
         const int row0 = tile * TM;
         bool prologue_issued = false;   // chunks 0..PF-1 of the coming unit are already in flight
+        // one round trip for all matrix offsets of this walker instead of a dependent global load per branch
+        for (int i = threadIdx.x; i < p.n_ops; i += NTHREADS) {
+            const TreeOp& o = ts->ops[i];
+            ts->moff[i] = (o.kind == 0) ? p.mat_off[(size_t)w * p.n_mat + o.key] : 0;
+        }
+        __syncthreads();
 
         for (int oi = 0; oi < p.n_ops; ++oi) {
-            const TreeOp op = p.ops[oi];
+            const TreeOp op = ts->ops[oi];
             const double* V0 = (op.src_kind[0] == 0) ? p.E + (size_t)op.src[0] * p.E_leaf_stride + (size_t)row0 * Fp
                                                      : my_scratch + (size_t)op.src[0] * TM * Fp;
             const double* V1 = (op.nsrc == 2) ? my_scratch + (size_t)op.src[1] * TM * Fp : V0;
@@ -422,7 +448,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
             bool identity = false;
             int64_t moff = 0;
             if (op.kind == 0) {
-                moff = p.mat_off[(size_t)w * p.n_mat + op.key];
+                moff = ts->moff[oi];
                 identity = moff < 0;  // N*t below the first generation: P = I, Y = V exactly (transition_data_2d.py:184-187)
             } else {
                 ri = &p.rate[(size_t)w * p.n_rate + op.key];
@@ -468,6 +494,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                 const double2* a2 = reinterpret_cast<const double2*>(V0);
                 const double2* b2 = reinterpret_cast<const double2*>(V1);
                 double2* d2 = reinterpret_cast<double2*>(dst);
+                if (p.debug < 3)
                 for (int base = 0; base < n2; base += NTHREADS * 4) {
                     double2 v[4], q2[4], r2[4];
 #pragma unroll
@@ -505,15 +532,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
 #pragma unroll
                 for (int j = 0; j < NTW; ++j) { acc[0][j][0] = acc[0][j][1] = acc[1][j][0] = acc[1][j][1] = 0.0; }
 
+                // ---- the GEMM unit that follows this one in the ring (next pass of this branch, or the next branch) ----
+                UnitDesc un;
+                un.nsrc = 1; un.v_is_E = 1; un.v0_row = 0; un.v1_row = 0; un.p_row = 0;
+                bool have_next = false, next_v_early = false;
+                if (nchunks >= PF) {
+                    if (pass + 1 < npass) {
+                        if (op.kind == 0 && !identity) {
+                            un = u; un.p_row = (int)(moff / Fp) + (t0 + 2 * NTW) * 8;
+                            have_next = true; next_v_early = true;   // same operands, nothing writes them
+                        }
+                    } else if (oi + 1 < p.n_ops) {
+                        const TreeOp& nx = ts->ops[oi + 1];
+                        const long long off = ts->moff[oi + 1];
+                        if (nx.kind == 0 && off >= 0) {
+                            un.nsrc = nx.nsrc;
+                            un.v_is_E = (nx.src_kind[0] == 0);
+                            un.v0_row = un.v_is_E ? nx.src[0] * p.R_pad + row0 : scratch_row0 + nx.src[0] * TM;
+                            un.v1_row = scratch_row0 + nx.src[1] * TM;
+                            un.p_row = (int)(off / Fp);
+                            have_next = true;
+                            next_v_early = !nx.dep_prev;   // otherwise an operand is the message this epilogue writes
+                        }
+                    }
+                }
+
                 if (op.kind == 0) {
                     if (!identity) {
                         u.p_row = (int)(moff / Fp) + t0 * 8;
-                        if (p.debug != 2 && !prologue_issued && threadIdx.x == 0) {
+                        if (p.debug < 2 && !prologue_issued && threadIdx.x == 0) {
                             if (epi_n > 0) mbar_wait(&ts->epi, (epi_n - 1) & 1u);
                             for (int c = 0; c < PF && c < nchunks; ++c) { issue_P<NTW>(p, ring, ts, u, c, g + c); issue_V<NTW>(p, ring, ts, u, c, g + c); }
                         }
-                        if (op.nsrc == 2) gemm_unit<NTW, 2, false>(acc, p, ring, ts, u, nchunks, g, 1.0, 1.0);
-                        else gemm_unit<NTW, 1, false>(acc, p, ring, ts, u, nchunks, g, 1.0, 1.0);
+                        const int cross = have_next ? (next_v_early ? 2 : 1) : 0;
+                        if (op.nsrc == 2) gemm_unit<NTW, 2, false>(acc, p, ring, ts, u, nchunks, g, 1.0, 1.0, un, cross, epi_n);
+                        else gemm_unit<NTW, 1, false>(acc, p, ring, ts, u, nchunks, g, 1.0, 1.0, un, cross, epi_n);
                         g += nchunks;
                         prologue_issued = false;
                     }
@@ -525,42 +578,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                         const double w0 = (g0r >= 0) ? ((seg == g0r - 1 ? ts->row_a[rA] : 0.0) + (seg == g0r ? ts->row_d[rA] : 0.0)) : 0.0;
                         const double w1 = (g1r >= 0) ? ((seg == g1r - 1 ? ts->row_a[rA + 8] : 0.0) + (seg == g1r ? ts->row_d[rA + 8] : 0.0)) : 0.0;
                         u.p_row = (int)(ri->off / Fp) + (seg - ri->gbase) * blk_rows + t0 * 8;
-                        if (p.debug != 2 && threadIdx.x == 0) {
+                        if (p.debug < 2 && threadIdx.x == 0) {
                             if (epi_n > 0) mbar_wait(&ts->epi, (epi_n - 1) & 1u);
                             for (int c = 0; c < PF && c < nchunks; ++c) { issue_P<NTW>(p, ring, ts, u, c, g + c); issue_V<NTW>(p, ring, ts, u, c, g + c); }
                         }
-                        if (op.nsrc == 2) gemm_unit<NTW, 2, true>(acc, p, ring, ts, u, nchunks, g, w0, w1);
-                        else gemm_unit<NTW, 1, true>(acc, p, ring, ts, u, nchunks, g, w0, w1);
+                        if (op.nsrc == 2) gemm_unit<NTW, 2, true>(acc, p, ring, ts, u, nchunks, g, w0, w1, un, 0, epi_n);
+                        else gemm_unit<NTW, 1, true>(acc, p, ring, ts, u, nchunks, g, w0, w1, un, 0, epi_n);
                         g += nchunks;
                     }
                     prologue_issued = false;
                 }
 
-                // ---- start the first chunks of the next GEMM unit under this epilogue ----
-                // P tiles right away; V tiles of a following pass too (same operands); V tiles of the next branch once
-                // every warp has published its part of this epilogue (they may be the message being written now).
-                UnitDesc un;
-                bool have_next = false, next_same_op = false;
-                if (pass + 1 < npass) {
-                    if (op.kind == 0 && !identity) { un = u; un.p_row = (int)(moff / Fp) + (t0 + 2 * NTW) * 8; have_next = true; next_same_op = true; }
-                } else if (oi + 1 < p.n_ops) {
-                    const TreeOp nx = p.ops[oi + 1];
-                    if (nx.kind == 0) {
-                        const int64_t off = p.mat_off[(size_t)w * p.n_mat + nx.key];
-                        if (off >= 0) {
-                            un.nsrc = nx.nsrc;
-                            un.v_is_E = (nx.src_kind[0] == 0);
-                            un.v0_row = un.v_is_E ? nx.src[0] * p.R_pad + row0 : scratch_row0 + nx.src[0] * TM;
-                            un.v1_row = scratch_row0 + nx.src[1] * TM;
-                            un.p_row = (int)(off / Fp);
-                            have_next = true;
-                        }
-                    }
-                }
-                if (p.debug != 2 && have_next && threadIdx.x == 0) {
-                    for (int c = 0; c < PF && c < nchunks; ++c) issue_P<NTW>(p, ring, ts, un, c, g + c);
-                    if (next_same_op || un.v_is_E) {
-                        for (int c = 0; c < PF && c < nchunks; ++c) issue_V<NTW>(p, ring, ts, un, c, g + c);
+                // Units that could not run ahead inside the main loop (age-scaled branches, identity-skipped GEMMs): start the
+                // next unit's tiles here, under the epilogue.
+                const bool issued_in_loop = (op.kind == 0 && !identity);
+                if (p.debug < 2 && have_next && !issued_in_loop && threadIdx.x == 0) {
+                    for (int c = 0; c < PF; ++c) issue_P<NTW>(p, ring, ts, un, c, g + c);
+                    if (next_v_early) {
+                        if (epi_n > 0) mbar_wait(&ts->epi, (epi_n - 1) & 1u);
+                        for (int c = 0; c < PF; ++c) issue_V<NTW>(p, ring, ts, un, c, g + c);
                     }
                 }
                 __syncwarp();
@@ -568,7 +604,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                 // ---------------- epilogue ----------------
                 double dot0 = 0.0, dot1 = 0.0;
                 const bool plain_store = (op.kind == 0 && !identity && p.Yout == nullptr && op.first && !op.last);
-                if (plain_store) {
+                if (plain_store && p.debug >= 4) {
+                    // measurement only: no stores
+                } else if (plain_store) {
                     // the common case: the message is just stored (two base pointers, immediate offsets)
                     double* d0 = dst + (size_t)rA * Fp + (t0 + wn * NTW) * 8 + 2 * (lane & 3);
                     double* d1 = d0 + (size_t)8 * Fp;
@@ -658,9 +696,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                     ++epi_n;
                 }
                 if (have_next) {
-                    if (p.debug != 2 && !(next_same_op || un.v_is_E) && threadIdx.x == 0) {
+                    if (p.debug < 2 && !next_v_early && threadIdx.x == 0) {
+                        // the next branch reads the message just written: wait until every warp has published it
                         mbar_wait(&ts->epi, (epi_n - 1) & 1u);
-                        for (int c = 0; c < PF && c < nchunks; ++c) issue_V<NTW>(p, ring, ts, un, c, g + c);
+                        for (int c = 0; c < PF; ++c) issue_V<NTW>(p, ring, ts, un, c, g + c);
                     }
                     prologue_issued = true;
                 }
@@ -825,6 +864,10 @@ __global__ void unpad_rows_kernel(const double* __restrict__ src, double* __rest
     dst[idx] = src[(size_t)r * Fp + f];
 }
 
+__global__ void fill_nan_kernel(double* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
 // stat[widx[i]][0..F) -> dst[i][0..Fp) zero padded
 __global__ void gather_pad_kernel(const double* __restrict__ src, const int32_t* __restrict__ widx, double* __restrict__ dst,
                                   int n, int F, int Fp) {

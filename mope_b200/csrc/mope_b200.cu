@@ -100,7 +100,7 @@ struct mope_ctx {
     int max_slots = 0, max_tiles = 0, max_asc2 = 0;
     // host staging (pinned, grow-only)
     char* pinned = nullptr;
-    size_t pinned_cap = 0;
+    size_t pinned_cap = 0, pinned_off = 0;
     // small library-owned device scratch for the operator-level entry points
     char* opbuf = nullptr;
     size_t opbuf_cap = 0;
@@ -124,6 +124,20 @@ int ensure_pinned(mope_ctx* c, size_t bytes) {
     size_t cap = align_up(bytes + bytes / 4, 1 << 16);
     CUDA_TRY(cudaMallocHost(&c->pinned, cap));
     c->pinned_cap = cap;
+    return 0;
+}
+
+// Pinned staging as a ring: consecutive asynchronous calls take consecutive pieces; the stream is only synchronised
+// when the ring wraps (everything staged before is consumed by then) or has to grow.
+int stage_alloc(mope_ctx* c, size_t bytes, cudaStream_t st, char** out) {
+    bytes = align_up(std::max<size_t>(bytes, 64), 256);
+    if (c->pinned_off + bytes > c->pinned_cap) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (int rc = ensure_pinned(c, std::max(bytes * 4, (size_t)8 << 20))) return rc;
+        c->pinned_off = 0;
+    }
+    *out = c->pinned + c->pinned_off;
+    c->pinned_off += bytes;
     return 0;
 }
 
@@ -214,13 +228,43 @@ int validate(const mope_tables_desc* t, const mope_model_desc* m) {
 int compile_schedule(const mope_pedigree_desc& pd, const std::vector<int>& fixed_key_of_branch,
                      const std::vector<int>& rate_key_of_branch, Pedigree& out) {
     const int nb = pd.n_branches, root = pd.n_branches;
-    std::vector<int> nchild(nb + 1, 0), seen(nb + 1, 0);
+    if (nb > MAX_OPS) return fail(MOPE_E_INVALID, "tree has %d branches; this build stages at most %d", nb, MAX_OPS);
+    std::vector<int> nchild(nb + 1, 0), seen(nb + 1, 0), done_children(nb + 1, 0);
     std::vector<std::vector<int>> pending(nb + 1);  // message slots waiting at a node
     for (int b = 0; b < nb; ++b) nchild[pd.br_parent[b]]++;
+
+    // Execution order: any topological order gives bit-identical results (every message has fixed operands).
+    // Postorder makes most internal branches consume the message written by the op right before them, which
+    // stalls the copy pipeline on that epilogue; so among the ready branches prefer the earliest (postorder)
+    // one that does not depend on the op just scheduled.
+    std::vector<int> order;
+    {
+        std::vector<char> scheduled(nb, 0);
+        int prev = -1;
+        for (int n = 0; n < nb; ++n) {
+            int pick = -1, fallback = -1;
+            for (int b = 0; b < nb; ++b) {
+                if (scheduled[b] || done_children[b] != nchild[b]) continue;   // not ready
+                if (fallback < 0) fallback = b;
+                const bool dep = (prev >= 0 && pd.br_parent[prev] == b);
+                if (!dep) { pick = b; break; }
+            }
+            if (pick < 0) pick = fallback;
+            if (pick < 0) return fail(MOPE_E_INVALID, "branch table is not a tree");
+            // keep the walk close to postorder: do not start a new leaf while an internal branch further left is
+            // ready and independent (the scan above already returns the left-most candidate)
+            scheduled[pick] = 1;
+            done_children[pd.br_parent[pick]]++;
+            order.push_back(pick);
+            prev = pick;
+        }
+    }
+
     std::vector<int> free_slots;
     int n_slots = 0;
+    int prev_dst = -1;
     out.ops_h.clear();
-    for (int b = 0; b < nb; ++b) {
+    for (int b : order) {
         TreeOp op{};
         const int par = pd.br_parent[b];
         op.sib[0] = op.sib[1] = -1;
@@ -231,11 +275,14 @@ int compile_schedule(const mope_pedigree_desc& pd, const std::vector<int>& fixed
             op.src[0] = pd.br_leaf[b];
             op.src_kind[1] = 0;
             op.src[1] = 0;
+            op.dep_prev = 0;
         } else {
             if (nchild[b] == 0 || pending[b].empty()) return fail(MOPE_E_INVALID, "internal node %d has no children", b);
             op.nsrc = (int)pending[b].size();
             for (int i = 0; i < op.nsrc; ++i) { op.src_kind[i] = 1; op.src[i] = pending[b][i]; }
             if (op.nsrc == 1) { op.src_kind[1] = 1; op.src[1] = op.src[0]; }
+            op.dep_prev = 0;
+            for (int i = 0; i < op.nsrc; ++i) if (op.src[i] == prev_dst) op.dep_prev = 1;
         }
         seen[par]++;
         const bool completes_root = (par == root && seen[par] == nchild[par]);
@@ -245,13 +292,12 @@ int compile_schedule(const mope_pedigree_desc& pd, const std::vector<int>& fixed
             op.first = 1;
             for (size_t i = 0; i < pending[par].size(); ++i) op.sib[i] = pending[par][i];
         } else if (pending[par].size() < 2) {
-            int s;
-            if (!free_slots.empty()) { s = free_slots.back(); free_slots.pop_back(); }
-            else s = n_slots++;
-            // never hand out a slot this op is still reading
-            op.dst = s;
+            int sl;
+            if (!free_slots.empty()) { sl = free_slots.front(); free_slots.erase(free_slots.begin()); }  // oldest first
+            else sl = n_slots++;
+            op.dst = sl;
             op.first = 1;
-            pending[par].push_back(s);
+            pending[par].push_back(sl);
         } else {
             op.dst = pending[par][1];
             op.first = 0;
@@ -259,6 +305,7 @@ int compile_schedule(const mope_pedigree_desc& pd, const std::vector<int>& fixed
         if (pd.br_mult[b] >= 0) { op.kind = 1; op.key = rate_key_of_branch[b]; op.mult = pd.br_mult[b]; }
         else { op.kind = 0; op.key = fixed_key_of_branch[b]; op.mult = -1; }
         out.ops_h.push_back(op);
+        prev_dst = op.dst;
         // the operands are free once this op has run
         if (pd.br_leaf[b] < 0) for (int sl : pending[b]) free_slots.push_back(sl);
     }
@@ -588,17 +635,10 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
     CUtensorMap tmapS;
     if (int rc = make_tmap(&tmapS, scratch, (uint64_t)c->num_sms * c->max_slots * TM, Fp, TM)) return rc;
 
-    // outputs of invalid walkers: NaN (the host wrapper raises ValueError like the reference)
-    {
-        // fill everything with NaN once; valid walkers overwrite
-        std::vector<double> nanv(W, std::numeric_limits<double>::quiet_NaN());
-        size_t need = (size_t)W * sizeof(double);
-        if (ensure_pinned(c, need)) return MOPE_E_CUDA;
-        // (pinned buffer is re-used below; this copy is ordered on the stream before any kernel)
-        std::memcpy(c->pinned, nanv.data(), need);
-        CUDA_TRY(cudaMemcpyAsync(d_out_ll, c->pinned, need, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-    }
+    // outputs of invalid walkers: NaN (the host wrapper raises ValueError like the reference); valid walkers overwrite
+    fill_nan_kernel<<<(W + 255) / 256, 256, 0, st>>>(d_out_ll, W);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
 
     c->last_gemm_ops = 0;
     c->last_identity_ops = 0;
@@ -656,9 +696,8 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
                      sz_stat = (size_t)Wc * Fp * sizeof(double);
         const size_t stage_bytes = align_up(sz_jobs, 64) + align_up(sz_mo, 64) + align_up(sz_rate, 64) + align_up(sz_widx, 64) +
                                    (stat_on_device ? 0 : align_up(sz_stat, 64));
-        CUDA_TRY(cudaStreamSynchronize(st));  // previous chunk's staging is consumed
-        if (ensure_pinned(c, stage_bytes)) return MOPE_E_CUDA;
-        char* hp = c->pinned;
+        char* hp = nullptr;
+        if (int rc = stage_alloc(c, stage_bytes, st, &hp)) return rc;
         auto push = [&](void* dptr, const void* src, size_t bytes) -> int {
             if (bytes == 0) return 0;
             std::memcpy(hp, src, bytes);
@@ -762,9 +801,8 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
     if (!out_on_device) {
         // device -> host
         size_t need = (size_t)W * sizeof(double) * (1 + (out_root_ll ? c->n_ped : 0) + (out_log_asc ? c->asc_total : 0));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        if (ensure_pinned(c, need)) return MOPE_E_CUDA;
-        char* hp = c->pinned;
+        char* hp = nullptr;
+        if (int rc = stage_alloc(c, need, st, &hp)) return rc;
         CUDA_TRY(cudaMemcpyAsync(hp, d_out_ll, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, st));
         char* hp_root = hp + (size_t)W * sizeof(double);
         char* hp_asc = hp_root + (out_root_ll ? (size_t)W * c->n_ped * sizeof(double) : 0);
@@ -1231,7 +1269,7 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
     CUDA_TRY(cudaMemcpyAsync(P.rate, &ri, sizeof(RateInfo), cudaMemcpyHostToDevice, st));
     TreeOp op{};
     op.nsrc = 1; op.src_kind[0] = 0; op.src[0] = 0; op.src_kind[1] = 0; op.src[1] = 0; op.dst = -1; op.first = 1;
-    op.kind = (kind == 1) ? 1 : 0; op.key = 0; op.mult = 0; op.last = 0; op.sib[0] = op.sib[1] = -1;
+    op.kind = (kind == 1) ? 1 : 0; op.key = 0; op.mult = 0; op.last = 0; op.sib[0] = op.sib[1] = -1; op.dep_prev = 0;
     CUDA_TRY(cudaMemcpyAsync(P.op, &op, sizeof(TreeOp), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(P.raw, child, (size_t)n_rows * F * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(P.par, parent, (size_t)n_rows * F * sizeof(double), cudaMemcpyHostToDevice, st));

@@ -154,6 +154,35 @@ class Engine:
         _lib.check(rc, "mope_b200_eval")
         return (ll, status, root, lasc) if want_components else (ll, status)
 
+    def loglike_pipelined(self, params: np.ndarray, stat_fn, n_chunks: int = 4):
+        """End-to-end evaluation with the host-side root distributions overlapped with the device work: the batch is
+        cut into `n_chunks`; while the device evaluates chunk i (enqueued, not awaited) the host computes stat_fn for
+        chunk i+1.  One device->host read of the log-likelihoods at the end.  Returns (ll, status)."""
+        torch = self.torch
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        W = params.shape[0]
+        dev = "cuda:%d" % self.device
+        if getattr(self, "_pipe_W", 0) < W:
+            self._stat_pin = torch.empty((W, self.F), dtype=torch.float64, pin_memory=True)
+            self._stat_dev = torch.empty((W, self.F), dtype=torch.float64, device=dev)
+            self._out_dev = torch.empty(W, dtype=torch.float64, device=dev)
+            self._out_pin = torch.empty(W, dtype=torch.float64, pin_memory=True)
+            self._pipe_W = W
+        status = np.zeros(W, dtype=np.int32)
+        bounds = np.linspace(0, W, min(n_chunks, max(W, 1)) + 1).astype(int)
+        stat_pin_np = self._stat_pin.numpy()
+        with torch.cuda.device(self.device):
+            for i in range(len(bounds) - 1):
+                lo, hi = int(bounds[i]), int(bounds[i + 1])
+                if hi <= lo:
+                    continue
+                stat_pin_np[lo:hi] = stat_fn(params[lo:hi])
+                self._stat_dev[lo:hi].copy_(self._stat_pin[lo:hi], non_blocking=True)
+                status[lo:hi] = self.loglike_device(params[lo:hi], self._stat_dev[lo:hi], self._out_dev[lo:hi])
+            self._out_pin[:W].copy_(self._out_dev[:W], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return self._out_pin[:W].numpy().copy(), status
+
     def loglike_device(self, params_host: np.ndarray, stat_dev, out_dev):
         """Device-resident variant: stat_dev [W, F] and out_dev [W] are CUDA float64 tensors.  Enqueue only."""
         torch = self.torch

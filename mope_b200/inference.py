@@ -188,8 +188,11 @@ class Inference(object):
         X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
         if X.shape[1] != self.ndim:
             raise ValueError("expected parameter vectors of length {}".format(self.ndim))
-        stat = self.stationary_distributions(X)
-        ll, status = self.engine.loglike(X, stat)
+        if X.shape[0] >= 32:
+            # large batches: root distributions (host, SciPy) for the next chunk overlap the device work of the current one
+            ll, status = self.engine.loglike_pipelined(X, self.stationary_distributions)
+        else:
+            ll, status = self.engine.loglike(X, self.stationary_distributions(X))
         if raise_on_error and status.any():
             w = int(np.nonzero(status)[0][0])
             raise OutOfTableError("walker {}: {}".format(w, status_message(int(status[w]))))
