@@ -391,6 +391,18 @@ int launch_tree_t(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) 
     return 0;
 }
 
+// one warp per matrix row; warps per block bounded by the 48 KB default dynamic shared memory (Fp doubles per warp)
+int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d_pool, cudaStream_t st) {
+    const int Fp = c->Fp;
+    const int wpb = std::max(1, std::min(8, (int)((48 * 1024) / ((size_t)Fp * sizeof(double)))));
+    const long long rows = (long long)n_jobs * Fp;
+    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+    interp_kernel<<<grid, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, c->F, Fp);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
 int launch_tree(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) {
     switch (c->tree_variant) {
         case 5: return launch_tree_t<5>(c, tp, grid, st);
@@ -727,15 +739,8 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
 
         // interpolation
         if (n_blocks > 0) {
-            const int wpb = 8;
-            const long long rows = (long long)n_blocks * Fp;
-            const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-            {
-                ScopedTimer timer(c, st, &c->ev_interp);
-                interp_kernel<<<grid, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_jobs, (int)n_blocks, c->tables, d_pool, F, Fp);
-            }
-            CUDA_TRY(cudaGetLastError());
-            c->launches++;
+            ScopedTimer timer(c, st, &c->ev_interp);
+            if (int rc = launch_interp(c, d_jobs, n_blocks, d_pool, st)) return rc;
         }
 
         CUtensorMap tmapP;
@@ -1147,13 +1152,11 @@ int mope_b200_transition_matrix(mope_ctx* c, int bottleneck, double x, double sc
     double* d_blk = reinterpret_cast<double*>(c->opbuf + align_up(sizeof(InterpJob), 256));
     double* d_out = d_blk + blk;
     CUDA_TRY(cudaMemcpyAsync(d_job, po.jobs.data(), sizeof(InterpJob), cudaMemcpyHostToDevice, st));
-    const int wpb = 8;
-    interp_kernel<<<(Fp + wpb - 1) / wpb, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_job, 1, c->tables, d_blk, F, Fp);
-    CUDA_TRY(cudaGetLastError());
+    if (int rc = launch_interp(c, d_job, 1, d_blk, st)) return rc;
     const long long total = (long long)F * F;
     unpad_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_blk, d_out, F, F, Fp);
     CUDA_TRY(cudaGetLastError());
-    c->launches += 2;
+    c->launches += 1;
     CUDA_TRY(cudaMemcpyAsync(out_P, d_out, (size_t)F * F * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
@@ -1283,10 +1286,7 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
     pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P.raw, P.E, n_rows, F, Fp, R_pad);
     CUDA_TRY(cudaGetLastError());
     if (n_blocks) {
-        const int wpb = 8;
-        const long long rows = (long long)n_blocks * Fp;
-        interp_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(P.jobs, (int)n_blocks, c->tables, P.pool, F, Fp);
-        CUDA_TRY(cudaGetLastError());
+        if (int rc = launch_interp(c, P.jobs, n_blocks, P.pool, st)) return rc;
     }
     TreeParams tp{};
     if (int rc = make_tmap(&tp.tmapE, P.E, (uint64_t)R_pad, Fp, TM)) return rc;

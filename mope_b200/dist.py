@@ -1,0 +1,154 @@
+"""Multi-GPU sharding of the log-likelihood: one process per GPU, torch.distributed for the plumbing.
+
+The path shards two ways, both without any exchange inside the pruning pass:
+
+* by WALKER -- what the reference's multiprocessing/MPI pool does (mope/inference.py:1194-1244): every rank holds
+  the tables and the whole dataset and evaluates its slice of the ensemble.  No data-path collective; an all-gather
+  of the per-walker results only if every rank needs the whole vector.
+* by LOCUS (large datasets) -- rows are independent given a walker's parameters.  Families are partitioned over the
+  ranks (a family's loci, its ascertainment pseudo-rows and its count/Poisson terms stay together), every rank
+  evaluates ALL walkers on its rows, and the per-walker partial sums are combined with ONE all-reduce(sum) of
+  W float64 values (NCCL over NVLink on GPUs, gloo in the CPU tests).
+
+The prior box depends on the multiplier (age) range of ALL families (inference.py:154-258), so locus shards are
+built with the global range (`mult_bounds`).
+"""
+from __future__ import annotations
+
+import io
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import model as _model
+
+
+def walker_slice(n_walkers: int, world: int, rank: int) -> slice:
+    """Contiguous, balanced slice of the ensemble owned by `rank`."""
+    bounds = np.linspace(0, n_walkers, world + 1).astype(int)
+    return slice(int(bounds[rank]), int(bounds[rank + 1]))
+
+
+def partition_families(family_of_locus: np.ndarray, families: np.ndarray, world: int) -> List[np.ndarray]:
+    """Split the family list into `world` contiguous groups with balanced row counts (loci + 2 ascertainment rows).
+    Every family of the ages table lands in exactly one group -- also families without any locus, whose Poisson
+    term still counts (inference.py:1113-1129)."""
+    rows = np.array([(family_of_locus == f).sum() + 2 for f in families], dtype=np.float64)
+    cum = np.cumsum(rows)
+    total = cum[-1] if len(cum) else 0.0
+    groups, start = [], 0
+    for r in range(world):
+        target = total * (r + 1) / world
+        end = int(np.searchsorted(cum, target - 1e-9, side="left")) + 1 if r < world - 1 else len(families)
+        end = max(end, start)
+        end = min(end, len(families))
+        groups.append(np.asarray(families[start:end]))
+        start = end
+    return groups
+
+
+def shard_pedigree_text(data_tsv: str, ages_tsv: str, world: int, rank: int) -> Tuple[str, str]:
+    """The rows of one pedigree's data / ages tables that belong to `rank` under the family partition."""
+    data = _model.read_table(data_tsv, True)
+    ages = _model.read_table(ages_tsv, True)
+    groups = partition_families(data["family"].values, ages["family"].values, world)
+    mine = set(groups[rank].tolist())
+    d = data[data["family"].isin(mine)]
+    a = ages[ages["family"].isin(mine)]
+    dbuf, abuf = io.StringIO(), io.StringIO()
+    d.to_csv(dbuf, sep="\t", index=False, na_rep="NA")
+    a.to_csv(abuf, sep="\t", index=False, na_rep="NA")
+    return dbuf.getvalue(), abuf.getvalue()
+
+
+def global_mult_bounds(tree_strs: Sequence[str], ages_tsvs: Sequence[str]):
+    """min/max multiplier per variable name over ALL families of all pedigrees (Inference.get_min_max_mults)."""
+    from . import newick
+    mins, maxes = {}, {}
+    for tree_str, ages_tsv in zip(tree_strs, ages_tsvs):
+        ages = _model.read_table(ages_tsv, True)
+        tree = newick.loads(tree_str)[0]
+        for nd in tree.postorder():
+            if nd is tree:
+                continue
+            v, m = nd.varname, nd.multipliername
+            lo, hi = (np.nanmin(ages[m].values), np.nanmax(ages[m].values)) if m else (1, 1)
+            mins.setdefault(v, []).append(lo)
+            maxes.setdefault(v, []).append(hi)
+    names = sorted(mins)
+    return names, np.array([min(mins[v]) for v in names]), np.array([max(maxes[v]) for v in names])
+
+
+def build_locus_sharded(data_tsvs: Sequence[str], tree_strs: Sequence[str], ages_tsvs: Sequence[str], tables, rank: int, world: int,
+                        **kw):
+    """An Inference over this rank's families (texts in, as `_inputs_are_text`), with the GLOBAL prior box."""
+    from .inference import Inference
+    _names, lo, hi = global_mult_bounds(tree_strs, ages_tsvs)
+    local = [shard_pedigree_text(d, a, world, rank) for d, a in zip(data_tsvs, ages_tsvs)]
+    return Inference([l[0] for l in local], list(tree_strs), [l[1] for l in local], tables, _inputs_are_text=True,
+                     mult_bounds=(lo, hi), **kw)
+
+
+def _dist_device(group=None):
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend(group)
+    return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+
+def allreduce_partials(ll_partial: np.ndarray, status: Optional[np.ndarray] = None, group=None):
+    """Sum of the per-walker partial log-likelihoods over the ranks (the path's only collective): all-reduce(sum)
+    of W float64 values; walker status bits are OR-ed (max) the same way."""
+    import torch
+    import torch.distributed as dist
+    dev = _dist_device(group)
+    t = torch.as_tensor(np.ascontiguousarray(ll_partial, dtype=np.float64)).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    out = t.cpu().numpy()
+    if status is None:
+        return out
+    s = torch.as_tensor(np.ascontiguousarray(status, dtype=np.int32)).to(dev)
+    # bitwise OR over ranks, bit by bit (MAX on each bit plane keeps it exact on every backend)
+    acc = torch.zeros_like(s)
+    for bit in range(8):
+        plane = (s >> bit) & 1
+        dist.all_reduce(plane, op=dist.ReduceOp.MAX, group=group)
+        acc |= plane << bit
+    st = acc.cpu().numpy()
+    out = np.where(st != 0, np.nan, out)
+    return out, st
+
+
+def allgather_walkers(ll_local: np.ndarray, n_walkers: int, group=None) -> np.ndarray:
+    """Walker sharding: concatenate the ranks' slices (padded all-gather; slices follow walker_slice)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = _dist_device(group)
+    width = max(walker_slice(n_walkers, world, r).stop - walker_slice(n_walkers, world, r).start for r in range(world))
+    buf = torch.zeros(width, dtype=torch.float64, device=dev)
+    buf[: ll_local.shape[0]] = torch.as_tensor(np.ascontiguousarray(ll_local, dtype=np.float64)).to(dev)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    out = np.empty(n_walkers)
+    for r in range(world):
+        sl = walker_slice(n_walkers, world, r)
+        out[sl] = parts[r][: sl.stop - sl.start].cpu().numpy()
+    return out
+
+
+def loglike_walker_sharded(inf, X: np.ndarray, group=None) -> np.ndarray:
+    """Every rank evaluates its slice of X; all ranks return the full vector."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sl = walker_slice(X.shape[0], world, rank)
+    local = inf.loglike_batch(X[sl], raise_on_error=False) if sl.stop > sl.start else np.zeros(0)
+    return allgather_walkers(local, X.shape[0], group)
+
+
+def loglike_locus_sharded(inf_local, X: np.ndarray, group=None):
+    """`inf_local` holds this rank's families (build_locus_sharded); returns the full-data log-likelihood of every
+    walker on all ranks."""
+    ll, status = inf_local.loglike_batch(X, raise_on_error=False, return_status=True)
+    ll = np.where(status != 0, 0.0, ll)
+    return allreduce_partials(ll, status, group)

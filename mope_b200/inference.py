@@ -52,7 +52,7 @@ class Inference(object):
                  transition_copy=None, transition_buf=None, transition_shape=None, print_debug=False,
                  log_unif_drift=False, inverse_bot_priors=False, post_is_prior=False, lower_drift_limit=1e-3,
                  upper_drift_limit=3, min_phred_score=None, selection_model=False, device=0, workspace_bytes=None,
-                 _inputs_are_text=False):
+                 _inputs_are_text=False, mult_bounds=None):
         if selection_model:
             raise NotImplementedError("the selection model is outside the GPU log-likelihood path")
         if data_are_freqs:
@@ -131,7 +131,9 @@ class Inference(object):
             # the reference raises at the first evaluation (likelihoods.py:381-382)
             warnings.warn("tree has bottleneck branches but no bottleneck tables were given")
 
-        self.min_mults, self.max_mults = self.get_min_max_mults()
+        # (locus-sharded runs pass the multiplier range of ALL families so that every shard has the same prior box)
+        self.min_mults, self.max_mults = self.get_min_max_mults() if mult_bounds is None else \
+            (np.asarray(mult_bounds[0], dtype=np.float64), np.asarray(mult_bounds[1], dtype=np.float64))
         self.header = "\t".join(["ll"] + [v + "_l" for v in self.varnames] + [v + "_m" for v in self.varnames]
                                 + ["log10ab", "log10polyprob"])
         self.lower, self.upper, self.ndim = self._get_likelihood_limits()

@@ -1,0 +1,145 @@
+"""GPU tests on the BASELINE.json workload shapes: oracle comparisons at sizes the oracle finishes in seconds, and
+size-independent properties (row-permutation invariance, additivity over a family partition, determinism) at the full
+cfg2 row count.  All through the C ABI."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TB = H.load_tables()
+RTOL = 1e-10
+
+
+def _tables_small():
+    from mope_b200 import TransitionTables
+    return TransitionTables(drift=TB["drift"], gens=TB["gens"], us=TB["us"], N=float(TB["N"]), freqs=TB["freqs"],
+                            breaks=TB["breaks"], bot=TB["bot"], nbs=TB["nbs"], bot_us=TB["bot_us"])
+
+
+def _oracle_for(ds, tables, **kw):
+    from oracle import mope_oracle as orc
+    drift = orc.TransitionData(tables.drift, tables.gens, tables.us, int(tables.N), tables.freqs, tables.breaks)
+    bot = orc.TransitionDataBottleneck(tables.bot, tables.nbs, tables.bot_us, int(tables.N)) if tables.bot is not None else None
+    return orc.Inference([(H.read_tsv(ds.data_tsv), ds.tree, H.read_tsv(ds.ages_tsv))], drift, bot, log_unif_drift=True, **kw)
+
+
+def _gpu_for(ds, tables, **kw):
+    from mope_b200 import Inference
+    return Inference([ds.data_tsv], [ds.tree], [ds.ages_tsv], tables, log_unif_drift=True, _inputs_are_text=True, **kw)
+
+
+def _check_vs_oracle(ds, tables, n_walkers, seed=3, shrink=0.1, **kw):
+    from mope_b200 import synth
+    I = _gpu_for(ds, tables, **kw)
+    try:
+        O = _oracle_for(ds, tables, **kw)
+        np.testing.assert_allclose(I.lower, O.lower, rtol=1e-15)
+        np.testing.assert_allclose(I.upper, O.upper, rtol=1e-15)
+        X = synth.walkers_in_prior_box(I.lower, I.upper, n_walkers, seed=seed, shrink=shrink)
+        ll = I.loglike_batch(X)
+        for i, x in enumerate(X):
+            O.clear_cache()
+            ref = O.loglike(x)
+            if np.isfinite(ref):
+                assert abs(ll[i] - ref) <= RTOL * abs(ref), (i, ll[i], ref)
+            else:
+                assert not np.isfinite(ll[i]) or ll[i] == ref
+        return I, X, ll
+    except Exception:
+        I.close()
+        raise
+
+
+def test_cfg2_shape_fixed_branches_vs_oracle():
+    from mope_b200 import synth
+    ds = synth.make_dataset(640, 16, tree=synth.balanced_tree(16), seed=5)
+    I, X, ll = _check_vs_oracle(ds, _tables_small(), 3)
+    assert I.peds[0].n_asc == 1 and I.num_loci[0] == 640      # one distinct ascertainment pair without multipliers
+    I.close()
+
+
+def test_cfg3_cfg4_shape_rate_and_bottleneck_branches_vs_oracle():
+    from mope_b200 import synth
+    tree = synth.balanced_tree(8, rate_leaves=True, rate_internal=True, bottleneck=True)
+    ds = synth.make_dataset(200, 8, tree=tree, seed=6)
+    I, X, ll = _check_vs_oracle(ds, _tables_small(), 3, shrink=0.25)
+    assert I.peds[0].n_asc == I.peds[0].n_fam                   # ages differ per family: no sharing
+    I.close()
+
+
+def test_leaf_minimum_and_unary_chain_trees_vs_oracle():
+    from mope_b200 import synth
+    for tree in ("(t0:a,t1:b)root;", "((((t0:a)n1:b)n2:c*child_age)n3:d^,t1:a)root;", "(t0:a,t1:a,t2:b,t3:c*mother_age)root;"):
+        nl = tree.count("t")
+        ds = synth.make_dataset(70, nl, tree=tree, seed=7)
+        # make_dataset names leaves t0..t{n-1}
+        I, X, ll = _check_vs_oracle(ds, _tables_small(), 2, shrink=0.25)
+        I.close()
+
+
+def test_f201_and_f1001_multipass_vs_oracle():
+    """F = 201 (bench grid size) and F = 1001 (cfg5: five N-passes per branch) on tables from the GPU generator."""
+    from mope_b200 import generate, synth
+    for brk, F, nloci, nleaves in ((0.005, 201, 60, 4), (1e-9, 1001, 12, 2)):
+        tb = generate.generate_tables(N=1000, breaks=(0.5, brk), gens=[1, 10, 100, 1000], us=[1e-8, 1e-5, 1e-3], device="cuda")
+        assert tb.F == F
+        ds = synth.make_dataset(nloci, nleaves, tree=synth.balanced_tree(nleaves), seed=8)
+        I, X, ll = _check_vs_oracle(ds, tb, 2, shrink=0.2)
+        I.close()
+
+
+def test_full_size_properties_cfg2_rows():
+    """L = 10 000 loci x 16 leaves (cfg2 rows): permutation invariance, family-partition additivity, determinism."""
+    from mope_b200 import synth
+    tables = _tables_small()
+    ds = synth.make_dataset(10000, 16, tree=synth.balanced_tree(16), seed=9)
+    I = _gpu_for(ds, tables)
+    X = synth.walkers_in_prior_box(I.lower, I.upper, 6, seed=4, shrink=0.15)
+    ll = I.loglike_batch(X)
+    assert np.isfinite(ll).all()
+    # determinism: same call twice, and duplicated walkers inside one batch, are bit-identical
+    np.testing.assert_array_equal(ll, I.loglike_batch(X))
+    dup = I.loglike_batch(np.concatenate([X, X]))
+    np.testing.assert_array_equal(dup[:6], dup[6:])
+    np.testing.assert_array_equal(dup[:6], ll)
+    I.close()
+    # row permutation
+    lines = ds.data_tsv.splitlines()
+    perm = np.random.RandomState(1).permutation(len(lines) - 1)
+    ds_p = synth.SyntheticPedigree("\n".join([lines[0]] + [lines[1 + i] for i in perm]) + "\n", ds.tree, ds.ages_tsv, ds.leaf_names,
+                                   ds.n_loci, ds.n_fam)
+    Ip = _gpu_for(ds_p, tables)
+    llp = Ip.loglike_batch(X)
+    Ip.close()
+    assert (np.abs(llp - ll) / np.abs(ll)).max() < 1e-12
+    # additivity over a family partition (what locus sharding relies on), incl. the global prior box
+    from mope_b200 import dist as mdist
+    parts = []
+    for r in range(3):
+        Il = mdist.build_locus_sharded([ds.data_tsv], [ds.tree], [ds.ages_tsv], tables, r, 3, log_unif_drift=True)
+        np.testing.assert_array_equal(Il.lower, I.lower)
+        np.testing.assert_array_equal(Il.upper, I.upper)
+        parts.append(Il.loglike_batch(X))
+        Il.close()
+    tot = parts[0] + parts[1] + parts[2]
+    assert (np.abs(tot - ll) / np.abs(ll)).max() < 1e-12
+
+
+def test_locus_shards_with_rate_branches_sum_to_full():
+    from mope_b200 import synth
+    from mope_b200 import dist as mdist
+    tables = _tables_small()
+    tree = synth.balanced_tree(4, rate_leaves=True, rate_internal=True, bottleneck=True)
+    ds = synth.make_dataset(900, 4, tree=tree, seed=10)
+    I = _gpu_for(ds, tables)
+    X = synth.walkers_in_prior_box(I.lower, I.upper, 5, seed=2, shrink=0.25)
+    ll = I.loglike_batch(X)
+    I.close()
+    tot = np.zeros_like(ll)
+    for r in range(2):
+        Il = mdist.build_locus_sharded([ds.data_tsv], [ds.tree], [ds.ages_tsv], tables, r, 2, log_unif_drift=True)
+        tot += Il.loglike_batch(X)
+        Il.close()
+    assert (np.abs(tot - ll) / np.abs(ll)).max() < 1e-12
