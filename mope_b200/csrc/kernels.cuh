@@ -251,6 +251,7 @@ constexpr int MAX_OPS = 96;  // branch ops staged in shared memory (trees with m
 struct TreeSmem {
     unsigned long long full[NS], empty[NS], epi;
     long long moff[MAX_OPS];   // per item: matrix offset of every shared-matrix op of this walker (negative = identity)
+    int32_t prow[MAX_OPS];     // the same as a row of the pool tensor map (offset / Fp, computed once per item)
     TreeOp ops[MAX_OPS];       // the branch schedule
     double rowdot[2][TM];
     double row_a[TM], row_d[TM];
@@ -426,7 +427,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
         // one round trip for all matrix offsets of this walker instead of a dependent global load per branch
         for (int i = threadIdx.x; i < p.n_ops; i += NTHREADS) {
             const TreeOp& o = ts->ops[i];
-            ts->moff[i] = (o.kind == 0) ? p.mat_off[(size_t)w * p.n_mat + o.key] : 0;
+            const long long off = (o.kind == 0) ? p.mat_off[(size_t)w * p.n_mat + o.key] : 0;
+            ts->moff[i] = off;
+            ts->prow[i] = off > 0 ? (int32_t)(off / Fp) : 0;
         }
         __syncthreads();
 
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                 if (nchunks >= PF) {
                     if (pass + 1 < npass) {
                         if (op.kind == 0 && !identity) {
-                            un = u; un.p_row = (int)(moff / Fp) + (t0 + 2 * NTW) * 8;
+                            un = u; un.p_row = ts->prow[oi] + (t0 + 2 * NTW) * 8;
                             have_next = true; next_v_early = true;   // same operands, nothing writes them
                         }
                     } else if (oi + 1 < p.n_ops) {
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                             un.v_is_E = (nx.src_kind[0] == 0);
                             un.v0_row = un.v_is_E ? nx.src[0] * p.R_pad + row0 : scratch_row0 + nx.src[0] * TM;
                             un.v1_row = scratch_row0 + nx.src[1] * TM;
-                            un.p_row = (int)(off / Fp);
+                            un.p_row = ts->prow[oi + 1];
                             have_next = true;
                             next_v_early = !nx.dep_prev;   // otherwise an operand is the message this epilogue writes
                         }
@@ -559,7 +562,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
 
                 if (op.kind == 0) {
                     if (!identity) {
-                        u.p_row = (int)(moff / Fp) + t0 * 8;
+                        u.p_row = ts->prow[oi] + t0 * 8;
                         if (p.debug < 2 && !prologue_issued && threadIdx.x == 0) {
                             if (epi_n > 0) mbar_wait(&ts->epi, (epi_n - 1) & 1u);
                             for (int c = 0; c < PF && c < nchunks; ++c) { issue_P<NTW>(p, ring, ts, u, c, g + c); issue_V<NTW>(p, ring, ts, u, c, g + c); }

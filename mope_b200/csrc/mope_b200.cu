@@ -293,7 +293,9 @@ int compile_schedule(const mope_pedigree_desc& pd, const std::vector<int>& fixed
             for (size_t i = 0; i < pending[par].size(); ++i) op.sib[i] = pending[par][i];
         } else if (pending[par].size() < 2) {
             int sl;
-            if (!free_slots.empty()) { sl = free_slots.front(); free_slots.erase(free_slots.begin()); }  // oldest first
+            // most recently freed first: that tile is still dirty in L2 and gets overwritten there instead of being
+            // written back to HBM
+            if (!free_slots.empty()) { sl = free_slots.back(); free_slots.pop_back(); }
             else sl = n_slots++;
             op.dst = sl;
             op.first = 1;
