@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile mope_b200/csrc into libmope_b200.so in-tree with nvcc for sm_100a."""
     srcs = [os.path.join(CSRC, "mope_b200.cu")]
-    deps = srcs + [os.path.join(CSRC, "kernels.cuh"), os.path.join(HERE, "..", "include", "mope_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "tree4.cuh"), os.path.join(HERE, "..", "include", "mope_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")

@@ -24,6 +24,15 @@ constexpr int KC = 16;        // K chunk in doubles (128 B per row)
 constexpr int NTHREADS = 256; // 8 warps: 4 along M (16 rows each) x 2 along N
 
 // One branch of the tree: Y = P . (product of the child messages of the node below the branch).
+// Storage position of natural column `col` (the k index of the GEMMs) in the k-permuted layout used together with
+// tree_kernel4 (tree4.cuh): inside every 16-wide chunk, (j_in, kk, h) -> 2*(2*j_in + h) + (kk & 1) + 8*(kk >> 1).
+__host__ __device__ __forceinline__ int kperm(int col) {
+    const int c = col >> 4, r = col & 15;
+    const int jin = r >> 3, kk = (r & 7) >> 1, h = r & 1;
+    const int q = 2 * jin + h;
+    return 16 * c + 2 * q + (kk & 1) + 8 * (kk >> 1);
+}
+
 struct TreeOp {
     int32_t nsrc;         // 1 or 2 operands, multiplied element-wise while the A fragments are read
     int32_t src_kind[2];  // 0 leaf emissions (leaf branches, nsrc = 1), 1 scratch slot
@@ -110,6 +119,7 @@ struct EmissionParams {
     const int8_t* asc_eN;    // [F] 1 where freq > 1-min_freq
     double* E;               // [S][R_pad][Fp]
     int32_t L, S, R, R_pad, F, Fp;
+    int32_t perm;            // 1: write columns in the k-permuted layout
 };
 
 __device__ __forceinline__ double lnchoose_dev(unsigned n, unsigned m) {
@@ -132,13 +142,13 @@ __global__ void emission_kernel(EmissionParams p) {
     }
     if (r >= p.L) {  // ascertainment pseudo-rows: e0 (even) / eN (odd), ascertainment.py:178-184
         const int8_t* e = ((r - p.L) & 1) ? p.asc_eN : p.asc_e0;
-        for (int f = lane; f < p.Fp; f += 32) out[f] = (f < p.F && e[f]) ? 1.0 : 0.0;
+        for (int f = lane; f < p.Fp; f += 32) out[p.perm ? kperm(f) : f] = (f < p.F && e[f]) ? 1.0 : 0.0;
         return;
     }
     const double x = p.counts[(size_t)r * p.S + s];
     const double nn = p.coverage[(size_t)r * p.S + s];
     if (isnan(x)) {  // missing tissue
-        for (int f = lane; f < p.Fp; f += 32) out[f] = (f < p.F) ? 1.0 : 0.0;
+        for (int f = lane; f < p.Fp; f += 32) out[p.perm ? kperm(f) : f] = (f < p.F) ? 1.0 : 0.0;
         return;
     }
     const unsigned uk = (unsigned)x, un = (unsigned)nn;
@@ -160,7 +170,7 @@ __global__ void emission_kernel(EmissionParams p) {
                 v = exp(e);
             }
         }
-        out[f] = v;
+        out[p.perm ? kperm(f) : f] = v;
     }
 }
 
@@ -169,7 +179,7 @@ __global__ void emission_kernel(EmissionParams p) {
 // _util.pyx:129-148).  One warp per matrix row; sequential row sum as in the reference.
 // Output block: Fp x Fp matrix (zero padded) followed by Fp row sums (of the un-normalised blend).
 // ------------------------------------------------------------------------------------------------
-__global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* tables, double* pool, int F, int Fp) {
+__global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* tables, double* pool, int F, int Fp, int perm) {
     extern __shared__ double srow[];  // [warps_per_block][Fp]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* row = srow + (size_t)wib * Fp;
@@ -188,7 +198,7 @@ __global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* t
         return;
     }
     if (jb.flags & 2) {  // identity short-cut (transition_data_2d.py:184-187)
-        for (int f = lane; f < Fp; f += 32) dst[f] = (f == i) ? 1.0 : 0.0;
+        for (int f = lane; f < Fp; f += 32) dst[perm ? kperm(f) : f] = (f == i) ? 1.0 : 0.0;
         if (lane == 0) dsum[i] = 1.0;
         return;
     }
@@ -221,7 +231,7 @@ __global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* t
     for (int f = lane; f < Fp; f += 32) {
         double v = (f < F) ? row[f] : 0.0;
         if (div) v = __ddiv_rn(v, s);
-        dst[f] = v;
+        dst[perm ? kperm(f) : f] = v;
     }
     if (lane == 0) dsum[i] = s;
 }
@@ -852,12 +862,12 @@ __global__ void pb_kernel(const double* __restrict__ qual, const int64_t* __rest
 }
 
 // simple helpers
-__global__ void pad_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, int n_rows, int F, int Fp, int rows_pad) {
+__global__ void pad_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, int n_rows, int F, int Fp, int rows_pad, int perm) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)rows_pad * Fp;
     if (idx >= total) return;
     const int r = (int)(idx / Fp), f = (int)(idx % Fp);
-    dst[idx] = (r < n_rows && f < F) ? src[(size_t)r * F + f] : 0.0;
+    dst[(size_t)r * Fp + (perm ? kperm(f) : f)] = (r < n_rows && f < F) ? src[(size_t)r * F + f] : 0.0;
 }
 __global__ void unpad_rows_kernel(const double* __restrict__ src, double* __restrict__ dst, int n_rows, int F, int Fp) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

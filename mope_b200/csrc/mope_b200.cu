@@ -18,6 +18,7 @@
 
 #include "../../include/mope_b200.h"
 #include "kernels.cuh"
+#include "tree4.cuh"
 
 using namespace mope;
 
@@ -69,6 +70,10 @@ struct Pedigree {
     double* fam_lgamma = nullptr;
     TreeOp* ops = nullptr;
     std::vector<TreeOp> ops_h;
+    // warp-owned-rows kernel (tree4.cuh): postorder schedule with chained messages
+    Op4* ops4 = nullptr;
+    std::vector<Op4> ops4_h;
+    int n_slots4 = 0;
     int asc_offset = 0;
     CUtensorMap tmapE;
 };
@@ -106,6 +111,9 @@ struct mope_ctx {
     size_t opbuf_cap = 0;
     int64_t launches = 0;
     int tree_variant = 13;
+    bool use_v4 = false;   // F <= 208: warp-owned rows + k-permuted operand layout
+    int ntt = 26;          // n-tiles per warp of tree_kernel4 (10, 16 or 26)
+    int max_slots4 = 1;
     // statistics of the last eval: branch GEMMs executed / skipped by the identity short-cut (per walker x branch)
     int64_t last_gemm_ops = 0, last_identity_ops = 0;
     // profiling
@@ -186,7 +194,11 @@ int make_tmap(CUtensorMap* out, const double* base, uint64_t rows, int Fp, int b
     return 0;
 }
 
-int tree_prows(const mope_ctx* c) { return 2 * c->tree_variant * 8; }
+int tree_prows(const mope_ctx* c) { return c->use_v4 ? c->ntt * 8 : 2 * c->tree_variant * 8; }
+// doubles of message scratch for a full grid
+size_t scratch_doubles(const mope_ctx* c) {
+    return c->use_v4 ? (size_t)c->num_sms * 8 * c->max_slots4 * c->ntt * 64 : (size_t)c->num_sms * c->max_slots * TM * c->Fp;
+}
 
 // searchsorted(side='left')
 inline int lower_bound_idx(const std::vector<double>& v, double x) {
@@ -317,6 +329,53 @@ int compile_schedule(const mope_pedigree_desc& pd, const std::vector<int>& fixed
     return 0;
 }
 
+// Schedule of tree_kernel4: plain postorder (branch b's last child is branch b-1, so its message is still in the
+// warp's fragments when b runs).  Messages of non-last children are parked in a slot; a node never holds more than
+// one parked product (later siblings fold into it).
+int compile_schedule4(const mope_pedigree_desc& pd, const std::vector<int>& fixed_key_of_branch,
+                      const std::vector<int>& rate_key_of_branch, Pedigree& out) {
+    const int nb = pd.n_branches, root = pd.n_branches;
+    std::vector<int> nchild(nb + 1, 0), seen(nb + 1, 0), slot(nb + 1, -1);
+    for (int b = 0; b < nb; ++b) nchild[pd.br_parent[b]]++;
+    std::vector<int> free_slots;
+    int n_slots = 0;
+    out.ops4_h.clear();
+    for (int b = 0; b < nb; ++b) {
+        Op4 op{};
+        const int par = pd.br_parent[b];
+        op.leaf = pd.br_leaf[b];
+        if (op.leaf < 0) {
+            // chained operand: the previous op must be this node's last child
+            if (b == 0 || pd.br_parent[b - 1] != b || seen[b] != nchild[b])
+                return fail(MOPE_E_INVALID, "branch table is not in postorder (branch %d)", b);
+        } else if (nchild[b] != 0) {
+            return fail(MOPE_E_INVALID, "branch %d is marked leaf but has children", b);
+        }
+        if (pd.br_mult[b] >= 0) { op.kind = 1; op.key = rate_key_of_branch[b]; op.mult = pd.br_mult[b]; }
+        else { op.kind = 0; op.key = fixed_key_of_branch[b]; op.mult = -1; }
+        seen[par]++;
+        const bool last_child = (seen[par] == nchild[par]);
+        op.mul_slot = -1; op.store_slot = -1; op.store_first = 0; op.last = 0;
+        if (!last_child) {
+            if (slot[par] < 0) {
+                if (!free_slots.empty()) { slot[par] = free_slots.back(); free_slots.pop_back(); }
+                else slot[par] = n_slots++;
+                op.store_first = 1;
+            }
+            op.store_slot = slot[par];
+        } else {
+            op.mul_slot = slot[par];
+            if (slot[par] >= 0) { free_slots.push_back(slot[par]); slot[par] = -1; }
+            op.last = (par == root) ? 1 : 0;
+            if (par != root && par != b + 1) return fail(MOPE_E_INVALID, "branch table is not in postorder (parent of %d)", b);
+        }
+        out.ops4_h.push_back(op);
+    }
+    if (out.ops4_h.empty() || !out.ops4_h.back().last) return fail(MOPE_E_INVALID, "schedule does not end at the root");
+    out.n_slots4 = std::max(n_slots, 1);
+    return 0;
+}
+
 struct ArenaPlan {
     size_t bytes = 0;
 };
@@ -339,9 +398,10 @@ int layout_arena(mope_ctx* c, const mope_tables_desc* t, const mope_model_desc* 
         double* fc = bump.take<double>(pd.n_fam);
         double* fl = bump.take<double>(pd.n_fam);
         TreeOp* ops = bump.take<TreeOp>(pd.n_branches);
+        Op4* ops4 = bump.take<Op4>(pd.n_branches);
         if (!dry) {
             Pedigree& P = c->peds[k];
-            P.E = E; P.mult = mu; P.fam_asc = fa; P.fam_count = fc; P.fam_lgamma = fl; P.ops = ops;
+            P.E = E; P.mult = mu; P.fam_asc = fa; P.fam_count = fc; P.fam_lgamma = fl; P.ops = ops; P.ops4 = ops4;
         }
     }
     // transient inputs of the emission kernel live at the arena tail; they are dead after create().
@@ -394,15 +454,39 @@ int launch_tree_t(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) 
 }
 
 // one warp per matrix row; warps per block bounded by the 48 KB default dynamic shared memory (Fp doubles per warp)
-int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d_pool, cudaStream_t st) {
+int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d_pool, cudaStream_t st, bool perm) {
     const int Fp = c->Fp;
     const int wpb = std::max(1, std::min(8, (int)((48 * 1024) / ((size_t)Fp * sizeof(double)))));
     const long long rows = (long long)n_jobs * Fp;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    interp_kernel<<<grid, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, c->F, Fp);
+    interp_kernel<<<grid, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, c->F, Fp, perm ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return 0;
+}
+
+template <int NTT>
+int launch_tree4_t(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(tree_kernel4<NTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg4<NTT>::SMEM_BYTES));
+        attr_set = true;
+    }
+    {
+        ScopedTimer timer(c, st, &c->ev_tree);
+        tree_kernel4<NTT><<<grid, NTHREADS, Cfg4<NTT>::SMEM_BYTES, st>>>(tp);
+    }
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int launch_tree4(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st) {
+    switch (c->ntt) {
+        case 10: return launch_tree4_t<10>(c, tp, grid, st);
+        case 16: return launch_tree4_t<16>(c, tp, grid, st);
+        default: return launch_tree4_t<26>(c, tp, grid, st);
+    }
 }
 
 int launch_tree(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) {
@@ -603,7 +687,7 @@ size_t per_walker_bytes(const mope_ctx* c, size_t n_blocks) {
 }
 
 size_t fixed_ws_bytes(const mope_ctx* c, int W) {
-    size_t b = (size_t)c->num_sms * c->max_slots * TM * c->Fp * sizeof(double);  // scratch
+    size_t b = scratch_doubles(c) * sizeof(double);  // scratch
     b += (size_t)W * sizeof(double) * (1 + c->n_ped);                             // out_ll, out_root
     b += (size_t)W * c->asc_total * sizeof(double);                               // out_log_asc
     b += (size_t)W * sizeof(int32_t);                                             // walker index
@@ -640,14 +724,15 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
     Bump ws;
     ws.base = (char*)workspace;
     ws.cap = ws_bytes;
-    double* scratch = ws.take<double>((size_t)c->num_sms * c->max_slots * TM * Fp);
+    double* scratch = ws.take<double>(scratch_doubles(c));
     double* d_out_ll = out_on_device ? out_ll : ws.take<double>(W);
     double* d_out_root = out_root_ll ? ws.take<double>((size_t)W * c->n_ped) : nullptr;
     double* d_out_asc = out_log_asc ? ws.take<double>((size_t)W * c->asc_total) : nullptr;
     if (!ws.ok()) return fail(MOPE_E_NOMEM, "workspace too small: %zu bytes, need more than %zu", ws_bytes, ws.used);
     const size_t fixed_used = ws.used;
     CUtensorMap tmapS;
-    if (int rc = make_tmap(&tmapS, scratch, (uint64_t)c->num_sms * c->max_slots * TM, Fp, TM)) return rc;
+    if (!c->use_v4)
+        if (int rc = make_tmap(&tmapS, scratch, (uint64_t)c->num_sms * c->max_slots * TM, Fp, TM)) return rc;
 
     // outputs of invalid walkers: NaN (the host wrapper raises ValueError like the reference); valid walkers overwrite
     fill_nan_kernel<<<(W + 255) / 256, 256, 0, st>>>(d_out_ll, W);
@@ -742,7 +827,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
         // interpolation
         if (n_blocks > 0) {
             ScopedTimer timer(c, st, &c->ev_interp);
-            if (int rc = launch_interp(c, d_jobs, n_blocks, d_pool, st)) return rc;
+            if (int rc = launch_interp(c, d_jobs, n_blocks, d_pool, st, c->use_v4)) return rc;
         }
 
         CUtensorMap tmapP;
@@ -758,6 +843,24 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
                     else c->last_gemm_ops++;
                 }
             }
+            const int tile_block_default = std::max(1, std::min(P.n_tiles, c->num_sms / 4));
+            const long long items = (long long)Wc * P.n_tiles;
+            const int grid = (int)std::min<long long>(items, c->num_sms);
+            if (c->use_v4) {
+                Tree4Params t4{};
+                t4.tmapE = P.tmapE; t4.tmapP = tmapP;
+                t4.E = P.E; t4.E_leaf_stride = (int64_t)P.R_pad * Fp;
+                t4.scratch = scratch;
+                t4.ops = P.ops4; t4.n_ops = (int)P.ops4_h.size(); t4.n_slots = c->max_slots4;
+                t4.R = P.R; t4.L = P.L; t4.R_pad = P.R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = P.n_tiles; t4.W = Wc;
+                t4.tile_block = tile_block_default;
+                if (const char* e = getenv("MOPE_TILE_BLOCK")) t4.tile_block = std::max(1, std::min(P.n_tiles, atoi(e)));
+                t4.pool = d_pool; t4.mat_off = d_mat_off; t4.n_mat = n_mat; t4.n_rate = n_rate; t4.rate = d_rate;
+                t4.mult = P.mult; t4.gens = c->gens_dev; t4.n_gens = c->n_gens; t4.Npop = c->N; t4.stat = d_stat;
+                t4.tile_ll = d_tile_ll; t4.asc_dot = d_asc_dot; t4.Yout = nullptr;
+                if (const char* e = getenv("MOPE_DEBUG_MODE")) t4.debug = atoi(e);
+                if (launch_tree4(c, t4, grid, st)) return MOPE_E_CUDA;
+            } else {
             TreeParams tp{};
             tp.tmapE = P.tmapE;
             tp.tmapS = tmapS;
@@ -784,9 +887,8 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
             tp.asc_dot = d_asc_dot;
             tp.Yout = nullptr;
             if (const char* e = getenv("MOPE_DEBUG_MODE")) tp.debug = atoi(e);  // measurement only (results are garbage)
-            const long long items = (long long)Wc * P.n_tiles;
-            const int grid = (int)std::min<long long>(items, c->num_sms);
             if (launch_tree(c, tp, grid, st)) return MOPE_E_CUDA;
+            }
 
             FinalizeParams fp{};
             fp.tile_ll = d_tile_ll; fp.asc_dot = d_asc_dot;
@@ -873,6 +975,9 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
     c->Fp = round_up_i(t->F, 16);
     c->NT = (t->F + 7) / 8;
     c->tree_variant = c->Fp <= 80 ? 5 : (c->Fp <= 128 ? 8 : 13);
+    // F <= 208: warp-owned rows (tree4.cuh); larger grids need several N passes per branch and use tree_kernel
+    c->use_v4 = (c->Fp <= 208) && !getenv("MOPE_FORCE_V3");
+    c->ntt = c->NT <= 10 ? 10 : (c->NT <= 16 ? 16 : 26);
     c->n_gens = t->n_gens; c->n_us = t->n_us;
     c->has_bot = t->bot != nullptr;
     c->n_nbs = c->has_bot ? t->n_nbs : 0;
@@ -969,6 +1074,10 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         asc_off += pd.n_asc;
         if (int rc = compile_schedule(pd, fk[k], rk[k], P)) return cleanup_fail(rc);
         c->max_slots = std::max(c->max_slots, P.n_slots);
+        if (c->use_v4) {
+            if (int rc = compile_schedule4(pd, fk[k], rk[k], P)) return cleanup_fail(rc);
+            c->max_slots4 = std::max(c->max_slots4, P.n_slots4);
+        }
         c->max_tiles = std::max(c->max_tiles, P.n_tiles);
         c->max_asc2 = std::max(c->max_asc2, 2 * P.n_asc);
 
@@ -986,6 +1095,8 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         CUDA_TRY_C(cudaMemcpyAsync(P.fam_count, pd.fam_count, (size_t)pd.n_fam * sizeof(double), cudaMemcpyHostToDevice, st));
         CUDA_TRY_C(cudaMemcpyAsync(P.fam_lgamma, pd.fam_lgamma, (size_t)pd.n_fam * sizeof(double), cudaMemcpyHostToDevice, st));
         CUDA_TRY_C(cudaMemcpyAsync(P.ops, P.ops_h.data(), (size_t)P.n_ops * sizeof(TreeOp), cudaMemcpyHostToDevice, st));
+        if (c->use_v4)
+            CUDA_TRY_C(cudaMemcpyAsync(P.ops4, P.ops4_h.data(), P.ops4_h.size() * sizeof(Op4), cudaMemcpyHostToDevice, st));
 
         // emissions: transient inputs at the arena tail
         Bump tail = bump;
@@ -1011,6 +1122,7 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         ep.counts = d_counts; ep.coverage = d_cov; ep.logp = d_logp; ep.log1mp = d_log1mp; ep.pclass = d_cls;
         ep.asc_e0 = d_e0; ep.asc_eN = d_eN; ep.E = P.E;
         ep.L = P.L; ep.S = P.n_leaves; ep.R = P.R; ep.R_pad = P.R_pad; ep.F = F; ep.Fp = Fp;
+        ep.perm = c->use_v4 ? 1 : 0;
         const long long warps = (long long)P.n_leaves * P.R_pad;
         const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
         emission_kernel<<<grid, 256, 0, st>>>(ep);
@@ -1154,7 +1266,7 @@ int mope_b200_transition_matrix(mope_ctx* c, int bottleneck, double x, double sc
     double* d_blk = reinterpret_cast<double*>(c->opbuf + align_up(sizeof(InterpJob), 256));
     double* d_out = d_blk + blk;
     CUDA_TRY(cudaMemcpyAsync(d_job, po.jobs.data(), sizeof(InterpJob), cudaMemcpyHostToDevice, st));
-    if (int rc = launch_interp(c, d_job, 1, d_blk, st)) return rc;
+    if (int rc = launch_interp(c, d_job, 1, d_blk, st, false)) return rc;
     const long long total = (long long)F * F;
     unpad_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_blk, d_out, F, F, Fp);
     CUDA_TRY(cudaGetLastError());
@@ -1203,6 +1315,7 @@ int mope_b200_leaf_likelihoods(mope_ctx* c, const double* counts, const double* 
     EmissionParams ep{};
     ep.counts = dc; ep.coverage = dn; ep.logp = dl; ep.log1mp = dl1; ep.pclass = cls; ep.asc_e0 = z; ep.asc_eN = z; ep.E = E;
     ep.L = L; ep.S = S; ep.R = L; ep.R_pad = R_pad; ep.F = F; ep.Fp = Fp;
+    ep.perm = 0;
     const long long warps = (long long)S * R_pad;
     emission_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(ep);
     CUDA_TRY(cudaGetLastError());
@@ -1285,11 +1398,27 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     const long long tot = (long long)R_pad * Fp;
-    pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P.raw, P.E, n_rows, F, Fp, R_pad);
+    pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(P.raw, P.E, n_rows, F, Fp, R_pad, c->use_v4 ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
     if (n_blocks) {
-        if (int rc = launch_interp(c, P.jobs, n_blocks, P.pool, st)) return rc;
+        if (int rc = launch_interp(c, P.jobs, n_blocks, P.pool, st, c->use_v4)) return rc;
     }
+    if (c->use_v4) {
+        Op4 o4{};
+        o4.leaf = 0; o4.kind = (kind == 1) ? 1 : 0; o4.key = 0; o4.mult = 0; o4.mul_slot = -1; o4.store_slot = -1; o4.store_first = 0; o4.last = 0;
+        static_assert(sizeof(Op4) <= sizeof(TreeOp), "the single-op staging buffer is sized for TreeOp");
+        CUDA_TRY(cudaMemcpyAsync(P.op, &o4, sizeof(Op4), cudaMemcpyHostToDevice, st));
+        Tree4Params t4{};
+        if (int rc = make_tmap(&t4.tmapE, P.E, (uint64_t)R_pad, Fp, TM)) return rc;
+        if (int rc = make_tmap(&t4.tmapP, P.pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + 1), Fp, tree_prows(c))) return rc;
+        t4.E = P.E; t4.E_leaf_stride = (int64_t)R_pad * Fp; t4.scratch = P.Y /*unused*/; t4.ops = reinterpret_cast<const Op4*>(P.op);
+        t4.n_ops = 1; t4.n_slots = 1;
+        t4.R = n_rows; t4.L = n_rows; t4.R_pad = R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = R_pad / TM; t4.W = 1;
+        t4.tile_block = t4.n_tiles;
+        t4.pool = P.pool; t4.mat_off = P.mo; t4.n_mat = 1; t4.n_rate = 1; t4.rate = P.rate; t4.mult = P.mult; t4.gens = c->gens_dev;
+        t4.n_gens = c->n_gens; t4.Npop = c->N; t4.stat = nullptr; t4.tile_ll = nullptr; t4.asc_dot = nullptr; t4.Yout = P.Y;
+        if (launch_tree4(c, t4, std::min(t4.n_tiles, c->num_sms), st)) return MOPE_E_CUDA;
+    } else {
     TreeParams tp{};
     if (int rc = make_tmap(&tp.tmapE, P.E, (uint64_t)R_pad, Fp, TM)) return rc;
     if (int rc = make_tmap(&tp.tmapS, P.Y, (uint64_t)R_pad, Fp, TM)) return rc;   // no scratch ring in single-op mode
@@ -1300,6 +1429,7 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
     tp.pool = P.pool; tp.mat_off = P.mo; tp.n_mat = 1; tp.n_rate = 1; tp.rate = P.rate; tp.mult = P.mult; tp.gens = c->gens_dev;
     tp.n_gens = c->n_gens; tp.Npop = c->N; tp.stat = nullptr; tp.tile_ll = nullptr; tp.asc_dot = nullptr; tp.Yout = P.Y;
     if (launch_tree(c, tp, std::min(tp.n_tiles, c->num_sms), st)) return MOPE_E_CUDA;
+    }
     const long long tot2 = (long long)n_rows * F;
     mul_unpad_kernel<<<(unsigned)((tot2 + 255) / 256), 256, 0, st>>>(P.Y, P.par, n_rows, F, Fp);
     CUDA_TRY(cudaGetLastError());

@@ -1,0 +1,362 @@
+// tree_kernel4 -- fused pruning pass, "warp-owned rows" variant (used when F <= 208).
+//
+// Same arithmetic as tree_kernel (kernels.cuh) with a different decomposition: each of the 8 warps of a CTA owns
+// 8 complete rows of the 64-row tile and all F output bins, so a message never has to cross warps:
+//   * the output of a branch GEMM sits in the warp's mma C fragments (thread (x, kk) holds bins 8n+2kk, 8n+2kk+1 of
+//     row x).  With the k index of an mma step taken as {8j + 2kk + h : kk = 0..3} those very registers are the A
+//     fragment of the NEXT branch (the parent's branch follows its last child in postorder), so chained messages
+//     go through a warp-private shared-memory buffer in fragment layout -- no global round trip, no proxy fence,
+//     no CTA-wide synchronisation;
+//   * only the message of a non-last child is parked in a warp-private scratch slot (fragment layout, coalesced
+//     16-byte accesses by the thread that later reads it back) and multiplied in when the last sibling arrives;
+//   * the only shared resource is the TMA ring with the P chunks (and emission chunks for leaf branches); since no
+//     copy depends on an epilogue any more, one lane streams the whole item PF chunks ahead without ever stalling
+//     on a dependency.
+// K layout: the transition matrices and the emission tensor are stored with their k (column) index permuted inside
+// every 16-wide chunk, kperm() below, so that the chained k sets land on the bank-conflict-free fragment positions
+// {2q, 2q+1, 2q+8, 2q+9} of the 128-byte swizzled chunk.
+#pragma once
+#include "kernels.cuh"
+
+namespace mope {
+
+constexpr int NS4 = 3;   // ring stages
+constexpr int PF4 = 2;   // prefetch distance (chunks)
+
+struct Op4 {
+    int32_t leaf;         // >= 0: leaf column, A operand = emission rows (TMA ring); -1: A operand chained from the previous op
+    int32_t kind;         // 0 shared matrix (fixed length or bottleneck), 1 per-row times (rate)
+    int32_t key;          // matrix key / rate key
+    int32_t mult;         // rate: multiplier column
+    int32_t mul_slot;     // >= 0: this op is the LAST child of its parent: multiply the parked sibling product in
+    int32_t store_slot;   // >= 0: not the last child: park the message (store_first) or fold it into the parked one
+    int32_t store_first;
+    int32_t last;         // completes the root: root reduction
+};
+
+struct Tree4Params {
+    CUtensorMap tmapE;      // emissions [n_leaves*R_pad][Fp] (k-permuted columns), box 16 x 64
+    CUtensorMap tmapP;      // matrix pool [n_blocks*(Fp+1)][Fp] (k-permuted columns), box 16 x 8*NTT
+    const double* E;
+    int64_t E_leaf_stride;
+    double* scratch;        // [gridDim.x][8 warps][n_slots][NTT][32][2]
+    const Op4* ops;
+    int32_t n_ops, n_slots;
+    int32_t R, L, R_pad, Fp, F, NT, n_tiles, W, tile_block;
+    const double* pool;
+    const int64_t* mat_off;  // [W][n_mat], negative = identity
+    int32_t n_mat, n_rate;
+    const RateInfo* rate;
+    const double* mult;
+    const double* gens;
+    int32_t n_gens;
+    double Npop;
+    const double* stat;      // [W][Fp] natural order
+    double* tile_ll;
+    double* asc_dot;
+    double* Yout;
+    int32_t debug;
+};
+
+struct Tree4Smem {
+    unsigned long long full[NS4], empty[NS4];
+    Op4 ops[MAX_OPS];
+    int32_t prow[MAX_OPS];     // per item: pool row of a shared-matrix op (negative = identity)
+    int32_t seg_lo[MAX_OPS], seg_hi[MAX_OPS];   // per item: generation-grid range of a rate op over the tile's rows
+    double rowval[TM];         // root reduction: per-row log-likelihood terms
+};
+
+template <int NTT>
+struct Cfg4 {
+    static constexpr int PROWS = NTT * 8;
+    static constexpr int E_BYTES = TM * KC * 8;          // 8 KB
+    static constexpr int P_BYTES = PROWS * KC * 8;
+    static constexpr int STAGE_BYTES = E_BYTES + P_BYTES;  // multiples of 1024
+    static constexpr int ABUF_BYTES = 8 * NTT * 32 * 16;   // chained operand, fragment layout [warp][n][lane][2]
+    static constexpr size_t SMEM_BYTES = (size_t)NS4 * STAGE_BYTES + ABUF_BYTES + sizeof(Tree4Smem) + 1024;
+};
+
+// per-row time weights of an age-scaled branch (transition_data_2d.py:183-224)
+__device__ __forceinline__ void rate_row(const Tree4Params& p, const Op4& op, const RateInfo* ri, int r, int& gi, double& a, double& d) {
+    gi = -1; a = 0.0; d = 0.0;
+    if (r >= p.R) return;
+    const double t = __dmul_rn(p.Npop, __dmul_rn(p.mult[(size_t)op.mult * p.R_pad + r], ri->len));
+    if (t < p.gens[0]) return;
+    int lo = 0, hi = p.n_gens;  // searchsorted left
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.gens[mid] < t) lo = mid + 1; else hi = mid; }
+    gi = lo < p.n_gens ? lo : p.n_gens - 1;
+    const double t2 = p.gens[gi];
+    const double t1 = p.gens[gi > 0 ? gi - 1 : p.n_gens - 1];
+    const double den = __dsub_rn(t2, t1);
+    a = __ddiv_rn(__dsub_rn(t2, t), den);
+    d = __ddiv_rn(__dsub_rn(t, t1), den);
+    if (gi == 0) a = 0.0;  // wrapped neighbour carries an exactly-zero weight
+}
+
+// the copy-issuing lane's cursor over the item's chunk sequence
+struct Producer4 {
+    int op, seg, chunk;   // next chunk to issue
+    unsigned g;           // its ring index
+};
+
+template <int NTT>
+__global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constant__ Tree4Params p) {
+    using Cfg = Cfg4<NTT>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    double* abuf_all = reinterpret_cast<double*>(ring + (size_t)NS4 * Cfg::STAGE_BYTES);
+    Tree4Smem* ts = reinterpret_cast<Tree4Smem*>(ring + (size_t)NS4 * Cfg::STAGE_BYTES + Cfg::ABUF_BYTES);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = lane >> 2, kk = lane & 3;
+    const int Fp = p.Fp;
+    const int nchunks = Fp / KC;
+    const int blk_rows = Fp + 1;
+    const size_t blk = (size_t)Fp * Fp + Fp;
+    double* abuf = abuf_all + (size_t)warp * NTT * 64;                       // [n][lane][2]
+    double* my_scratch = p.scratch + ((size_t)blockIdx.x * 8 + warp) * p.n_slots * NTT * 64;
+    // fragment addressing inside a stage (128 B swizzle, see kernels.cuh)
+    const int z = x ^ ((kk >> 1) << 2);
+    const int hb = (kk & 1) << 3;
+    const int a_base = (warp * 8 + x) * 128 + hb;
+    const int b_base = Cfg::E_BYTES + x * 128 + hb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS4; ++s) { mbar_init(&ts->full[s], 1); mbar_init(&ts->empty[s], NTHREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.n_ops; i += NTHREADS) ts->ops[i] = p.ops[i];
+    __syncthreads();
+
+    unsigned g = 0;   // chunks consumed so far (ring position)
+    const long long n_items = (long long)p.W * p.n_tiles;
+
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int w, tile;
+        {
+            const long long per_block = (long long)p.W * p.tile_block;
+            const int tb = (int)(item / per_block);
+            const int t_first = tb * p.tile_block;
+            const int t_count = min(p.tile_block, p.n_tiles - t_first);
+            const long long rem = item - (long long)tb * per_block;
+            w = (int)(rem / t_count);
+            tile = t_first + (int)(rem % t_count);
+        }
+        const int row0 = tile * TM;
+        const int my_row = row0 + warp * 8 + x;     // the row this thread's fragments belong to
+
+        // ---- per-item tables: matrix rows, generation ranges of the rate ops ----
+        for (int i = threadIdx.x; i < p.n_ops; i += NTHREADS) {
+            const Op4& o = ts->ops[i];
+            int pr = 0;
+            if (o.kind == 0) {
+                const long long off = p.mat_off[(size_t)w * p.n_mat + o.key];
+                pr = off < 0 ? -1 : (int)(off / Fp);
+            }
+            ts->prow[i] = pr;
+        }
+        for (int i = warp; i < p.n_ops; i += 8) {
+            const Op4& o = ts->ops[i];
+            if (o.kind != 1) continue;
+            const RateInfo* ri = &p.rate[(size_t)w * p.n_rate + o.key];
+            int lo = 0x7fffffff, hi = -1;
+            for (int hh = 0; hh < 2; ++hh) {
+                int gi; double a, d;
+                rate_row(p, o, ri, row0 + lane + 32 * hh, gi, a, d);
+                if (gi >= 0) { lo = min(lo, gi > 0 ? gi - 1 : 0); hi = max(hi, gi); }
+            }
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o2));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o2));
+            }
+            if (lane == 0) { ts->seg_lo[i] = lo; ts->seg_hi[i] = hi; }
+        }
+        __syncthreads();
+
+        // ---- copy producer (lane 0 of warp 0): walks the same unit sequence as the consumers, PF4 chunks ahead ----
+        Producer4 pr;
+        pr.op = 0; pr.seg = 0; pr.chunk = 0; pr.g = g;
+        auto produce = [&]() {
+            // advance to the next op that has chunks
+            while (pr.op < p.n_ops) {
+                const Op4& o = ts->ops[pr.op];
+                bool has = false;
+                int p_row = 0;
+                if (o.kind == 0) {
+                    if (ts->prow[pr.op] >= 0) { has = true; p_row = ts->prow[pr.op]; }
+                } else {
+                    const int lo = ts->seg_lo[pr.op], hi = ts->seg_hi[pr.op];
+                    if (pr.chunk == 0 && pr.seg == 0) pr.seg = lo;
+                    if (pr.seg <= hi) {
+                        has = true;
+                        const RateInfo* ri = &p.rate[(size_t)w * p.n_rate + o.key];
+                        p_row = (int)(ri->off / Fp) + (pr.seg - ri->gbase) * blk_rows;
+                    }
+                }
+                if (!has) { ++pr.op; pr.seg = 0; pr.chunk = 0; continue; }
+                const unsigned s = pr.g % NS4;
+                mbar_wait(&ts->empty[s], ((pr.g / NS4) & 1u) ^ 1u);
+                unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&ts->full[s], (unsigned)(Cfg::P_BYTES + (o.leaf >= 0 ? Cfg::E_BYTES : 0)));
+                tma_load_2d(st + Cfg::E_BYTES, &p.tmapP, pr.chunk * KC, p_row, &ts->full[s]);
+                if (o.leaf >= 0) tma_load_2d(st, &p.tmapE, pr.chunk * KC, o.leaf * p.R_pad + row0, &ts->full[s]);
+                ++pr.g;
+                if (++pr.chunk == nchunks) {
+                    pr.chunk = 0;
+                    if (o.kind == 1 && pr.seg < ts->seg_hi[pr.op]) ++pr.seg;
+                    else { ++pr.op; pr.seg = 0; }
+                }
+                return;
+            }
+        };
+        if (threadIdx.x == 0 && p.debug < 2) {
+            for (int i = 0; i < PF4; ++i) produce();
+        }
+        __syncwarp();
+
+        for (int oi = 0; oi < p.n_ops; ++oi) {
+            const Op4 op = ts->ops[oi];
+            const bool identity = (op.kind == 0 && ts->prow[oi] < 0);
+            const RateInfo* ri = (op.kind == 1) ? &p.rate[(size_t)w * p.n_rate + op.key] : nullptr;
+            int gi = 0;
+            double ra = 0.0, rd = 0.0;
+            if (op.kind == 1) rate_row(p, op, ri, my_row, gi, ra, rd);
+
+            double acc[NTT][2];
+#pragma unroll
+            for (int n = 0; n < NTT; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+
+            // ---------------- GEMM(s) ----------------
+            const int nseg = identity ? 0 : (op.kind == 0 ? 1 : max(0, ts->seg_hi[oi] - ts->seg_lo[oi] + 1));
+            for (int si = 0; si < nseg; ++si) {
+                double wgt = 1.0;
+                if (op.kind == 1) {
+                    const int seg = ts->seg_lo[oi] + si;
+                    wgt = (gi >= 0) ? ((seg == gi - 1 ? ra : 0.0) + (seg == gi ? rd : 0.0)) : 0.0;
+                }
+                for (int c = 0; c < nchunks; ++c) {
+                    if (threadIdx.x == 0 && p.debug < 2) produce();
+                    __syncwarp();
+                    const unsigned s = g % NS4;
+                    if (p.debug < 2) mbar_wait(&ts->full[s], (g / NS4) & 1u);
+                    const unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
+                    if (p.debug != 1) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int oq = ((q ^ z) << 4);
+                            double a;
+                            if (op.leaf >= 0) a = *reinterpret_cast<const double*>(st + a_base + oq);
+                            else a = abuf[((2 * c + (q >> 1)) * 32 + lane) * 2 + (q & 1)];
+                            if (op.kind == 1) a *= wgt;
+                            const unsigned char* pb = st + b_base + oq;
+#pragma unroll
+                            for (int n = 0; n < NTT; ++n) {
+                                const double b = *reinterpret_cast<const double*>(pb + n * 1024);
+                                dmma(acc[n][0], acc[n][1], a, b);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (p.debug < 2 && lane == 0) mbar_arrive(&ts->empty[s]);
+                    ++g;
+                }
+            }
+
+            // ---------------- post-op (warp local) ----------------
+            const bool row_ident = identity || (op.kind == 1 && gi < 0);
+            if (row_ident) {
+                // identity short-cut (transition_data_2d.py:184-187) or padding row: the message is the operand itself
+                if (op.leaf >= 0) {
+                    const double* e = p.E + (size_t)op.leaf * p.E_leaf_stride + (size_t)my_row * Fp;
+#pragma unroll
+                    for (int n = 0; n < NTT; ++n) {
+                        if (8 * n < Fp) {
+                            acc[n][0] = e[kperm(8 * n + 2 * kk)];
+                            acc[n][1] = e[kperm(8 * n + 2 * kk + 1)];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int n = 0; n < NTT; ++n) {
+                        const double2 v = *reinterpret_cast<const double2*>(abuf + (n * 32 + lane) * 2);
+                        acc[n][0] = v.x; acc[n][1] = v.y;
+                    }
+                }
+            } else if (op.kind == 1) {
+                // row renormalisation of the blended matrix (_util.pyx:138-147)
+                const double* s2 = p.pool + ri->off + (size_t)(gi - ri->gbase) * blk + (size_t)Fp * Fp;
+                const double* s1 = s2 - blk;
+                const bool two = (gi > 0 && ra != 0.0);
+#pragma unroll
+                for (int n = 0; n < NTT; ++n) {
+                    if (8 * n < Fp) {
+                        const int col = 8 * n + 2 * kk;
+                        double den0 = rd * s2[col], den1 = rd * s2[col + 1];
+                        if (two) { den0 += ra * s1[col]; den1 += ra * s1[col + 1]; }
+                        if (den0 > 1.0) acc[n][0] /= den0;
+                        if (den1 > 1.0) acc[n][1] /= den1;
+                    }
+                }
+            }
+
+            if (p.Yout != nullptr) {
+                double* yo = p.Yout + ((size_t)w * p.R_pad + my_row) * Fp + 2 * kk;
+#pragma unroll
+                for (int n = 0; n < NTT; ++n)
+                    if (8 * n < Fp) *reinterpret_cast<double2*>(yo + 8 * n) = make_double2(acc[n][0], acc[n][1]);
+                continue;
+            }
+
+            if (op.store_slot >= 0) {
+                // not the last child: park the message (or fold it into the siblings parked so far)
+                double2* sl = reinterpret_cast<double2*>(my_scratch + (size_t)op.store_slot * NTT * 64) + lane;
+                if (!op.store_first) {
+#pragma unroll
+                    for (int n = 0; n < NTT; ++n) { const double2 v = sl[n * 32]; acc[n][0] *= v.x; acc[n][1] *= v.y; }
+                }
+#pragma unroll
+                for (int n = 0; n < NTT; ++n) sl[n * 32] = make_double2(acc[n][0], acc[n][1]);
+                continue;
+            }
+            if (op.mul_slot >= 0) {
+                const double2* sl = reinterpret_cast<const double2*>(my_scratch + (size_t)op.mul_slot * NTT * 64) + lane;
+#pragma unroll
+                for (int n = 0; n < NTT; ++n) { const double2 v = sl[n * 32]; acc[n][0] *= v.x; acc[n][1] *= v.y; }
+            }
+            if (!op.last) {
+                // chain: this product is the operand of the parent's branch, which is the next op
+                __syncwarp();
+#pragma unroll
+                for (int n = 0; n < NTT; ++n) *reinterpret_cast<double2*>(abuf + (n * 32 + lane) * 2) = make_double2(acc[n][0], acc[n][1]);
+                __syncwarp();
+            } else {
+                // root reduction (_likes.pyx:312-322, 426-442)
+                const double* sv = p.stat + (size_t)w * Fp + 2 * kk;
+                double dot = 0.0;
+#pragma unroll
+                for (int n = 0; n < NTT; ++n)
+                    if (8 * n < Fp) dot += acc[n][0] * sv[8 * n] + acc[n][1] * sv[8 * n + 1];
+                dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+                if (kk == 0) {
+                    double v = 0.0;
+                    if (my_row < p.L) v = log(dot);
+                    else if (my_row < p.R) p.asc_dot[(size_t)w * (p.R - p.L) + (my_row - p.L)] = dot;
+                    ts->rowval[warp * 8 + x] = v;
+                }
+            }
+        }  // ops
+
+        __syncthreads();   // rowval complete; every warp is done with the item's tables
+        if (p.Yout == nullptr && warp == 0) {
+            double part = ts->rowval[lane] + ts->rowval[lane + 32];
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o2);
+            if (lane == 0) p.tile_ll[(size_t)w * p.n_tiles + tile] = part;
+        }
+        __syncthreads();
+    }  // items
+}
+
+}  // namespace mope
