@@ -197,7 +197,7 @@ int make_tmap(CUtensorMap* out, const double* base, uint64_t rows, int Fp, int b
 int tree_prows(const mope_ctx* c) { return c->use_v4 ? c->ntt * 8 : 2 * c->tree_variant * 8; }
 // doubles of message scratch for a full grid
 size_t scratch_doubles(const mope_ctx* c) {
-    return c->use_v4 ? (size_t)c->num_sms * 8 * c->max_slots4 * c->ntt * 64 : (size_t)c->num_sms * c->max_slots * TM * c->Fp;
+    return c->use_v4 ? (size_t)c->num_sms * 8 * (c->max_slots4 + 1) * c->ntt * 64 : (size_t)c->num_sms * c->max_slots * TM * c->Fp;
 }
 
 // searchsorted(side='left')

@@ -20,8 +20,9 @@
 
 namespace mope {
 
-constexpr int NS4 = 3;   // ring stages
-constexpr int PF4 = 2;   // prefetch distance (chunks)
+constexpr int NS4 = 6;   // ring stages
+constexpr int PF4 = 4;   // prefetch distance (chunks)
+constexpr int MAX_UNITS = 1024;   // GEMM units (op x generation segment) of one item
 
 struct Op4 {
     int32_t leaf;         // >= 0: leaf column, A operand = emission rows (TMA ring); -1: A operand chained from the previous op
@@ -39,7 +40,7 @@ struct Tree4Params {
     CUtensorMap tmapP;      // matrix pool [n_blocks*(Fp+1)][Fp] (k-permuted columns), box 16 x 8*NTT
     const double* E;
     int64_t E_leaf_stride;
-    double* scratch;        // [gridDim.x][8 warps][n_slots][NTT][32][2]
+    double* scratch;        // [gridDim.x][8 warps][n_slots + 1][NTT][32][2]; the last slot of a warp is its chain buffer
     const Op4* ops;
     int32_t n_ops, n_slots;
     int32_t R, L, R_pad, Fp, F, NT, n_tiles, W, tile_block;
@@ -63,6 +64,9 @@ struct Tree4Smem {
     Op4 ops[MAX_OPS];
     int32_t prow[MAX_OPS];     // per item: pool row of a shared-matrix op (negative = identity)
     int32_t seg_lo[MAX_OPS], seg_hi[MAX_OPS];   // per item: generation-grid range of a rate op over the tile's rows
+    int32_t unit_first[MAX_OPS + 1];            // per item: first GEMM unit of every op (exclusive scan of unit counts)
+    int32_t unit_prow[MAX_UNITS];               // per item: pool row of every GEMM unit (op x segment), in execution order
+    int32_t unit_erow[MAX_UNITS];               // per item: emission row of the unit's A operand, -1 = chained operand
     double rowval[TM];         // root reduction: per-row log-likelihood terms
 };
 
@@ -72,8 +76,7 @@ struct Cfg4 {
     static constexpr int E_BYTES = TM * KC * 8;          // 8 KB
     static constexpr int P_BYTES = PROWS * KC * 8;
     static constexpr int STAGE_BYTES = E_BYTES + P_BYTES;  // multiples of 1024
-    static constexpr int ABUF_BYTES = 8 * NTT * 32 * 16;   // chained operand, fragment layout [warp][n][lane][2]
-    static constexpr size_t SMEM_BYTES = (size_t)NS4 * STAGE_BYTES + ABUF_BYTES + sizeof(Tree4Smem) + 1024;
+    static constexpr size_t SMEM_BYTES = (size_t)NS4 * STAGE_BYTES + sizeof(Tree4Smem) + 1024;
 };
 
 // per-row time weights of an age-scaled branch (transition_data_2d.py:183-224)
@@ -93,19 +96,12 @@ __device__ __forceinline__ void rate_row(const Tree4Params& p, const Op4& op, co
     if (gi == 0) a = 0.0;  // wrapped neighbour carries an exactly-zero weight
 }
 
-// the copy-issuing lane's cursor over the item's chunk sequence
-struct Producer4 {
-    int op, seg, chunk;   // next chunk to issue
-    unsigned g;           // its ring index
-};
-
 template <int NTT>
 __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constant__ Tree4Params p) {
     using Cfg = Cfg4<NTT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    double* abuf_all = reinterpret_cast<double*>(ring + (size_t)NS4 * Cfg::STAGE_BYTES);
-    Tree4Smem* ts = reinterpret_cast<Tree4Smem*>(ring + (size_t)NS4 * Cfg::STAGE_BYTES + Cfg::ABUF_BYTES);
+    Tree4Smem* ts = reinterpret_cast<Tree4Smem*>(ring + (size_t)NS4 * Cfg::STAGE_BYTES);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = lane >> 2, kk = lane & 3;
@@ -113,8 +109,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
     const int nchunks = Fp / KC;
     const int blk_rows = Fp + 1;
     const size_t blk = (size_t)Fp * Fp + Fp;
-    double* abuf = abuf_all + (size_t)warp * NTT * 64;                       // [n][lane][2]
-    double* my_scratch = p.scratch + ((size_t)blockIdx.x * 8 + warp) * p.n_slots * NTT * 64;
+    double* my_scratch = p.scratch + ((size_t)blockIdx.x * 8 + warp) * (p.n_slots + 1) * NTT * 64;
+    // Chained operand: thread-private values in fragment layout [n][lane][2].  The thread that writes an element is the
+    // one that reads it back (its C fragment is its A fragment), so plain global accesses in program order suffice;
+    // the buffer lives in L2 and the reads run one chunk ahead of the MMAs.
+    double* abuf = my_scratch + (size_t)p.n_slots * NTT * 64;
     // fragment addressing inside a stage (128 B swizzle, see kernels.cuh)
     const int z = x ^ ((kk >> 1) << 2);
     const int hb = (kk & 1) << 3;
@@ -174,46 +173,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         }
         __syncthreads();
 
-        // ---- copy producer (lane 0 of warp 0): walks the same unit sequence as the consumers, PF4 chunks ahead ----
-        Producer4 pr;
-        pr.op = 0; pr.seg = 0; pr.chunk = 0; pr.g = g;
-        auto produce = [&]() {
-            // advance to the next op that has chunks
-            while (pr.op < p.n_ops) {
-                const Op4& o = ts->ops[pr.op];
-                bool has = false;
-                int p_row = 0;
-                if (o.kind == 0) {
-                    if (ts->prow[pr.op] >= 0) { has = true; p_row = ts->prow[pr.op]; }
-                } else {
-                    const int lo = ts->seg_lo[pr.op], hi = ts->seg_hi[pr.op];
-                    if (pr.chunk == 0 && pr.seg == 0) pr.seg = lo;
-                    if (pr.seg <= hi) {
-                        has = true;
-                        const RateInfo* ri = &p.rate[(size_t)w * p.n_rate + o.key];
-                        p_row = (int)(ri->off / Fp) + (pr.seg - ri->gbase) * blk_rows;
-                    }
-                }
-                if (!has) { ++pr.op; pr.seg = 0; pr.chunk = 0; continue; }
-                const unsigned s = pr.g % NS4;
-                mbar_wait(&ts->empty[s], ((pr.g / NS4) & 1u) ^ 1u);
-                unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
-                mbar_expect_tx(&ts->full[s], (unsigned)(Cfg::P_BYTES + (o.leaf >= 0 ? Cfg::E_BYTES : 0)));
-                tma_load_2d(st + Cfg::E_BYTES, &p.tmapP, pr.chunk * KC, p_row, &ts->full[s]);
-                if (o.leaf >= 0) tma_load_2d(st, &p.tmapE, pr.chunk * KC, o.leaf * p.R_pad + row0, &ts->full[s]);
-                ++pr.g;
-                if (++pr.chunk == nchunks) {
-                    pr.chunk = 0;
-                    if (o.kind == 1 && pr.seg < ts->seg_hi[pr.op]) ++pr.seg;
-                    else { ++pr.op; pr.seg = 0; }
-                }
-                return;
+        // ---- flat list of the item's GEMM units (op x segment) so that ANY warp can issue chunk number k of the item:
+        //      the copies are issued round-robin by lane 0 of warp (k mod 8), which spreads the issue cost evenly ----
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int i = 0; i < p.n_ops; ++i) {
+                const Op4& o = ts->ops[i];
+                ts->unit_first[i] = n;
+                n += (o.kind == 0) ? (ts->prow[i] >= 0 ? 1 : 0) : max(0, ts->seg_hi[i] - ts->seg_lo[i] + 1);
             }
-        };
-        if (threadIdx.x == 0 && p.debug < 2) {
-            for (int i = 0; i < PF4; ++i) produce();
+            ts->unit_first[p.n_ops] = n;
         }
+        __syncthreads();
+        const int n_units = ts->unit_first[p.n_ops];
+        if (n_units > MAX_UNITS) { asm volatile("trap;"); }
+        for (int i = threadIdx.x; i < p.n_ops; i += NTHREADS) {
+            const Op4& o = ts->ops[i];
+            const int u0 = ts->unit_first[i], cnt = ts->unit_first[i + 1] - u0;
+            const int erow = o.leaf >= 0 ? o.leaf * p.R_pad + row0 : -1;
+            if (o.kind == 0) {
+                if (cnt) { ts->unit_prow[u0] = ts->prow[i]; ts->unit_erow[u0] = erow; }
+            } else if (cnt) {
+                const RateInfo* ri = &p.rate[(size_t)w * p.n_rate + o.key];
+                const int base = (int)(ri->off / Fp) + (ts->seg_lo[i] - ri->gbase) * blk_rows;
+                for (int k2 = 0; k2 < cnt; ++k2) { ts->unit_prow[u0 + k2] = base + k2 * blk_rows; ts->unit_erow[u0 + k2] = erow; }
+            }
+        }
+        __syncthreads();
+        const int total_chunks = n_units * nchunks;
+        const unsigned g_item0 = g;
+        // issue chunk number `rel` of the item (called by one lane)
+        auto issue = [&](int rel) {
+            const int u = rel / nchunks, ch = rel - u * nchunks;
+            const unsigned gg = g_item0 + (unsigned)rel;
+            const unsigned s = gg % NS4;
+            mbar_wait(&ts->empty[s], ((gg / NS4) & 1u) ^ 1u);
+            unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
+            const int erow = ts->unit_erow[u];
+            mbar_expect_tx(&ts->full[s], (unsigned)(Cfg::P_BYTES + (erow >= 0 ? Cfg::E_BYTES : 0)));
+            tma_load_2d(st + Cfg::E_BYTES, &p.tmapP, ch * KC, ts->unit_prow[u], &ts->full[s]);
+            if (erow >= 0) tma_load_2d(st, &p.tmapE, ch * KC, erow, &ts->full[s]);
+        };
+        if (p.debug < 2 && lane == 0 && warp < PF4 && warp < total_chunks) issue(warp);
         __syncwarp();
+        int crel = 0;   // chunks of this item consumed so far
 
         for (int oi = 0; oi < p.n_ops; ++oi) {
             const Op4 op = ts->ops[oi];
@@ -235,9 +238,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                     const int seg = ts->seg_lo[oi] + si;
                     wgt = (gi >= 0) ? ((seg == gi - 1 ? ra : 0.0) + (seg == gi ? rd : 0.0)) : 0.0;
                 }
+                double an[4] = {0.0, 0.0, 0.0, 0.0};   // chained A values of the coming chunk
+                if (op.leaf < 0) {
+                    const double2 v0 = *reinterpret_cast<const double2*>(abuf + (0 * 32 + lane) * 2);
+                    const double2 v1 = *reinterpret_cast<const double2*>(abuf + (1 * 32 + lane) * 2);
+                    an[0] = v0.x; an[1] = v0.y; an[2] = v1.x; an[3] = v1.y;
+                }
                 for (int c = 0; c < nchunks; ++c) {
-                    if (threadIdx.x == 0 && p.debug < 2) produce();
+                    {
+                        const int rel = crel + PF4;
+                        if (p.debug < 2 && lane == 0 && (rel & 7) == warp && rel < total_chunks) issue(rel);
+                    }
                     __syncwarp();
+                    double ac[4] = {an[0], an[1], an[2], an[3]};
+                    if (op.leaf < 0 && c + 1 < nchunks) {
+                        const double2 v0 = *reinterpret_cast<const double2*>(abuf + ((2 * c + 2) * 32 + lane) * 2);
+                        const double2 v1 = *reinterpret_cast<const double2*>(abuf + ((2 * c + 3) * 32 + lane) * 2);
+                        an[0] = v0.x; an[1] = v0.y; an[2] = v1.x; an[3] = v1.y;
+                    }
                     const unsigned s = g % NS4;
                     if (p.debug < 2) mbar_wait(&ts->full[s], (g / NS4) & 1u);
                     const unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
@@ -247,7 +265,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                             const int oq = ((q ^ z) << 4);
                             double a;
                             if (op.leaf >= 0) a = *reinterpret_cast<const double*>(st + a_base + oq);
-                            else a = abuf[((2 * c + (q >> 1)) * 32 + lane) * 2 + (q & 1)];
+                            else a = ac[q];
                             if (op.kind == 1) a *= wgt;
                             const unsigned char* pb = st + b_base + oq;
 #pragma unroll
@@ -260,6 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                     __syncwarp();
                     if (p.debug < 2 && lane == 0) mbar_arrive(&ts->empty[s]);
                     ++g;
+                    ++crel;
                 }
             }
 
