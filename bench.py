@@ -389,8 +389,17 @@ def run_ours(args):
         # compulsory HBM bytes per launch (fused ideal): emissions once per walker pass + matrices + outputs
         n_leaves = len(inf.leaf_names[0])
         alg_bytes = (R * n_leaves * 208 * 8) * 1.0 + W * n_keys * (5 * F * F * 8)
-        roofline = {"bound": "tensor", "kernel": "tree_kernel<13> (fused pruning pass, mma.sync.m8n8k4.f64)", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        traffic = None
+        try:
+            # DRAM bytes of the dominant kernel from the committed ncu capture of this same workload (per launch)
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tj = json.load(f)
+            if args.loci == 10000 and args.leaves == 16 and W == 256 and F == 201:
+                traffic = tj["traffic_bytes_per_launch"]
+        except Exception:
+            pass
+        roofline = {"bound": "tensor", "kernel": "tree_kernel4<26> (fused pruning pass: TMA ring + mma.sync.m8n8k4.f64, warp-owned rows)", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, profiles/r01_traffic.json)",
                     "peak_source": "fp64 DMMA register-only loop measured live in this run (MEASURED_PEAKS.json has no fp64 entry; "
                                    "its dense-bf16 figure does not bound an fp64 kernel)",
                     "flops_per_launch": flops_per_launch, "branch_gemms_per_launch": int(gemm_ops),

@@ -339,9 +339,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 continue;
             }
             if (op.mul_slot >= 0) {
-                const double2* sl = reinterpret_cast<const double2*>(my_scratch + (size_t)op.mul_slot * NTT * 64) + lane;
+                const double* slot_base = my_scratch + (size_t)op.mul_slot * NTT * 64;
+                const double2* sl = reinterpret_cast<const double2*>(slot_base) + lane;
 #pragma unroll
                 for (int n = 0; n < NTT; ++n) { const double2 v = sl[n * 32]; acc[n][0] *= v.x; acc[n][1] *= v.y; }
+                // the parked product is dead now: drop its lines from L2 instead of letting them be written back to HBM
+                __syncwarp();
+                for (int line = lane; line < (NTT * 64 * 8) / 128; line += 32)
+                    asm volatile("discard.global.L2 [%0], 128;\n" ::"l"(slot_base + line * 16) : "memory");
             }
             if (!op.last) {
                 // chain: this product is the operand of the parent's branch, which is the next op

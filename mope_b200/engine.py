@@ -169,7 +169,10 @@ class Engine:
             self._out_pin = torch.empty(W, dtype=torch.float64, pin_memory=True)
             self._pipe_W = W
         status = np.zeros(W, dtype=np.int32)
-        bounds = np.linspace(0, W, min(n_chunks, max(W, 1)) + 1).astype(int)
+        # growing chunks: only the first (small) chunk's host work is exposed, every later one hides under the
+        # device work of its predecessor
+        fr = np.array([0.0, 1.0, 4.0, 8.0, 16.0]) / 16.0 if n_chunks == 4 else np.linspace(0, 1, n_chunks + 1)
+        bounds = np.unique(np.round(fr * W).astype(int))
         stat_pin_np = self._stat_pin.numpy()
         with torch.cuda.device(self.device):
             for i in range(len(bounds) - 1):
