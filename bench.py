@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--walkers", type=int, default=256, help="walkers per GPU")
     ap.add_argument("--breaks", type=float, default=0.005, help="min_bin_size of --breaks 0.5 m (0.005 -> F=201)")
     ap.add_argument("--grid", default="default", choices=["default", "small"])
+    ap.add_argument("--tree", default="fixed", choices=["fixed", "rates", "bottleneck"],
+                    help="fixed: cfg2 (default); rates: cfg3 (age-scaled leaf branches + one age-scaled internal); "
+                         "bottleneck: cfg4 (one ^ branch + age-scaled internal)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-walkers", type=int, default=0, help="walkers per step of the CPU sample (default: host cores)")
     return ap.parse_args()
@@ -57,18 +60,22 @@ def make_tables(args, device=None):
         gens, us = generate.DEFAULT_GENS, generate.DEFAULT_MUTS
     else:
         gens, us = [1, 2, 5, 10, 20, 50, 100, 200, 500, 1000, 2000, 3000], [1e-9, 1e-7, 1e-5, 1e-3]
-    return generate.generate_tables(N=1000, breaks=(0.5, args.breaks), gens=gens, us=us, device=device)
+    nbs = generate.DEFAULT_BOTS if args.tree == "bottleneck" else None
+    return generate.generate_tables(N=1000, breaks=(0.5, args.breaks), gens=gens, us=us, nbs=nbs, device=device)
 
 
 def make_workload(args):
     from mope_b200 import synth
-    ds = synth.make_dataset(args.loci, args.leaves, tree=synth.balanced_tree(args.leaves))
+    tree = synth.balanced_tree(args.leaves, rate_leaves=(args.tree == "rates"), rate_internal=(args.tree != "fixed"),
+                               bottleneck=(args.tree == "bottleneck"))
+    ds = synth.make_dataset(args.loci, args.leaves, tree=tree)
     return ds
 
 
 def workload_name(args, F):
-    return "cfg2: synthetic L=%d loci x S=%d tissues, balanced %d-leaf tree (B=%d fixed-length branches), F=%d, W=%d walkers/GPU" % (
-        args.loci, args.leaves, args.leaves, 2 * args.leaves - 2, F, args.walkers)
+    kind = {"fixed": "cfg2", "rates": "cfg3-like", "bottleneck": "cfg4-like"}[args.tree]
+    return "%s: synthetic L=%d loci x S=%d tissues, balanced %d-leaf tree (B=%d branches, %s), F=%d, W=%d walkers/GPU" % (
+        kind, args.loci, args.leaves, args.leaves, 2 * args.leaves - 2, args.tree, F, args.walkers)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -68,7 +68,7 @@ class PedigreeModel:
         return int(self.asc_mult.shape[1])
 
 
-def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame) -> PedigreeModel:
+def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort_rows: bool = True) -> PedigreeModel:
     tree = newick.loads(tree_str)[0]
     nodes = [nd for nd in tree.postorder() if nd is not tree]
     leaf_names = [nd.name for nd in nodes if nd.is_leaf]
@@ -138,6 +138,29 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame) -> P
         asc_mult = np.ascontiguousarray(np.array(uniq).T)
         fam_asc = np.array(fam_asc_l, dtype=np.int32)
 
+    if M > 0 and sort_rows and len(fam_ids) > 1:
+        # Age-scaled branches blend the two generation-grid matrices around N*age*rate, so a 64-row tile only needs
+        # the grid cells its rows fall into.  Order the families along a k-d tree of their (log) multiplier values:
+        # tiles become narrow in EVERY multiplier column at once.  Row order does not change any result beyond the
+        # association order of the final sum over loci.
+        rank_of_fam_pos = np.empty(len(fam_ids), dtype=np.int64)
+        rank_of_fam_pos[_kd_order(np.log(np.maximum(fam_mult.T, 1e-300)), leaf_size=8)] = np.arange(len(fam_ids))
+        pos_of_fam = {}
+        for i, f in enumerate(fam_ids):
+            pos_of_fam.setdefault(f, i)
+        locus_rank = np.array([rank_of_fam_pos[pos_of_fam[f]] if f in pos_of_fam else len(fam_ids) for f in family])
+        order = np.argsort(locus_rank, kind="stable")
+        X, n, family = np.ascontiguousarray(X[order]), np.ascontiguousarray(n[order]), family[order]
+        row_mult = np.ascontiguousarray(row_mult[:, order])
+        # distinct ascertainment pairs in the same order
+        uniq_rank = np.full(asc_mult.shape[1], len(fam_ids), dtype=np.int64)
+        np.minimum.at(uniq_rank, fam_asc, rank_of_fam_pos)
+        uorder = np.argsort(uniq_rank, kind="stable")
+        new_index = np.empty_like(uorder)
+        new_index[uorder] = np.arange(len(uorder))
+        asc_mult = np.ascontiguousarray(asc_mult[:, uorder])
+        fam_asc = new_index[fam_asc].astype(np.int32)
+
     idx_of = {id(nd): i for i, nd in enumerate(nodes)}
     idx_of[id(tree)] = len(nodes)
     br_parent = np.array([idx_of[id(nd.parent)] for nd in nodes], dtype=np.int32)
@@ -150,6 +173,25 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame) -> P
                          counts=X, coverage=n, family=family, ages=ages, row_mult=np.ascontiguousarray(row_mult),
                          asc_mult=asc_mult, fam_asc=fam_asc, fam_count=counts.astype(np.float64),
                          br_parent=br_parent, br_leaf=br_leaf, br_mult=br_mult, br_bottleneck=br_bott)
+
+
+def _kd_order(P: np.ndarray, leaf_size: int = 8) -> np.ndarray:
+    """Indices of the rows of P [n, d] in k-d tree order (recursive median split along the widest coordinate)."""
+    out = []
+    stack = [np.arange(P.shape[0])]
+    while stack:
+        idx = stack.pop()
+        if idx.shape[0] <= leaf_size:
+            out.append(idx)
+            continue
+        sub = P[idx]
+        col = int(np.argmax(sub.max(axis=0) - sub.min(axis=0)))
+        o = np.argsort(sub[:, col], kind="stable")
+        half = idx.shape[0] // 2
+        # LIFO: push the upper half first so that the lower half comes out first
+        stack.append(idx[o[half:]])
+        stack.append(idx[o[:half]])
+    return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
 
 
 def fam_lgamma(counts: np.ndarray) -> np.ndarray:

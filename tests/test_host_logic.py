@@ -51,7 +51,8 @@ def test_newick_errors():
 def test_model_compile_matches_reference(name):
     case = CASES[name]
     for k, ped in enumerate(case["peds"]):
-        pm = model.compile_pedigree(model.read_table(ped["data"], True), ped["tree"], model.read_table(ped["ages"], True))
+        pm = model.compile_pedigree(model.read_table(ped["data"], True), ped["tree"], model.read_table(ped["ages"], True),
+                                    sort_rows=False)
         assert pm.branch_names == case["branch_names"][k]
         assert pm.leaf_names == case["leaf_names"][k]
         assert pm.num_loci == int(OUT[name + "/num_loci_%d" % k])
@@ -65,6 +66,29 @@ def test_model_compile_matches_reference(name):
         for j, m in enumerate(pm.multipliernames):
             np.testing.assert_array_equal(pm.row_mult[j], o.row_mult[m])
             np.testing.assert_array_equal(pm.asc_mult[j][pm.fam_asc], np.asarray(o.ages[m], dtype=np.float64))
+
+
+def test_row_sorting_is_a_consistent_permutation():
+    """The k-d ordering of families (narrow age ranges per 64-row tile) only permutes rows; every row keeps its
+    counts, coverage, family and multiplier values, and families map to the same ascertainment multiplier tuples."""
+    ped = CASES["example_both"]["peds"][0]
+    args = (model.read_table(ped["data"], True), ped["tree"], model.read_table(ped["ages"], True))
+    a = model.compile_pedigree(*args, sort_rows=False)
+    b = model.compile_pedigree(*args, sort_rows=True)
+
+    def rows(pm):
+        return sorted((tuple(np.nan_to_num(pm.counts[i], nan=-1.0)), tuple(pm.coverage[i]), pm.family[i], tuple(pm.row_mult[:, i]))
+                      for i in range(pm.num_loci))
+    assert rows(a) == rows(b)
+    assert not np.array_equal(a.family, b.family)          # it did reorder something
+    np.testing.assert_array_equal(a.fam_count, b.fam_count)
+    for f in range(a.n_fam):
+        np.testing.assert_array_equal(a.asc_mult[:, a.fam_asc[f]], b.asc_mult[:, b.fam_asc[f]])
+    # families of neighbouring rows are close in every multiplier column: tile-wise spread shrinks
+    def tile_spread(pm, tile=16):
+        lm = np.log(pm.row_mult)
+        return np.mean([np.ptp(lm[:, i:i + tile], axis=1).max() for i in range(0, pm.num_loci, tile)])
+    assert tile_spread(b) < 0.6 * tile_spread(a)
 
 
 def test_stationary_distribution_bit_identical_to_reference():
