@@ -278,6 +278,92 @@ class Inference(object):
             print("@@", v, self.logprior(self.fold(x)))
         return v
 
+    # ------------------------------------------------------------------------------------------
+    # MCMC driver (inference.py:1248-1363) on top of the batched posterior
+    # ------------------------------------------------------------------------------------------
+    def translate_positions(self, pos):
+        """mope/_util.pyx:29-53: log10 -> natural scale for the chain file; drift within one decade of its lower bound is
+        reported as 0 (point mass) with a NaN mutation rate; root parameters stay in log10."""
+        pos = np.asarray(pos, dtype=np.float64)
+        ret = pos.copy()
+        nv = self.num_varnames
+        zero = pos[:, :nv] <= self.lower[:nv] + 1
+        ret[:, :nv] = np.where(zero, 0.0, 10 ** pos[:, :nv])
+        ret[:, nv:2 * nv] = np.where(zero, np.nan, 10 ** pos[:, nv:2 * nv])
+        return ret
+
+    @staticmethod
+    def print_csv_lines(arr, lnprobs, file=None):
+        """mope/_util.pyx:17-26 (same print calls, hence the same number formatting)."""
+        import sys
+        file = file or sys.stdout
+        npos, ncols = arr.shape
+        for i in range(npos):
+            print(lnprobs[i], "\t", sep="", end="", file=file)
+            for j in range(ncols - 1):
+                print(arr[i, j], "\t", sep="", end="", file=file)
+            print(arr[i, ncols - 1], file=file)
+
+    def _get_initial_mcmc_position(self, num_walkers, prev_chain, rng, file=None):
+        """inference.py:1248-1319.  Fresh start: uniform in the prior box (log10 units) until every walker has a finite
+        likelihood and prior.  `prev_chain`: last num_walkers rows of a chain file; the file holds translated values, which
+        are mapped back to log10 (zero drift -> half a decade above its lower bound, NaN mutation -> redrawn); the reference
+        feeds the translated values back unchanged, which restarts in natural units."""
+        import sys
+        import pandas as pd
+        nv = self.num_varnames
+        if prev_chain is not None:
+            try:
+                prev = pd.read_csv(prev_chain, sep="\t", header=None, dtype=np.float64, comment="#")
+            except Exception:
+                prev = pd.read_csv(prev_chain, sep="\t", header=0, dtype=np.float64, comment="#")
+            vals = prev.iloc[-num_walkers:, 1:].values
+            if vals.shape != (num_walkers, self.ndim):
+                raise ValueError("previous chain does not hold {} walkers of dimension {}".format(num_walkers, self.ndim))
+            pos = np.empty_like(vals)
+            drift, mut = vals[:, :nv], vals[:, nv:2 * nv]
+            zero = ~(drift > 0)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                pos[:, :nv] = np.where(zero, self.lower[:nv] + 0.5, np.log10(drift))
+                redraw = rng.uniform(np.tile(self.lower[nv:2 * nv], (num_walkers, 1)), np.tile(self.upper[nv:2 * nv], (num_walkers, 1)))
+                pos[:, nv:2 * nv] = np.where(np.isfinite(mut) & (mut > 0), np.log10(mut), redraw)
+            pos[:, 2 * nv:] = vals[:, 2 * nv:]
+            return pos
+        while True:
+            pos = rng.uniform(np.tile(self.lower, (num_walkers, 1)), np.tile(self.upper, (num_walkers, 1)))
+            if not self.log_unif_drift:
+                pos[:, :nv] = np.log10(rng.uniform(np.tile(10 ** self.lower[:nv], (num_walkers, 1)),
+                                                   np.tile(10 ** self.upper[:nv], (num_walkers, 1))))
+            logl_val = self.loglike_batch(pos, raise_on_error=False)
+            logp_val = np.array([self.logprior(x) for x in pos])
+            if np.all(np.isfinite(logl_val)) and np.all(np.isfinite(logp_val)):
+                return pos
+            if not np.all(np.isfinite(logl_val)):
+                print("# warning: attempted start at initial position where log-likelihood is not finite", file=file or sys.stdout)
+            if not np.all(np.isfinite(logp_val)):
+                print("# warning: attempted start at initial position where prior is not finite", file=file or sys.stdout)
+
+    def run_mcmc(self, num_iter, num_walkers, num_processes=1, mpi=False, prev_chain=None, start_from="prior", init_norm_sd=0.2,
+                 chain_alpha=2.0, init_pos=None, pool=None, seed=None, file=None):
+        """inference.py:1322-1363 with the built-in stretch-move sampler; every half-step is one device call.  `pool`,
+        `num_processes` and `mpi` are accepted for signature compatibility and ignored (the GPU is the pool)."""
+        import sys
+        from .ensemble import EnsembleSampler
+        global inf_data
+        inf_data = self
+        file = file or sys.stdout
+        print("# " + " ".join(sys.argv), file=file)
+        rng = np.random.RandomState(seed)
+        if init_pos is None:
+            init_pos = self._get_initial_mcmc_position(num_walkers, prev_chain, rng, file=file)
+        print(self.header, file=file)
+        sampler = EnsembleSampler(num_walkers, self.ndim, self.log_posterior_batch, a=chain_alpha,
+                                  seed=None if seed is None else seed + 1)
+        for ps, lnprobs, _state in sampler.sample(init_pos, iterations=num_iter):
+            self.print_csv_lines(self.translate_positions(ps), lnprobs, file=file)
+        print("# mean acceptance across chains:", np.mean(sampler.acceptance_fraction), file=file)
+        return sampler
+
     def close(self):
         self.engine.close()
 

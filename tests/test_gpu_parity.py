@@ -197,3 +197,42 @@ def test_gpu_pool_map(inf_both):
     assert H.relerr(got, OUT["example_both/loglike"][:5]).max() <= RTOL_LL
     assert pool.map(minf.logp, list(X)) == [inf_both.logprior(x) for x in X]
     assert pool.map(lambda v: float(v.sum()), list(X)) == [float(x.sum()) for x in X]
+
+
+def test_run_mcmc_chain_file_and_resume(tmp_path):
+    """Inference.run_mcmc: chain file format of the reference (print_csv_lines / translate_positions), the printed
+    log-posteriors belong to the printed positions, and --prev-chain style resume."""
+    import io
+    I = _inference(CASES["test_rate_two_loci"])
+    try:
+        nw, nit = 2 * I.ndim + 2, 6
+        buf = io.StringIO()
+        sampler = I.run_mcmc(nit, nw, chain_alpha=1.4, seed=11, file=buf)
+        lines = buf.getvalue().splitlines()
+        assert lines[0].startswith("# ") and lines[1] == I.header and lines[-1].startswith("# mean acceptance across chains:")
+        body = [l for l in lines[2:-1]]
+        assert len(body) == nw * nit
+        vals = np.array([[float(t) for t in l.split("\t")] for l in body])
+        assert vals.shape == (nw * nit, I.ndim + 1)
+        nv = I.num_varnames
+        # zero drift <=> NaN mutation rate; otherwise natural-scale values inside the prior box
+        zero = vals[:, 1:1 + nv] == 0
+        assert np.array_equal(zero, np.isnan(vals[:, 1 + nv:1 + 2 * nv]))
+        assert np.all(np.isfinite(vals[:, 0]))
+        # last ensemble: recompute the log-posterior of the non-degenerate walkers from the printed values
+        last = vals[-nw:]
+        ok = ~zero[-nw:].any(axis=1)
+        if ok.any():
+            x = last[ok, 1:].copy()
+            x[:, :2 * nv] = np.log10(x[:, :2 * nv])
+            lp = I.log_posterior_batch(x)
+            assert (np.abs(lp - last[ok, 0]) / np.abs(last[ok, 0])).max() < 1e-9
+        assert 0.0 <= np.mean(sampler.acceptance_fraction) <= 1.0
+        # resume from the written chain
+        fn = tmp_path / "chain.txt"
+        fn.write_text(buf.getvalue())
+        buf2 = io.StringIO()
+        I.run_mcmc(2, nw, prev_chain=str(fn), chain_alpha=1.4, seed=5, file=buf2)
+        assert len([l for l in buf2.getvalue().splitlines() if not l.startswith("#")]) == 1 + 2 * nw
+    finally:
+        I.close()
