@@ -22,7 +22,6 @@ namespace mope {
 
 constexpr int NS4 = 6;   // ring stages
 constexpr int PF4 = 4;   // prefetch distance (chunks)
-constexpr int MAX_UNITS = 1024;   // GEMM units (op x generation segment) of one item
 
 struct Op4 {
     int32_t leaf;         // >= 0: leaf column, A operand = emission rows (TMA ring); -1: A operand chained from the previous op
@@ -64,9 +63,8 @@ struct Tree4Smem {
     Op4 ops[MAX_OPS];
     int32_t prow[MAX_OPS];     // per item: pool row of a shared-matrix op (negative = identity)
     int32_t seg_lo[MAX_OPS], seg_hi[MAX_OPS];   // per item: generation-grid range of a rate op over the tile's rows
-    int32_t unit_first[MAX_OPS + 1];            // per item: first GEMM unit of every op (exclusive scan of unit counts)
-    int32_t unit_prow[MAX_UNITS];               // per item: pool row of every GEMM unit (op x segment), in execution order
-    int32_t unit_erow[MAX_UNITS];               // per item: emission row of the unit's A operand, -1 = chained operand
+    int32_t unit_first[MAX_OPS + 1];            // per item: first GEMM unit (op x generation segment) of every op
+    int32_t unit_prow0[MAX_OPS];                // per item: pool row of the op's first unit (later segments: + k*(Fp+1))
     double rowval[TM];         // root reduction: per-row log-likelihood terms
 };
 
@@ -186,18 +184,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         }
         __syncthreads();
         const int n_units = ts->unit_first[p.n_ops];
-        if (n_units > MAX_UNITS) { asm volatile("trap;"); }
         for (int i = threadIdx.x; i < p.n_ops; i += NTHREADS) {
             const Op4& o = ts->ops[i];
-            const int u0 = ts->unit_first[i], cnt = ts->unit_first[i + 1] - u0;
-            const int erow = o.leaf >= 0 ? o.leaf * p.R_pad + row0 : -1;
-            if (o.kind == 0) {
-                if (cnt) { ts->unit_prow[u0] = ts->prow[i]; ts->unit_erow[u0] = erow; }
-            } else if (cnt) {
-                const RateInfo* ri = &p.rate[(size_t)w * p.n_rate + o.key];
-                const int base = (int)(ri->off / Fp) + (ts->seg_lo[i] - ri->gbase) * blk_rows;
-                for (int k2 = 0; k2 < cnt; ++k2) { ts->unit_prow[u0 + k2] = base + k2 * blk_rows; ts->unit_erow[u0 + k2] = erow; }
+            int r0 = ts->prow[i];
+            if (o.kind == 1) {
+                r0 = 0;
+                if (ts->seg_hi[i] >= ts->seg_lo[i]) {
+                    const RateInfo* ri = &p.rate[(size_t)w * p.n_rate + o.key];
+                    r0 = (int)(ri->off / Fp) + (ts->seg_lo[i] - ri->gbase) * blk_rows;
+                }
             }
+            ts->unit_prow0[i] = r0;
         }
         __syncthreads();
         const int total_chunks = n_units * nchunks;
@@ -205,13 +202,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         // issue chunk number `rel` of the item (called by one lane)
         auto issue = [&](int rel) {
             const int u = rel / nchunks, ch = rel - u * nchunks;
+            // the op that owns unit u: last op with unit_first[op] <= u (ops without units have empty ranges)
+            int lo = 0, hi = p.n_ops - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (ts->unit_first[mid] <= u) lo = mid; else hi = mid - 1;
+            }
+            const Op4& o = ts->ops[lo];
+            const int prow_u = ts->unit_prow0[lo] + (u - ts->unit_first[lo]) * blk_rows;
+            const int erow = o.leaf >= 0 ? o.leaf * p.R_pad + row0 : -1;
             const unsigned gg = g_item0 + (unsigned)rel;
             const unsigned s = gg % NS4;
             mbar_wait(&ts->empty[s], ((gg / NS4) & 1u) ^ 1u);
             unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
-            const int erow = ts->unit_erow[u];
             mbar_expect_tx(&ts->full[s], (unsigned)(Cfg::P_BYTES + (erow >= 0 ? Cfg::E_BYTES : 0)));
-            tma_load_2d(st + Cfg::E_BYTES, &p.tmapP, ch * KC, ts->unit_prow[u], &ts->full[s]);
+            tma_load_2d(st + Cfg::E_BYTES, &p.tmapP, ch * KC, prow_u, &ts->full[s]);
             if (erow >= 0) tma_load_2d(st, &p.tmapE, ch * KC, erow, &ts->full[s]);
         };
         if (p.debug < 2 && lane == 0 && warp < PF4 && warp < total_chunks) issue(warp);
