@@ -79,10 +79,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("MOPE_B200_LIB", LIB_PATH)   # kernel-tuning experiments load a variant build
+    if not os.path.exists(path):
         raise RuntimeError("mope_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                           "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+                           "(nvcc, sm_100a).  There is no CPU fallback." % path)
+    L = C.CDLL(path)
     dp, vp, ip = C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int32)
     L.mope_b200_arena_bytes.argtypes = [C.POINTER(TablesDesc), C.POINTER(ModelDesc), C.POINTER(C.c_size_t)]
     L.mope_b200_create.argtypes = [C.POINTER(TablesDesc), C.POINTER(ModelDesc), C.c_int, vp, C.c_size_t, vp, C.POINTER(vp)]

@@ -73,6 +73,7 @@ struct Pedigree {
     // warp-owned-rows kernel (tree4.cuh): postorder schedule with chained messages
     Op4* ops4 = nullptr;
     std::vector<Op4> ops4_h;
+    int tmem_slot4 = -1;
     int n_slots4 = 0;
     int asc_offset = 0;
     CUtensorMap tmapE;
@@ -373,6 +374,11 @@ int compile_schedule4(const mope_pedigree_desc& pd, const std::vector<int>& fixe
     }
     if (out.ops4_h.empty() || !out.ops4_h.back().last) return fail(MOPE_E_INVALID, "schedule does not end at the root");
     out.n_slots4 = std::max(n_slots, 1);
+    // the slot that is written most often lives in tensor memory (tree4.cuh), the others in the L2 scratch
+    std::vector<int> parks(out.n_slots4, 0);
+    for (const Op4& o : out.ops4_h) if (o.store_slot >= 0) parks[o.store_slot]++;
+    out.tmem_slot4 = -1;
+    for (int i = 0, best = 0; i < out.n_slots4; ++i) if (parks[i] > best) { best = parks[i]; out.tmem_slot4 = i; }
     return 0;
 }
 
@@ -851,7 +857,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
                 t4.tmapE = P.tmapE; t4.tmapP = tmapP;
                 t4.E = P.E; t4.E_leaf_stride = (int64_t)P.R_pad * Fp;
                 t4.scratch = scratch;
-                t4.ops = P.ops4; t4.n_ops = (int)P.ops4_h.size(); t4.n_slots = c->max_slots4;
+                t4.ops = P.ops4; t4.n_ops = (int)P.ops4_h.size(); t4.n_slots = c->max_slots4; t4.tmem_slot = P.tmem_slot4;
                 t4.R = P.R; t4.L = P.L; t4.R_pad = P.R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = P.n_tiles; t4.W = Wc;
                 t4.tile_block = tile_block_default;
                 if (const char* e = getenv("MOPE_TILE_BLOCK")) t4.tile_block = std::max(1, std::min(P.n_tiles, atoi(e)));
@@ -1412,7 +1418,7 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
         if (int rc = make_tmap(&t4.tmapE, P.E, (uint64_t)R_pad, Fp, TM)) return rc;
         if (int rc = make_tmap(&t4.tmapP, P.pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + 1), Fp, tree_prows(c))) return rc;
         t4.E = P.E; t4.E_leaf_stride = (int64_t)R_pad * Fp; t4.scratch = P.Y /*unused*/; t4.ops = reinterpret_cast<const Op4*>(P.op);
-        t4.n_ops = 1; t4.n_slots = 1;
+        t4.n_ops = 1; t4.n_slots = 1; t4.tmem_slot = -1;
         t4.R = n_rows; t4.L = n_rows; t4.R_pad = R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = R_pad / TM; t4.W = 1;
         t4.tile_block = t4.n_tiles;
         t4.pool = P.pool; t4.mat_off = P.mo; t4.n_mat = 1; t4.n_rate = 1; t4.rate = P.rate; t4.mult = P.mult; t4.gens = c->gens_dev;

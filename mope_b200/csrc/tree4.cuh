@@ -5,10 +5,11 @@
 //   * the output of a branch GEMM sits in the warp's mma C fragments (thread (x, kk) holds bins 8n+2kk, 8n+2kk+1 of
 //     row x).  With the k index of an mma step taken as {8j + 2kk + h : kk = 0..3} those very registers are the A
 //     fragment of the NEXT branch (the parent's branch follows its last child in postorder), so chained messages
-//     go through a warp-private shared-memory buffer in fragment layout -- no global round trip, no proxy fence,
-//     no CTA-wide synchronisation;
-//   * only the message of a non-last child is parked in a warp-private scratch slot (fragment layout, coalesced
-//     16-byte accesses by the thread that later reads it back) and multiplied in when the last sibling arrives;
+//     go through warp-private TENSOR MEMORY columns (tcgen05.st / tcgen05.ld, thread i <-> TMEM lane i) -- no global
+//     round trip, no proxy fence, no CTA-wide synchronisation;
+//   * only the message of a non-last child is parked (fragment layout) and multiplied in when the last sibling
+//     arrives: the busiest slot of the schedule lives in tensor memory too, the others in an L2-resident scratch
+//     (coalesced 16-byte accesses by the thread that later reads them back);
 //   * the only shared resource is the TMA ring with the P chunks (and emission chunks for leaf branches); since no
 //     copy depends on an epilogue any more, one lane streams the whole item PF chunks ahead without ever stalling
 //     on a dependency.
@@ -20,8 +21,12 @@
 
 namespace mope {
 
-constexpr int NS4 = 6;   // ring stages
-constexpr int PF4 = 4;   // prefetch distance (chunks)
+#ifndef MOPE_NS4
+#define MOPE_NS4 6
+#define MOPE_PF4 4
+#endif
+constexpr int NS4 = MOPE_NS4;   // ring stages
+constexpr int PF4 = MOPE_PF4;   // prefetch distance (chunks); NS4 - PF4 >= 2 keeps the issuing lane from waiting on the slowest warp
 
 struct Op4 {
     int32_t leaf;         // >= 0: leaf column, A operand = emission rows (TMA ring); -1: A operand chained from the previous op
@@ -55,7 +60,8 @@ struct Tree4Params {
     double* tile_ll;
     double* asc_dot;
     double* Yout;
-    int32_t debug;
+    int32_t debug;           // measurement only, bit flags: 1 skip the MMAs, 2 skip the copies and ring barriers
+    int32_t tmem_slot;       // id of the parked-message slot that lives in tensor memory (-1: none)
 };
 
 struct Tree4Smem {
@@ -66,6 +72,7 @@ struct Tree4Smem {
     int32_t unit_first[MAX_OPS + 1];            // per item: first GEMM unit (op x generation segment) of every op
     int32_t unit_prow0[MAX_OPS];                // per item: pool row of the op's first unit (later segments: + k*(Fp+1))
     double rowval[TM];         // root reduction: per-row log-likelihood terms
+    uint32_t tmem_base;        // tcgen05.alloc result
 };
 
 template <int NTT>
@@ -94,6 +101,55 @@ __device__ __forceinline__ void rate_row(const Tree4Params& p, const Op4& op, co
     if (gi == 0) a = 0.0;  // wrapped neighbour carries an exactly-zero weight
 }
 
+// ---- tensor memory as warp-private scratch ----------------------------------------------------------------------
+// A message in fragment layout is thread-private (the thread that writes an element is the one that reads it back), so
+// it can live in TMEM: with the 32x32b shape thread i of warp w owns TMEM lane 32*(w%4)+i, and every warp gets 256 of
+// the 512 columns of its lane quarter.  One 16-wide chunk of a row (4 doubles per thread) is 8 columns.  Measured on
+// B200 (profiles/microbench/tmem_scratch.cu): tcgen05.st 317 B/clk/SM, tcgen05.ld 340 B/clk/SM, against 32 B/clk/SM
+// for the same bursts stored to global memory.
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, double v0, double v1, double v2, double v3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
+                 :: "r"(taddr),
+                    "r"(__double2loint(v0)), "r"(__double2hiint(v0)), "r"(__double2loint(v1)), "r"(__double2hiint(v1)),
+                    "r"(__double2loint(v2)), "r"(__double2hiint(v2)), "r"(__double2loint(v3)), "r"(__double2hiint(v3))
+                 : "memory");
+}
+// asynchronous: the registers are valid after tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ double u2d(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
+constexpr int TMEM_COLS = 512;        // whole tensor memory of the SM (one CTA per SM)
+constexpr int TMEM_WARP_COLS = 256;   // per warp: chain buffer at column 0, one parked slot after it
+
+// One 16-wide K chunk of a branch GEMM for the warp's 8 rows: 4 k steps x NTT n-tiles.  A comes from the emission chunk
+// in the stage (LEAF) or from the chained fragment values `ac`; RATE scales it by the row's segment weight.
+template <int NTT, bool LEAF, bool RATE, bool NO_LDS>
+__device__ __forceinline__ void chunk_mma(double (&acc)[NTT][2], const unsigned char* st, int a_base, int b_base, int z,
+                                          const double (&ac)[4], double wgt, int nq) {
+    double a[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (LEAF) a[q] = *reinterpret_cast<const double*>(st + a_base + ((q ^ z) << 4));
+        else a[q] = ac[q];
+        if (RATE) a[q] *= wgt;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q >= nq) break;   // all-padding k step (zero columns): nothing to add
+        const unsigned char* pb = st + b_base + ((q ^ z) << 4);
+#pragma unroll
+        for (int n = 0; n < NTT; ++n) {
+            const double b = NO_LDS ? wgt : *reinterpret_cast<const double*>(pb + n * 1024);
+            dmma(acc[n][0], acc[n][1], a[q], b);
+        }
+    }
+}
+
 template <int NTT>
 __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constant__ Tree4Params p) {
     using Cfg = Cfg4<NTT>;
@@ -108,10 +164,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
     const int blk_rows = Fp + 1;
     const size_t blk = (size_t)Fp * Fp + Fp;
     double* my_scratch = p.scratch + ((size_t)blockIdx.x * 8 + warp) * (p.n_slots + 1) * NTT * 64;
-    // Chained operand: thread-private values in fragment layout [n][lane][2].  The thread that writes an element is the
-    // one that reads it back (its C fragment is its A fragment), so plain global accesses in program order suffice;
-    // the buffer lives in L2 and the reads run one chunk ahead of the MMAs.
-    double* abuf = my_scratch + (size_t)p.n_slots * NTT * 64;
     // fragment addressing inside a stage (128 B swizzle, see kernels.cuh)
     const int z = x ^ ((kk >> 1) << 2);
     const int hb = (kk & 1) << 3;
@@ -123,7 +175,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     for (int i = threadIdx.x; i < p.n_ops; i += NTHREADS) ts->ops[i] = p.ops[i];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&ts->tmem_base)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    // Chained operand (the message of a node's last child, operand of the node's own branch = the next op) and the parked
+    // slot p.tmem_slot: warp-private tensor-memory columns
+    const uint32_t t_chain = ts->tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * TMEM_WARP_COLS);
+    const uint32_t t_slot = t_chain + NTT * 4;
+    static_assert(2 * NTT * 4 <= TMEM_WARP_COLS && NTT % 2 == 0, "chain buffer + one slot must fit the warp's TMEM columns");
+
+    // k steps of the last chunk that hold at least one real column (natural k = 16c + 8(q>>1) + (q&1) + 2kk)
+    int nq_last = 0;
+    for (int q = 0; q < 4; ++q) nq_last += (16 * (nchunks - 1) + 8 * (q >> 1) + (q & 1) < p.F) ? 1 : 0;
+    const bool no_mma = p.debug & 1, no_copy = p.debug & 2;
+    constexpr bool no_lds = false;
 
     unsigned g = 0;   // chunks consumed so far (ring position)
     const long long n_items = (long long)p.W * p.n_tiles;
@@ -219,7 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             tma_load_2d(st + Cfg::E_BYTES, &p.tmapP, ch * KC, prow_u, &ts->full[s]);
             if (erow >= 0) tma_load_2d(st, &p.tmapE, ch * KC, erow, &ts->full[s]);
         };
-        if (p.debug < 2 && lane == 0 && warp < PF4 && warp < total_chunks) issue(warp);
+        if (!no_copy && lane == 0 && warp < PF4 && warp < total_chunks) issue(warp);
         __syncwarp();
         int crel = 0;   // chunks of this item consumed so far
 
@@ -243,45 +312,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                     const int seg = ts->seg_lo[oi] + si;
                     wgt = (gi >= 0) ? ((seg == gi - 1 ? ra : 0.0) + (seg == gi ? rd : 0.0)) : 0.0;
                 }
-                double an[4] = {0.0, 0.0, 0.0, 0.0};   // chained A values of the coming chunk
-                if (op.leaf < 0) {
-                    const double2 v0 = *reinterpret_cast<const double2*>(abuf + (0 * 32 + lane) * 2);
-                    const double2 v1 = *reinterpret_cast<const double2*>(abuf + (1 * 32 + lane) * 2);
-                    an[0] = v0.x; an[1] = v0.y; an[2] = v1.x; an[3] = v1.y;
-                }
+                uint32_t an[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // chained A values of the coming chunk (tcgen05.ld in flight)
+                if (op.leaf < 0) tmem_ld4_issue(t_chain, an);
                 for (int c = 0; c < nchunks; ++c) {
                     {
                         const int rel = crel + PF4;
-                        if (p.debug < 2 && lane == 0 && (rel & 7) == warp && rel < total_chunks) issue(rel);
+                        if (!no_copy && lane == 0 && (rel & 7) == warp && rel < total_chunks) issue(rel);
                     }
                     __syncwarp();
-                    double ac[4] = {an[0], an[1], an[2], an[3]};
-                    if (op.leaf < 0 && c + 1 < nchunks) {
-                        const double2 v0 = *reinterpret_cast<const double2*>(abuf + ((2 * c + 2) * 32 + lane) * 2);
-                        const double2 v1 = *reinterpret_cast<const double2*>(abuf + ((2 * c + 3) * 32 + lane) * 2);
-                        an[0] = v0.x; an[1] = v0.y; an[2] = v1.x; an[3] = v1.y;
+                    double ac[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (op.leaf < 0) {
+                        tmem_wait_ld();
+                        ac[0] = u2d(an[0], an[1]); ac[1] = u2d(an[2], an[3]); ac[2] = u2d(an[4], an[5]); ac[3] = u2d(an[6], an[7]);
+                        if (c + 1 < nchunks) tmem_ld4_issue(t_chain + 8 * (c + 1), an);
                     }
                     const unsigned s = g % NS4;
-                    if (p.debug < 2) mbar_wait(&ts->full[s], (g / NS4) & 1u);
+                    if (!no_copy) mbar_wait(&ts->full[s], (g / NS4) & 1u);
+                    const int nq = (c + 1 == nchunks) ? nq_last : 4;
                     const unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
-                    if (p.debug != 1) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int oq = ((q ^ z) << 4);
-                            double a;
-                            if (op.leaf >= 0) a = *reinterpret_cast<const double*>(st + a_base + oq);
-                            else a = ac[q];
-                            if (op.kind == 1) a *= wgt;
-                            const unsigned char* pb = st + b_base + oq;
-#pragma unroll
-                            for (int n = 0; n < NTT; ++n) {
-                                const double b = *reinterpret_cast<const double*>(pb + n * 1024);
-                                dmma(acc[n][0], acc[n][1], a, b);
-                            }
+                    if (!no_mma) {
+                        // the four operand flavours get their own straight-line code: nothing but LDS + DMMA between k steps
+                        if (op.leaf >= 0) {
+                            if (op.kind == 1) chunk_mma<NTT, true, true, no_lds>(acc, st, a_base, b_base, z, ac, wgt, nq);
+                            else chunk_mma<NTT, true, false, no_lds>(acc, st, a_base, b_base, z, ac, wgt, nq);
+                        } else {
+                            if (op.kind == 1) chunk_mma<NTT, false, true, no_lds>(acc, st, a_base, b_base, z, ac, wgt, nq);
+                            else chunk_mma<NTT, false, false, no_lds>(acc, st, a_base, b_base, z, ac, wgt, nq);
                         }
                     }
                     __syncwarp();
-                    if (p.debug < 2 && lane == 0) mbar_arrive(&ts->empty[s]);
+                    if (!no_copy && lane == 0) mbar_arrive(&ts->empty[s]);
                     ++g;
                     ++crel;
                 }
@@ -289,9 +349,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
 
             // ---------------- post-op (warp local) ----------------
             const bool row_ident = identity || (op.kind == 1 && gi < 0);
-            if (row_ident) {
-                // identity short-cut (transition_data_2d.py:184-187) or padding row: the message is the operand itself
-                if (op.leaf >= 0) {
+            // identity short-cut (transition_data_2d.py:184-187) or padding row: the message is the operand itself
+            if (op.leaf >= 0) {
+                if (row_ident) {
                     const double* e = p.E + (size_t)op.leaf * p.E_leaf_stride + (size_t)my_row * Fp;
 #pragma unroll
                     for (int n = 0; n < NTT; ++n) {
@@ -300,14 +360,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                             acc[n][1] = e[kperm(8 * n + 2 * kk + 1)];
                         }
                     }
-                } else {
+                }
+            } else if (__any_sync(0xffffffffu, row_ident)) {
+                // tensor-memory loads are warp-wide: every lane reads, the lanes of identity rows keep the values
 #pragma unroll
-                    for (int n = 0; n < NTT; ++n) {
-                        const double2 v = *reinterpret_cast<const double2*>(abuf + (n * 32 + lane) * 2);
-                        acc[n][0] = v.x; acc[n][1] = v.y;
+                for (int c = 0; c < NTT / 2; ++c) {
+                    uint32_t r[8];
+                    tmem_ld4_issue(t_chain + 8 * c, r);
+                    tmem_wait_ld();
+                    if (row_ident) {
+                        acc[2 * c][0] = u2d(r[0], r[1]); acc[2 * c][1] = u2d(r[2], r[3]);
+                        acc[2 * c + 1][0] = u2d(r[4], r[5]); acc[2 * c + 1][1] = u2d(r[6], r[7]);
                     }
                 }
-            } else if (op.kind == 1) {
+            }
+            if (!row_ident && op.kind == 1) {
                 // row renormalisation of the blended matrix (_util.pyx:138-147)
                 const double* s2 = p.pool + ri->off + (size_t)(gi - ri->gbase) * blk + (size_t)Fp * Fp;
                 const double* s1 = s2 - blk;
@@ -332,18 +399,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 continue;
             }
 
+            __syncwarp();   // the tensor-memory instructions below are warp-wide
             if (op.store_slot >= 0) {
                 // not the last child: park the message (or fold it into the siblings parked so far)
-                double2* sl = reinterpret_cast<double2*>(my_scratch + (size_t)op.store_slot * NTT * 64) + lane;
-                if (!op.store_first) {
+                if (op.store_slot == p.tmem_slot) {
+                    if (!op.store_first) {
 #pragma unroll
-                    for (int n = 0; n < NTT; ++n) { const double2 v = sl[n * 32]; acc[n][0] *= v.x; acc[n][1] *= v.y; }
+                        for (int c = 0; c < NTT / 2; ++c) {
+                            uint32_t r[8];
+                            tmem_ld4_issue(t_slot + 8 * c, r);
+                            tmem_wait_ld();
+                            acc[2 * c][0] *= u2d(r[0], r[1]); acc[2 * c][1] *= u2d(r[2], r[3]);
+                            acc[2 * c + 1][0] *= u2d(r[4], r[5]); acc[2 * c + 1][1] *= u2d(r[6], r[7]);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < NTT / 2; ++c)
+                        tmem_st4(t_slot + 8 * c, acc[2 * c][0], acc[2 * c][1], acc[2 * c + 1][0], acc[2 * c + 1][1]);
+                    tmem_wait_st();
+                } else {
+                    double2* sl = reinterpret_cast<double2*>(my_scratch + (size_t)op.store_slot * NTT * 64) + lane;
+                    if (!op.store_first) {
+#pragma unroll
+                        for (int n = 0; n < NTT; ++n) { const double2 v = sl[n * 32]; acc[n][0] *= v.x; acc[n][1] *= v.y; }
+                    }
+#pragma unroll
+                    for (int n = 0; n < NTT; ++n) sl[n * 32] = make_double2(acc[n][0], acc[n][1]);
                 }
-#pragma unroll
-                for (int n = 0; n < NTT; ++n) sl[n * 32] = make_double2(acc[n][0], acc[n][1]);
                 continue;
             }
-            if (op.mul_slot >= 0) {
+            if (op.mul_slot >= 0 && op.mul_slot == p.tmem_slot) {
+#pragma unroll
+                for (int c = 0; c < NTT / 2; ++c) {
+                    uint32_t r[8];
+                    tmem_ld4_issue(t_slot + 8 * c, r);
+                    tmem_wait_ld();
+                    acc[2 * c][0] *= u2d(r[0], r[1]); acc[2 * c][1] *= u2d(r[2], r[3]);
+                    acc[2 * c + 1][0] *= u2d(r[4], r[5]); acc[2 * c + 1][1] *= u2d(r[6], r[7]);
+                }
+            } else if (op.mul_slot >= 0) {
                 const double* slot_base = my_scratch + (size_t)op.mul_slot * NTT * 64;
                 const double2* sl = reinterpret_cast<const double2*>(slot_base) + lane;
 #pragma unroll
@@ -355,10 +449,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             }
             if (!op.last) {
                 // chain: this product is the operand of the parent's branch, which is the next op
-                __syncwarp();
 #pragma unroll
-                for (int n = 0; n < NTT; ++n) *reinterpret_cast<double2*>(abuf + (n * 32 + lane) * 2) = make_double2(acc[n][0], acc[n][1]);
-                __syncwarp();
+                for (int c = 0; c < NTT / 2; ++c)
+                    tmem_st4(t_chain + 8 * c, acc[2 * c][0], acc[2 * c][1], acc[2 * c + 1][0], acc[2 * c + 1][1]);
+                tmem_wait_st();
             } else {
                 // root reduction (_likes.pyx:312-322, 426-442)
                 const double* sv = p.stat + (size_t)w * Fp + 2 * kk;
@@ -386,6 +480,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         }
         __syncthreads();
     }  // items
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(ts->tmem_base), "n"(TMEM_COLS));
 }
 
 }  // namespace mope
