@@ -97,6 +97,7 @@ struct mope_ctx {
     double* tables = nullptr;  // drift [G][U][F][F] then bot [NB][UB][F][F]
     int64_t bot_base = 0;
     double* gens_dev = nullptr;
+    int32_t* work_ctr = nullptr;   // item counter of tree_kernel4 (zeroed before every launch)
     // model
     int n_var = 0, ndim = 0, n_ped = 0, asc_total = 0;
     double min_phred = -1, min_freq = 0, genome = 0, penalty = 0;
@@ -392,7 +393,8 @@ int layout_arena(mope_ctx* c, const mope_tables_desc* t, const mope_model_desc* 
     size_t ntab = (size_t)t->n_gens * t->n_us * FF + (t->bot ? (size_t)t->n_nbs * t->n_bot_us * FF : 0);
     double* tab = bump.take<double>(ntab);
     double* gd = bump.take<double>(t->n_gens);
-    if (!dry) { c->tables = tab; c->gens_dev = gd; c->bot_base = (int64_t)t->n_gens * t->n_us * FF; }
+    int32_t* wc = bump.take<int32_t>(64);
+    if (!dry) { c->tables = tab; c->gens_dev = gd; c->work_ctr = wc; c->bot_base = (int64_t)t->n_gens * t->n_us * FF; }
     const int Fp = round_up_i(t->F, 16);
     for (int k = 0; k < m->n_ped; ++k) {
         const mope_pedigree_desc& pd = m->peds[k];
@@ -478,9 +480,12 @@ int launch_tree4_t(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st
         CUDA_TRY(cudaFuncSetAttribute(tree_kernel4<NTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg4<NTT>::SMEM_BYTES));
         attr_set = true;
     }
+    CUDA_TRY(cudaMemsetAsync(c->work_ctr, 0, sizeof(int32_t), st));
     {
         ScopedTimer timer(c, st, &c->ev_tree);
-        tree_kernel4<NTT><<<grid, NTHREADS, Cfg4<NTT>::SMEM_BYTES, st>>>(tp);
+        Tree4Params tq = tp;
+        tq.work_ctr = c->work_ctr;
+        tree_kernel4<NTT><<<grid, NTHREADS, Cfg4<NTT>::SMEM_BYTES, st>>>(tq);
     }
     CUDA_TRY(cudaGetLastError());
     c->launches++;

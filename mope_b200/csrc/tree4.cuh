@@ -21,6 +21,14 @@
 
 namespace mope {
 
+#ifdef MOPE_PROF   // per-warp cycle accounting for kernel tuning (printed by two CTAs at the end of the kernel)
+#define PROF_DECL long long pf_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pf_c0 = clock64(), pf_start = pf_c0;
+#define PROF_MARK(i) { const long long pf_c1 = clock64(); pf_t[i] += pf_c1 - pf_c0; pf_c0 = pf_c1; }
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#endif
+
 #ifndef MOPE_NS4
 #define MOPE_NS4 6
 #define MOPE_PF4 4
@@ -62,6 +70,7 @@ struct Tree4Params {
     double* Yout;
     int32_t debug;           // measurement only, bit flags: 1 skip the MMAs, 2 skip the copies and ring barriers
     int32_t tmem_slot;       // id of the parked-message slot that lives in tensor memory (-1: none)
+    int32_t* work_ctr;       // zeroed before the launch: next item to hand out (items differ in cost: identity branches)
 };
 
 struct Tree4Smem {
@@ -73,6 +82,7 @@ struct Tree4Smem {
     int32_t unit_prow0[MAX_OPS];                // per item: pool row of the op's first unit (later segments: + k*(Fp+1))
     double rowval[TM];         // root reduction: per-row log-likelihood terms
     uint32_t tmem_base;        // tcgen05.alloc result
+    long long cur_item;        // the item the CTA works on (handed out dynamically)
 };
 
 template <int NTT>
@@ -195,9 +205,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
     constexpr bool no_lds = false;
 
     unsigned g = 0;   // chunks consumed so far (ring position)
+    PROF_DECL
     const long long n_items = (long long)p.W * p.n_tiles;
 
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (;;) {
+        // items are handed out dynamically in the L2-friendly order: a CTA that drew cheap items (walkers with many
+        // identity branches) simply draws more of them
+        if (threadIdx.x == 0) ts->cur_item = (long long)atomicAdd(p.work_ctr, 1);
+        __syncthreads();
+        const long long item = ts->cur_item;
+        if (item >= n_items) break;
         int w, tile;
         {
             const long long per_block = (long long)p.W * p.tile_block;
@@ -291,6 +308,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         if (!no_copy && lane == 0 && warp < PF4 && warp < total_chunks) issue(warp);
         __syncwarp();
         int crel = 0;   // chunks of this item consumed so far
+        PROF_MARK(0)   // item setup
 
         for (int oi = 0; oi < p.n_ops; ++oi) {
             const Op4 op = ts->ops[oi];
@@ -317,9 +335,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 for (int c = 0; c < nchunks; ++c) {
                     {
                         const int rel = crel + PF4;
+                        PROF_MARK(1)   // compute (tail of the previous chunk) + loop control
                         if (!no_copy && lane == 0 && (rel & 7) == warp && rel < total_chunks) issue(rel);
                     }
                     __syncwarp();
+                    PROF_MARK(2)   // copy issue
                     double ac[4] = {0.0, 0.0, 0.0, 0.0};
                     if (op.leaf < 0) {
                         tmem_wait_ld();
@@ -327,7 +347,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                         if (c + 1 < nchunks) tmem_ld4_issue(t_chain + 8 * (c + 1), an);
                     }
                     const unsigned s = g % NS4;
+                    PROF_MARK(1)
                     if (!no_copy) mbar_wait(&ts->full[s], (g / NS4) & 1u);
+                    PROF_MARK(3)   // waiting for the stage
                     const int nq = (c + 1 == nchunks) ? nq_last : 4;
                     const unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
                     if (!no_mma) {
@@ -347,6 +369,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 }
             }
 
+            PROF_MARK(1)
             // ---------------- post-op (warp local) ----------------
             const bool row_ident = identity || (op.kind == 1 && gi < 0);
             // identity short-cut (transition_data_2d.py:184-187) or padding row: the message is the operand itself
@@ -396,7 +419,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
 #pragma unroll
                 for (int n = 0; n < NTT; ++n)
                     if (8 * n < Fp) *reinterpret_cast<double2*>(yo + 8 * n) = make_double2(acc[n][0], acc[n][1]);
-                continue;
+                { PROF_MARK(4) continue; }
             }
 
             __syncwarp();   // the tensor-memory instructions below are warp-wide
@@ -426,7 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
 #pragma unroll
                     for (int n = 0; n < NTT; ++n) sl[n * 32] = make_double2(acc[n][0], acc[n][1]);
                 }
-                continue;
+                { PROF_MARK(4) continue; }
             }
             if (op.mul_slot >= 0 && op.mul_slot == p.tmem_slot) {
 #pragma unroll
@@ -469,6 +492,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                     ts->rowval[warp * 8 + x] = v;
                 }
             }
+            PROF_MARK(4)   // post-op
         }  // ops
 
         __syncthreads();   // rowval complete; every warp is done with the item's tables
@@ -479,7 +503,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             if (lane == 0) p.tile_ll[(size_t)w * p.n_tiles + tile] = part;
         }
         __syncthreads();
+        PROF_MARK(5)   // item end (barriers, tile sum)
     }  // items
+#ifdef MOPE_PROF
+    if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
+        const double tot = (double)(clock64() - pf_start);
+        printf("cta %3d warp %d: total %.3e cyc; setup %.2f%% compute %.2f%% issue %.2f%% wait_full %.2f%% post %.2f%% item_end %.2f%%\n", (int)blockIdx.x, warp, tot,
+               100.0 * pf_t[0] / tot, 100.0 * pf_t[1] / tot, 100.0 * pf_t[2] / tot, 100.0 * pf_t[3] / tot, 100.0 * pf_t[4] / tot, 100.0 * pf_t[5] / tot);
+    }
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(ts->tmem_base), "n"(TMEM_COLS));
