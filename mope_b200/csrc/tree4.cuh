@@ -285,27 +285,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         __syncthreads();
         const int total_chunks = n_units * nchunks;
         const unsigned g_item0 = g;
-        // issue chunk number `rel` of the item (called by one lane)
-        auto issue = [&](int rel) {
-            const int u = rel / nchunks, ch = rel - u * nchunks;
-            // the op that owns unit u: last op with unit_first[op] <= u (ops without units have empty ranges)
-            int lo = 0, hi = p.n_ops - 1;
+        // Copies are issued round-robin: lane 0 of warp k issues chunks k, k+8, ... of the item.  It tracks the position of
+        // its next chunk (op, unit inside the op, chunk inside the unit) incrementally; only the first one is searched for.
+        int iss_rel = warp, iss_op = 0, iss_uo = 0, iss_ch = 0;
+        if (lane == 0 && iss_rel < total_chunks) {
+            const int u = iss_rel / nchunks;
+            iss_ch = iss_rel - u * nchunks;
+            int lo = 0, hi = p.n_ops - 1;   // last op with unit_first[op] <= u (ops without units have empty ranges)
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
                 if (ts->unit_first[mid] <= u) lo = mid; else hi = mid - 1;
             }
-            const Op4& o = ts->ops[lo];
-            const int prow_u = ts->unit_prow0[lo] + (u - ts->unit_first[lo]) * blk_rows;
+            iss_op = lo;
+            iss_uo = u - ts->unit_first[lo];
+        }
+        auto issue_next = [&]() {   // called by lane 0: issue chunk iss_rel, then step 8 chunks ahead
+            const Op4& o = ts->ops[iss_op];
+            const int prow_u = ts->unit_prow0[iss_op] + iss_uo * blk_rows;
             const int erow = o.leaf >= 0 ? o.leaf * p.R_pad + row0 : -1;
-            const unsigned gg = g_item0 + (unsigned)rel;
+            const unsigned gg = g_item0 + (unsigned)iss_rel;
             const unsigned s = gg % NS4;
+            PROF_MARK(2)
             mbar_wait(&ts->empty[s], ((gg / NS4) & 1u) ^ 1u);
+            PROF_MARK(6)   // waiting for the stage to be released
             unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
             mbar_expect_tx(&ts->full[s], (unsigned)(Cfg::P_BYTES + (erow >= 0 ? Cfg::E_BYTES : 0)));
-            tma_load_2d(st + Cfg::E_BYTES, &p.tmapP, ch * KC, prow_u, &ts->full[s]);
-            if (erow >= 0) tma_load_2d(st, &p.tmapE, ch * KC, erow, &ts->full[s]);
+            tma_load_2d(st + Cfg::E_BYTES, &p.tmapP, iss_ch * KC, prow_u, &ts->full[s]);
+            if (erow >= 0) tma_load_2d(st, &p.tmapE, iss_ch * KC, erow, &ts->full[s]);
+            PROF_MARK(7)   // expect_tx + TMA issue
+            iss_rel += 8;
+            iss_ch += 8;
+            while (iss_ch >= nchunks && iss_op < p.n_ops) {
+                iss_ch -= nchunks;
+                ++iss_uo;
+                while (iss_op < p.n_ops && iss_uo >= ts->unit_first[iss_op + 1] - ts->unit_first[iss_op]) { ++iss_op; iss_uo = 0; }
+            }
         };
-        if (!no_copy && lane == 0 && warp < PF4 && warp < total_chunks) issue(warp);
+        if (!no_copy && lane == 0 && warp < PF4 && warp < total_chunks) issue_next();
         __syncwarp();
         int crel = 0;   // chunks of this item consumed so far
         PROF_MARK(0)   // item setup
@@ -336,7 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                     {
                         const int rel = crel + PF4;
                         PROF_MARK(1)   // compute (tail of the previous chunk) + loop control
-                        if (!no_copy && lane == 0 && (rel & 7) == warp && rel < total_chunks) issue(rel);
+                        if (!no_copy && lane == 0 && rel == iss_rel && rel < total_chunks) issue_next();
                     }
                     __syncwarp();
                     PROF_MARK(2)   // copy issue
@@ -508,8 +524,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
 #ifdef MOPE_PROF
     if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
         const double tot = (double)(clock64() - pf_start);
-        printf("cta %3d warp %d: total %.3e cyc; setup %.2f%% compute %.2f%% issue %.2f%% wait_full %.2f%% post %.2f%% item_end %.2f%%\n", (int)blockIdx.x, warp, tot,
-               100.0 * pf_t[0] / tot, 100.0 * pf_t[1] / tot, 100.0 * pf_t[2] / tot, 100.0 * pf_t[3] / tot, 100.0 * pf_t[4] / tot, 100.0 * pf_t[5] / tot);
+        printf("cta %3d warp %d: total %.3e cyc; setup %.2f%% compute %.2f%% issue %.2f%% wait_full %.2f%% post %.2f%% item_end %.2f%% wait_empty %.2f%% tma %.2f%%\n", (int)blockIdx.x, warp, tot,
+               100.0 * pf_t[0] / tot, 100.0 * pf_t[1] / tot, 100.0 * pf_t[2] / tot, 100.0 * pf_t[3] / tot, 100.0 * pf_t[4] / tot, 100.0 * pf_t[5] / tot,
+               100.0 * pf_t[6] / tot, 100.0 * pf_t[7] / tot);
     }
 #endif
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
