@@ -182,6 +182,15 @@ int mope_b200_branch_update(mope_ctx* ctx, int kind, const double* child, double
 int mope_b200_non_asc_probs(mope_ctx* ctx, const double* qualities, const int64_t* qual_off, int n_sets,
                             const double* freqs, int F, double min_empirical_freq, void* stream, double* out);
 
+/* Host helper of the root prior (likelihoods.discretize_beta_distn, mope/likelihoods.py:27-41: st.beta.cdf at the
+ * cell edges).  out[i][j] = betainc(ab[i], ab[i], edges[j]) evaluated with `betainc_fn`, the C entry point of SciPy's
+ * own regularised incomplete beta function (scipy.special.cython_special.__pyx_capi__["__pyx_fuse_0betainc"],
+ * signature double(double a, double b, double x, int skip_dispatch)) -- the values are bit-identical to
+ * scipy.stats.beta.cdf, which the CDF differences of the reference require; rows are split over n_threads native
+ * threads (no interpreter lock involved).  Pure host code: no context, no device. */
+int mope_b200_beta_cdf_table(void* betainc_fn, const double* ab, int n_ab, const double* edges, int n_edges,
+                             double* out, int n_threads);
+
 const char* mope_b200_last_error(void);
 const char* mope_b200_version(void);
 

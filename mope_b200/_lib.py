@@ -58,7 +58,7 @@ class ModelDesc(C.Structure):
 SYMBOLS = ["mope_b200_arena_bytes", "mope_b200_create", "mope_b200_destroy", "mope_b200_workspace_bytes",
            "mope_b200_eval", "mope_b200_eval_device", "mope_b200_launch_count", "mope_b200_last_eval_stats", "mope_b200_set_profiling",
            "mope_b200_kernel_times", "mope_b200_fp64_peak", "mope_b200_transition_matrix",
-           "mope_b200_leaf_likelihoods", "mope_b200_branch_update", "mope_b200_non_asc_probs",
+           "mope_b200_leaf_likelihoods", "mope_b200_branch_update", "mope_b200_non_asc_probs", "mope_b200_beta_cdf_table",
            "mope_b200_last_error", "mope_b200_version"]
 
 ST_MESSAGES = {
@@ -101,6 +101,7 @@ def lib():
     L.mope_b200_leaf_likelihoods.argtypes = [vp, dp, dp, C.c_int, C.c_int, dp, C.c_int, C.c_double, vp, dp]
     L.mope_b200_branch_update.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, C.c_double, vp, ip]
     L.mope_b200_non_asc_probs.argtypes = [vp, dp, C.POINTER(C.c_int64), C.c_int, dp, C.c_int, C.c_double, vp, dp]
+    L.mope_b200_beta_cdf_table.argtypes = [vp, dp, C.c_int, dp, C.c_int, dp, C.c_int]
     L.mope_b200_last_error.restype = C.c_char_p
     L.mope_b200_version.restype = C.c_char_p
     for name in SYMBOLS:

@@ -7,6 +7,7 @@
 //   * the branch schedule (postorder walk of likelihoods.py:352-397) compiled once into TreeOp records;
 //   * chunking walkers so that the per-chunk matrix pool fits the caller's workspace.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -14,6 +15,7 @@
 #include <cstdlib>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mope_b200.h"
@@ -108,6 +110,9 @@ struct mope_ctx {
     // host staging (pinned, grow-only)
     char* pinned = nullptr;
     size_t pinned_cap = 0, pinned_off = 0;
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};   // recorded when the staging ring leaves half 0 / half 1
+    bool pin_ev_valid[2] = {false, false};
+    int pin_half = 0;
     // small library-owned device scratch for the operator-level entry points
     char* opbuf = nullptr;
     size_t opbuf_cap = 0;
@@ -137,14 +142,27 @@ int ensure_pinned(mope_ctx* c, size_t bytes) {
     return 0;
 }
 
-// Pinned staging as a ring: consecutive asynchronous calls take consecutive pieces; the stream is only synchronised
-// when the ring wraps (everything staged before is consumed by then) or has to grow.
+// Pinned staging as a ring of two halves: consecutive asynchronous calls take consecutive pieces.  When the ring moves on
+// to the other half it records an event, and before it re-enters a half it waits for the event recorded when that half
+// was left -- work enqueued a whole half-ring of calls ago, i.e. normally long finished.  (A plain stream synchronise on
+// wrap-around would stall the host behind the pruning kernel in flight.)
 int stage_alloc(mope_ctx* c, size_t bytes, cudaStream_t st, char** out) {
     bytes = align_up(std::max<size_t>(bytes, 64), 256);
-    if (c->pinned_off + bytes > c->pinned_cap) {
+    if (bytes * 2 > c->pinned_cap) {
         CUDA_TRY(cudaStreamSynchronize(st));
-        if (int rc = ensure_pinned(c, std::max(bytes * 4, (size_t)8 << 20))) return rc;
+        if (int rc = ensure_pinned(c, std::max(bytes * 8, (size_t)16 << 20))) return rc;
         c->pinned_off = 0;
+        c->pin_half = 0;
+        c->pin_ev_valid[0] = c->pin_ev_valid[1] = false;
+    }
+    const size_t half = (c->pinned_cap / 2) & ~(size_t)255;
+    if (c->pinned_off + bytes > (size_t)(c->pin_half + 1) * half) {
+        if (!c->pin_ev[c->pin_half]) CUDA_TRY(cudaEventCreateWithFlags(&c->pin_ev[c->pin_half], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(c->pin_ev[c->pin_half], st));
+        c->pin_ev_valid[c->pin_half] = true;
+        c->pin_half ^= 1;
+        c->pinned_off = (size_t)c->pin_half * half;
+        if (c->pin_ev_valid[c->pin_half]) CUDA_TRY(cudaEventSynchronize(c->pin_ev[c->pin_half]));
     }
     *out = c->pinned + c->pinned_off;
     c->pinned_off += bytes;
@@ -720,6 +738,13 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
     const int ndim = c->ndim, Fp = c->Fp, F = c->F;
     const int n_mat = (int)c->fixed_keys.size(), n_rate = (int)c->rate_keys.size();
 
+    // host-side phase timing (MOPE_HOST_PROF=<ms>: print the phases of calls whose host part exceeds <ms>)
+    static const double host_prof_ms = getenv("MOPE_HOST_PROF") ? atof(getenv("MOPE_HOST_PROF")) : -1.0;
+    std::vector<std::pair<const char*, double>> hp_marks;
+    const auto hp_t0 = std::chrono::steady_clock::now();
+    auto hp_mark = [&](const char* name) {
+        if (host_prof_ms >= 0.0) hp_marks.emplace_back(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hp_t0).count());
+    };
     // 1. plan sizes / statuses
     std::vector<WalkerPlan> plans(W);
     std::vector<int> good;
@@ -730,6 +755,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
         if (plans[w].status == 0) good.push_back(w);
     }
     const int Wg = (int)good.size();
+    hp_mark("plan_sizes");
 
     // 2. carve the walker-independent part of the workspace
     Bump ws;
@@ -752,6 +778,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
 
     c->last_gemm_ops = 0;
     c->last_identity_ops = 0;
+    hp_mark("fill_nan");
     // 3. chunk the valid walkers
     size_t gi0 = 0;
     // staging size upper bound for one chunk is computed per chunk
@@ -785,6 +812,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
             b0 += plans[w].n_blocks;
         }
         if (po.jobs.size() != n_blocks) return fail(MOPE_E_INVALID, "internal: plan size mismatch (%zu vs %zu)", po.jobs.size(), n_blocks);
+        hp_mark("plan_jobs");
 
         // carve the chunk part
         Bump cw = ws;
@@ -808,6 +836,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
                                    (stat_on_device ? 0 : align_up(sz_stat, 64));
         char* hp = nullptr;
         if (int rc = stage_alloc(c, stage_bytes, st, &hp)) return rc;
+        hp_mark("stage_alloc");
         auto push = [&](void* dptr, const void* src, size_t bytes) -> int {
             if (bytes == 0) return 0;
             std::memcpy(hp, src, bytes);
@@ -854,6 +883,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
                     else c->last_gemm_ops++;
                 }
             }
+            hp_mark("copies+interp");
             const int tile_block_default = std::max(1, std::min(P.n_tiles, c->num_sms / 4));
             const long long items = (long long)Wc * P.n_tiles;
             const int grid = (int)std::min<long long>(items, c->num_sms);
@@ -914,8 +944,14 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
             finalize_kernel<<<Wc, 256, 0, st>>>(fp);
             CUDA_TRY(cudaGetLastError());
             c->launches++;
+            hp_mark("tree+finalize");
         }
         gi0 = gi1;
+    }
+    if (host_prof_ms >= 0.0 && !hp_marks.empty() && hp_marks.back().second > host_prof_ms) {
+        fprintf(stderr, "[mope_b200 host] eval W=%d:", W);
+        for (auto& m : hp_marks) fprintf(stderr, " %s@%.2f", m.first, m.second);
+        fprintf(stderr, "\n");
     }
 
     if (!out_on_device) {
@@ -1153,6 +1189,7 @@ int mope_b200_destroy(mope_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (int i = 0; i < 2; ++i) if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
     if (c->opbuf) cudaFree(c->opbuf);
     for (auto& pr : c->ev_tree) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pr : c->ev_interp) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -1483,6 +1520,27 @@ int mope_b200_non_asc_probs(mope_ctx* c, const double* qualities, const int64_t*
     c->launches++;
     CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)n_sets * F * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mope_b200_beta_cdf_table(void* betainc_fn, const double* ab, int n_ab, const double* edges, int n_edges, double* out, int n_threads) {
+    if (!betainc_fn || !ab || !edges || !out || n_ab < 0 || n_edges < 0) return fail(MOPE_E_INVALID, "beta_cdf_table: bad argument");
+    typedef double (*fn_t)(double, double, double, int);
+    const fn_t fn = reinterpret_cast<fn_t>(betainc_fn);
+    auto rows = [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            const double a = ab[i];
+            double* o = out + (size_t)i * n_edges;
+            for (int j = 0; j < n_edges; ++j) o[j] = fn(a, a, edges[j], 1);
+        }
+    };
+    const int nt = std::max(1, std::min(n_threads, n_ab / 4));
+    if (nt <= 1) { rows(0, n_ab); return 0; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (int t = 1; t < nt; ++t) th.emplace_back(rows, (int)((long long)n_ab * t / nt), (int)((long long)n_ab * (t + 1) / nt));
+    rows(0, (int)((long long)n_ab / nt));
+    for (auto& x : th) x.join();
     return 0;
 }
 

@@ -93,6 +93,7 @@ class Engine:
                                                  self.arena.numel(), stream, C.byref(ctx)), "mope_b200_create")
         self.ctx = ctx
         self._ws = None
+        self._ws_ok = set()
         self._ws_limit = workspace_bytes
         self._keep = []
 
@@ -114,20 +115,26 @@ class Engine:
         return int(self.lib.mope_b200_launch_count(self.ctx))
 
     def _workspace(self, W: int):
+        """Device workspace for W walkers (grow-only).  The size query and cudaMemGetInfo run only the first time a
+        batch size is seen: cudaMemGetInfo stalls for tens of milliseconds while kernels are in flight."""
         torch = self.torch
+        if self._ws is not None and W in self._ws_ok:
+            return self._ws
         mn, full = C.c_size_t(0), C.c_size_t(0)
         _lib.check(self.lib.mope_b200_workspace_bytes(self.ctx, int(W), C.byref(mn), C.byref(full)), "mope_b200_workspace_bytes")
         want = int(full.value)
-        if self._ws_limit is not None:
-            want = max(int(mn.value), min(want, int(self._ws_limit)))
-        else:
-            free, _total = torch.cuda.mem_get_info(self.device)
-            reuse = self._ws.numel() if self._ws is not None else 0
-            want = max(int(mn.value), min(want, int(0.85 * (free + reuse))))
         if self._ws is None or self._ws.numel() < want:
-            self._ws = None
-            with torch.cuda.device(self.device):
-                self._ws = torch.empty(want, dtype=torch.uint8, device="cuda:%d" % self.device)
+            if self._ws_limit is not None:
+                want = max(int(mn.value), min(want, int(self._ws_limit)))
+            else:
+                free, _total = torch.cuda.mem_get_info(self.device)
+                reuse = self._ws.numel() if self._ws is not None else 0
+                want = max(int(mn.value), min(want, int(0.85 * (free + reuse))))
+            if self._ws is None or self._ws.numel() < want:
+                self._ws = None
+                with torch.cuda.device(self.device):
+                    self._ws = torch.empty(want, dtype=torch.uint8, device="cuda:%d" % self.device)
+        self._ws_ok.add(W)
         return self._ws
 
     # ------------------------------------------------------------------------------------------
