@@ -71,7 +71,10 @@ def test_cfg3_cfg4_shape_rate_and_bottleneck_branches_vs_oracle():
 
 def test_leaf_minimum_and_unary_chain_trees_vs_oracle():
     from mope_b200 import synth
-    for tree in ("(t0:a,t1:b)root;", "((((t0:a)n1:b)n2:c*child_age)n3:d^,t1:a)root;", "(t0:a,t1:a,t2:b,t3:c*mother_age)root;"):
+    for tree in ("(t0:a,t1:b)root;", "((((t0:a)n1:b)n2:c*child_age)n3:d^,t1:a)root;", "(t0:a,t1:a,t2:b,t3:c*mother_age)root;",
+                 # multifurcations below the root and several live parked messages: exercises the tensor-memory slot, the
+                 # L2 slots and the fold-into-a-parked-message path of tree_kernel4 together
+                 "((t0:a,t1:b,t2:c)n1:d,((t3:a,t4:b)n2:c,(t5:d,t6:a*mother_age,t7:b)n3:e)n4:a)root;"):
         nl = tree.count("t")
         ds = synth.make_dataset(70, nl, tree=tree, seed=7)
         # make_dataset names leaves t0..t{n-1}
