@@ -491,11 +491,11 @@ int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d
     return 0;
 }
 
-template <int NTT>
+template <int NTT, int NFULL, bool SCALAR>
 int launch_tree4_t(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(tree_kernel4<NTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg4<NTT>::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(tree_kernel4<NTT, NFULL, SCALAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg4<NTT>::SMEM_BYTES));
         attr_set = true;
     }
     CUDA_TRY(cudaMemsetAsync(c->work_ctr, 0, sizeof(int32_t), st));
@@ -503,18 +503,31 @@ int launch_tree4_t(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st
         ScopedTimer timer(c, st, &c->ev_tree);
         Tree4Params tq = tp;
         tq.work_ctr = c->work_ctr;
-        tree_kernel4<NTT><<<grid, NTHREADS, Cfg4<NTT>::SMEM_BYTES, st>>>(tq);
+        tree_kernel4<NTT, NFULL, SCALAR><<<grid, NTHREADS, Cfg4<NTT>::SMEM_BYTES, st>>>(tq);
     }
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return 0;
 }
 
+// n-tiles that go through the tensor pipe: all-padding tiles are skipped, and a last tile with a single real column
+// (F = 8k + 1: the grid sizes 201 and 65) is done by scalar FMAs (tree4.cuh).  Specialisations exist for the grid
+// sizes in use; any other F runs the generic instance of its size class.
 int launch_tree4(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st) {
+    const int full = c->F / 8, rem = c->F % 8;
+    const int nf = rem <= 1 ? full : full + 1;
+    const bool sc = rem == 1;
+    const bool generic = getenv("MOPE_TREE4_GENERIC") != nullptr;
     switch (c->ntt) {
-        case 10: return launch_tree4_t<10>(c, tp, grid, st);
-        case 16: return launch_tree4_t<16>(c, tp, grid, st);
-        default: return launch_tree4_t<26>(c, tp, grid, st);
+        case 10:
+            if (!generic && nf == 8 && sc) return launch_tree4_t<10, 8, true>(c, tp, grid, st);
+            return launch_tree4_t<10, 10, false>(c, tp, grid, st);
+        case 16:
+            if (!generic && nf == 15 && !sc) return launch_tree4_t<16, 15, false>(c, tp, grid, st);
+            return launch_tree4_t<16, 16, false>(c, tp, grid, st);
+        default:
+            if (!generic && nf == 25 && sc) return launch_tree4_t<26, 25, true>(c, tp, grid, st);
+            return launch_tree4_t<26, 26, false>(c, tp, grid, st);
     }
 }
 

@@ -138,9 +138,12 @@ constexpr int TMEM_WARP_COLS = 256;   // per warp: chain buffer at column 0, one
 
 // One 16-wide K chunk of a branch GEMM for the warp's 8 rows: 4 k steps x NTT n-tiles.  A comes from the emission chunk
 // in the stage (LEAF) or from the chained fragment values `ac`; RATE scales it by the row's segment weight.
-template <int NTT, bool LEAF, bool RATE, bool NO_LDS>
-__device__ __forceinline__ void chunk_mma(double (&acc)[NTT][2], const unsigned char* st, int a_base, int b_base, int z,
-                                          const double (&ac)[4], double wgt, int nq) {
+// Only the first NFULL n-tiles go through the tensor pipe.  With SCALAR the single real column of tile NFULL (F = 8 NFULL
+// + 1, e.g. F = 201) is accumulated by one DFMA per k step into `sacc` (partial sum over the thread's own k indices; the
+// four kk lanes of a row are added up after the GEMM) instead of spending a whole DMMA on seven padding columns.
+template <int NTT, int NFULL, bool SCALAR, bool LEAF, bool RATE, bool NO_LDS>
+__device__ __forceinline__ void chunk_mma(double (&acc)[NTT][2], double& sacc, const unsigned char* st, int a_base, int b_base, int z,
+                                          int bs_base, int z0, const double (&ac)[4], double wgt, int nq) {
     double a[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -152,15 +155,18 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[NTT][2], const unsigned 
     for (int q = 0; q < 4; ++q) {
         if (q >= nq) break;   // all-padding k step (zero columns): nothing to add
         const unsigned char* pb = st + b_base + ((q ^ z) << 4);
+        double ps = 0.0;
+        if (SCALAR) ps = *reinterpret_cast<const double*>(st + bs_base + ((q ^ z0) << 4));   // P[8 NFULL][k], same for all 8 rows
 #pragma unroll
-        for (int n = 0; n < NTT; ++n) {
+        for (int n = 0; n < NFULL; ++n) {
             const double b = NO_LDS ? wgt : *reinterpret_cast<const double*>(pb + n * 1024);
             dmma(acc[n][0], acc[n][1], a[q], b);
         }
+        if (SCALAR) sacc = fma(a[q], ps, sacc);
     }
 }
 
-template <int NTT>
+template <int NTT, int NFULL, bool SCALAR>
 __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constant__ Tree4Params p) {
     using Cfg = Cfg4<NTT>;
     extern __shared__ unsigned char smem_raw[];
@@ -179,6 +185,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
     const int hb = (kk & 1) << 3;
     const int a_base = (warp * 8 + x) * 128 + hb;
     const int b_base = Cfg::E_BYTES + x * 128 + hb;
+    const int z0 = (kk >> 1) << 2;                               // row 8 NFULL of the chunk (the scalar column's matrix row)
+    const int bs_base = Cfg::E_BYTES + hb + NFULL * 1024;
+    static_assert(NFULL + (SCALAR ? 1 : 0) <= NTT, "n-tiles");
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS4; ++s) { mbar_init(&ts->full[s], 1); mbar_init(&ts->empty[s], NTHREADS / 32); }
@@ -337,6 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             double acc[NTT][2];
 #pragma unroll
             for (int n = 0; n < NTT; ++n) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+            double sacc = 0.0;
 
             // ---------------- GEMM(s) ----------------
             const int nseg = identity ? 0 : (op.kind == 0 ? 1 : max(0, ts->seg_hi[oi] - ts->seg_lo[oi] + 1));
@@ -371,11 +381,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                     if (!no_mma) {
                         // the four operand flavours get their own straight-line code: nothing but LDS + DMMA between k steps
                         if (op.leaf >= 0) {
-                            if (op.kind == 1) chunk_mma<NTT, true, true, no_lds>(acc, st, a_base, b_base, z, ac, wgt, nq);
-                            else chunk_mma<NTT, true, false, no_lds>(acc, st, a_base, b_base, z, ac, wgt, nq);
+                            if (op.kind == 1) chunk_mma<NTT, NFULL, SCALAR, true, true, no_lds>(acc, sacc, st, a_base, b_base, z, bs_base, z0, ac, wgt, nq);
+                            else chunk_mma<NTT, NFULL, SCALAR, true, false, no_lds>(acc, sacc, st, a_base, b_base, z, bs_base, z0, ac, wgt, nq);
                         } else {
-                            if (op.kind == 1) chunk_mma<NTT, false, true, no_lds>(acc, st, a_base, b_base, z, ac, wgt, nq);
-                            else chunk_mma<NTT, false, false, no_lds>(acc, st, a_base, b_base, z, ac, wgt, nq);
+                            if (op.kind == 1) chunk_mma<NTT, NFULL, SCALAR, false, true, no_lds>(acc, sacc, st, a_base, b_base, z, bs_base, z0, ac, wgt, nq);
+                            else chunk_mma<NTT, NFULL, SCALAR, false, false, no_lds>(acc, sacc, st, a_base, b_base, z, bs_base, z0, ac, wgt, nq);
                         }
                     }
                     __syncwarp();
@@ -385,6 +395,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 }
             }
 
+            if (SCALAR) {
+                // column 8 NFULL: add the partial sums of the row's four kk lanes; lane kk = 0 owns the column
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+                acc[NFULL][0] = (kk == 0) ? sacc : 0.0;
+            }
             PROF_MARK(1)
             // ---------------- post-op (warp local) ----------------
             const bool row_ident = identity || (op.kind == 1 && gi < 0);

@@ -83,9 +83,10 @@ def test_leaf_minimum_and_unary_chain_trees_vs_oracle():
 
 
 def test_f201_and_f1001_multipass_vs_oracle():
-    """F = 201 (bench grid size) and F = 1001 (cfg5: five N-passes per branch) on tables from the GPU generator."""
+    """F = 201 (bench grid size), F = 115 (the published default binning) and F = 1001 (cfg5: five N-passes per branch)
+    on tables from the GPU generator; F = 201 also with the generic kernel instance (no scalar last column)."""
     from mope_b200 import generate, synth
-    for brk, F, nloci, nleaves in ((0.005, 201, 60, 4), (1e-9, 1001, 12, 2)):
+    for brk, F, nloci, nleaves in ((0.005, 201, 60, 4), (0.01, 115, 60, 4), (1e-9, 1001, 12, 2)):
         tb = generate.generate_tables(N=1000, breaks=(0.5, brk), gens=[1, 10, 100, 1000], us=[1e-8, 1e-5, 1e-3], device="cuda")
         assert tb.F == F
         ds = synth.make_dataset(nloci, nleaves, tree=synth.balanced_tree(nleaves), seed=8)
