@@ -75,7 +75,7 @@ struct Pedigree {
     // warp-owned-rows kernel (tree4.cuh): postorder schedule with chained messages
     Op4* ops4 = nullptr;
     std::vector<Op4> ops4_h;
-    int tmem_slot4 = -1;
+    std::vector<int> slot_parks4;   // how often each slot is written per item
     int n_slots4 = 0;
     int asc_offset = 0;
     CUtensorMap tmapE;
@@ -393,11 +393,9 @@ int compile_schedule4(const mope_pedigree_desc& pd, const std::vector<int>& fixe
     }
     if (out.ops4_h.empty() || !out.ops4_h.back().last) return fail(MOPE_E_INVALID, "schedule does not end at the root");
     out.n_slots4 = std::max(n_slots, 1);
-    // the slot that is written most often lives in tensor memory (tree4.cuh), the others in the L2 scratch
-    std::vector<int> parks(out.n_slots4, 0);
-    for (const Op4& o : out.ops4_h) if (o.store_slot >= 0) parks[o.store_slot]++;
-    out.tmem_slot4 = -1;
-    for (int i = 0, best = 0; i < out.n_slots4; ++i) if (parks[i] > best) { best = parks[i]; out.tmem_slot4 = i; }
+    // parks per slot: the busiest slots get the tensor-memory homes (placement happens at launch, tree4.cuh)
+    out.slot_parks4.assign(out.n_slots4, 0);
+    for (const Op4& o : out.ops4_h) if (o.store_slot >= 0) out.slot_parks4[o.store_slot]++;
     return 0;
 }
 
@@ -489,6 +487,17 @@ int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return 0;
+}
+
+// homes of the parked-message slots: the busiest ones get the warp's whole tensor-memory slots, the rest the L2 scratch
+void place_slots4(const mope_ctx* c, const std::vector<int>& parks, int32_t (&home)[MAX_SLOTS4]) {
+    for (int i = 0; i < MAX_SLOTS4; ++i) home[i] = SLOT_HOME_L2;
+    const int tm_slots = 256 / (c->ntt * 4) - 1;
+    std::vector<int> order;
+    for (int i = 0; i < (int)parks.size() && i < MAX_SLOTS4; ++i) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return parks[a] > parks[b]; });
+    for (int r = 0; r < (int)order.size() && r < tm_slots; ++r)
+        if (parks[order[r]] > 0) home[order[r]] = r;
 }
 
 template <int NTT, int NFULL, bool SCALAR>
@@ -905,7 +914,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
                 t4.tmapE = P.tmapE; t4.tmapP = tmapP;
                 t4.E = P.E; t4.E_leaf_stride = (int64_t)P.R_pad * Fp;
                 t4.scratch = scratch;
-                t4.ops = P.ops4; t4.n_ops = (int)P.ops4_h.size(); t4.n_slots = c->max_slots4; t4.tmem_slot = P.tmem_slot4;
+                t4.ops = P.ops4; t4.n_ops = (int)P.ops4_h.size(); t4.n_slots = c->max_slots4; place_slots4(c, P.slot_parks4, t4.slot_home);
                 t4.R = P.R; t4.L = P.L; t4.R_pad = P.R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = P.n_tiles; t4.W = Wc;
                 t4.tile_block = tile_block_default;
                 if (const char* e = getenv("MOPE_TILE_BLOCK")) t4.tile_block = std::max(1, std::min(P.n_tiles, atoi(e)));
@@ -1473,7 +1482,7 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
         if (int rc = make_tmap(&t4.tmapE, P.E, (uint64_t)R_pad, Fp, TM)) return rc;
         if (int rc = make_tmap(&t4.tmapP, P.pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + 1), Fp, tree_prows(c))) return rc;
         t4.E = P.E; t4.E_leaf_stride = (int64_t)R_pad * Fp; t4.scratch = P.Y /*unused*/; t4.ops = reinterpret_cast<const Op4*>(P.op);
-        t4.n_ops = 1; t4.n_slots = 1; t4.tmem_slot = -1;
+        t4.n_ops = 1; t4.n_slots = 1; place_slots4(c, std::vector<int>(), t4.slot_home);
         t4.R = n_rows; t4.L = n_rows; t4.R_pad = R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = R_pad / TM; t4.W = 1;
         t4.tile_block = t4.n_tiles;
         t4.pool = P.pool; t4.mat_off = P.mo; t4.n_mat = 1; t4.n_rate = 1; t4.rate = P.rate; t4.mult = P.mult; t4.gens = c->gens_dev;

@@ -29,12 +29,9 @@ namespace mope {
 #define PROF_MARK(i)
 #endif
 
-#ifndef MOPE_NS4
-#define MOPE_NS4 6
-#define MOPE_PF4 4
-#endif
-constexpr int NS4 = MOPE_NS4;   // ring stages
-constexpr int PF4 = MOPE_PF4;   // prefetch distance (chunks); NS4 - PF4 >= 2 keeps the issuing lane from waiting on the slowest warp
+constexpr int NS4_MAX = 6;   // most ring stages of any configuration (Cfg4<NTT>::NS)
+constexpr int MAX_SLOTS4 = 16;  // parked-message slots with a placement entry (further slots live in the L2 scratch)
+constexpr int SLOT_HOME_L2 = -1;
 
 struct Op4 {
     int32_t leaf;         // >= 0: leaf column, A operand = emission rows (TMA ring); -1: A operand chained from the previous op
@@ -69,12 +66,13 @@ struct Tree4Params {
     double* asc_dot;
     double* Yout;
     int32_t debug;           // measurement only, bit flags: 1 skip the MMAs, 2 skip the copies and ring barriers
-    int32_t tmem_slot;       // id of the parked-message slot that lives in tensor memory (-1: none)
+    int32_t slot_home[MAX_SLOTS4];   // where a parked slot lives: k >= 0 the k-th tensor-memory slot of the warp,
+                                     // SLOT_HOME_L2 the L2 scratch
     int32_t* work_ctr;       // zeroed before the launch: next item to hand out (items differ in cost: identity branches)
 };
 
 struct Tree4Smem {
-    unsigned long long full[NS4], empty[NS4];
+    unsigned long long full[NS4_MAX], empty[NS4_MAX];
     Op4 ops[MAX_OPS];
     int32_t prow[MAX_OPS];     // per item: pool row of a shared-matrix op (negative = identity)
     int32_t seg_lo[MAX_OPS], seg_hi[MAX_OPS];   // per item: generation-grid range of a rate op over the tile's rows
@@ -91,7 +89,16 @@ struct Cfg4 {
     static constexpr int E_BYTES = TM * KC * 8;          // 8 KB
     static constexpr int P_BYTES = PROWS * KC * 8;
     static constexpr int STAGE_BYTES = E_BYTES + P_BYTES;  // multiples of 1024
-    static constexpr size_t SMEM_BYTES = (size_t)NS4 * STAGE_BYTES + sizeof(Tree4Smem) + 1024;
+    // ring depth: a prefetch distance of 2 chunks with 2 stages of slack is as fast as deeper rings (measured), and the
+    // shared memory it does not take stays L1 (the wide configuration gains 0.6 % from the larger L1)
+    static constexpr int NS = (NTT > 16) ? 4 : 6;
+    static constexpr int PF = NS - 2;   // NS - PF >= 2 keeps the issuing lane from waiting on the slowest warp
+    // tensor-memory budget of a warp (256 columns): chain buffer + TM_SLOTS whole parked slots (F = 201: 1, F = 115: 3,
+    // F = 65: 5).  Splitting one more slot between the 48 spare columns of the wide configuration and shared memory or
+    // the L2 scratch was measured slower than leaving it in the scratch.
+    static constexpr int MSG_COLS = NTT * 4;
+    static constexpr int TM_SLOTS = 256 / MSG_COLS - 1;
+    static constexpr size_t SMEM_BYTES = (size_t)NS * STAGE_BYTES + sizeof(Tree4Smem) + 1024;
 };
 
 // per-row time weights of an age-scaled branch (transition_data_2d.py:183-224)
@@ -134,7 +141,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ double u2d(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
 constexpr int TMEM_COLS = 512;        // whole tensor memory of the SM (one CTA per SM)
-constexpr int TMEM_WARP_COLS = 256;   // per warp: chain buffer at column 0, one parked slot after it
+constexpr int TMEM_WARP_COLS = 256;   // per warp: chain buffer at column 0, parked slots after it (Cfg4)
 
 // One 16-wide K chunk of a branch GEMM for the warp's 8 rows: 4 k steps x NTT n-tiles.  A comes from the emission chunk
 // in the stage (LEAF) or from the chained fragment values `ac`; RATE scales it by the row's segment weight.
@@ -171,6 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
     using Cfg = Cfg4<NTT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* ring = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int NS4 = Cfg::NS, PF4 = Cfg::PF;
     Tree4Smem* ts = reinterpret_cast<Tree4Smem*>(ring + (size_t)NS4 * Cfg::STAGE_BYTES);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -202,10 +210,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     // Chained operand (the message of a node's last child, operand of the node's own branch = the next op) and the parked
-    // slot p.tmem_slot: warp-private tensor-memory columns
+    // slots with a tensor-memory home: warp-private tensor-memory columns
     const uint32_t t_chain = ts->tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * TMEM_WARP_COLS);
-    const uint32_t t_slot = t_chain + NTT * 4;
-    static_assert(2 * NTT * 4 <= TMEM_WARP_COLS && NTT % 2 == 0, "chain buffer + one slot must fit the warp's TMEM columns");
+    static_assert(Cfg::TM_SLOTS >= 1 && NTT % 2 == 0, "chain buffer + one slot must fit the warp's TMEM columns");
+    // acc *= slot, or slot = acc, chunk by chunk (a chunk = two n-tiles = 4 doubles per thread), wherever the slot lives
+    auto slot_mul = [&](double (&acc)[NTT][2], int slot) {
+        const int home = slot < MAX_SLOTS4 ? p.slot_home[slot] : SLOT_HOME_L2;
+        if (home != SLOT_HOME_L2) {
+            const uint32_t tb = t_chain + (uint32_t)((home + 1) * Cfg::MSG_COLS);
+#pragma unroll
+            for (int c = 0; c < NTT / 2; ++c) {
+                uint32_t r[8];
+                tmem_ld4_issue(tb + 8 * c, r);
+                tmem_wait_ld();
+                acc[2 * c][0] *= u2d(r[0], r[1]); acc[2 * c][1] *= u2d(r[2], r[3]);
+                acc[2 * c + 1][0] *= u2d(r[4], r[5]); acc[2 * c + 1][1] *= u2d(r[6], r[7]);
+            }
+        } else {
+            const double2* sl = reinterpret_cast<const double2*>(my_scratch + (size_t)slot * NTT * 64) + lane;
+#pragma unroll
+            for (int n = 0; n < NTT; ++n) { const double2 v = sl[n * 32]; acc[n][0] *= v.x; acc[n][1] *= v.y; }
+        }
+    };
+    auto slot_store = [&](const double (&acc)[NTT][2], int slot) {
+        const int home = slot < MAX_SLOTS4 ? p.slot_home[slot] : SLOT_HOME_L2;
+        if (home != SLOT_HOME_L2) {
+            const uint32_t tb = t_chain + (uint32_t)((home + 1) * Cfg::MSG_COLS);
+#pragma unroll
+            for (int c = 0; c < NTT / 2; ++c)
+                tmem_st4(tb + 8 * c, acc[2 * c][0], acc[2 * c][1], acc[2 * c + 1][0], acc[2 * c + 1][1]);
+            tmem_wait_st();
+        } else {
+            double2* sl = reinterpret_cast<double2*>(my_scratch + (size_t)slot * NTT * 64) + lane;
+#pragma unroll
+            for (int n = 0; n < NTT; ++n) sl[n * 32] = make_double2(acc[n][0], acc[n][1]);
+        }
+    };
+    // a consumed slot of the L2 scratch is dead: drop its lines from L2 instead of letting them be written back to HBM
+    auto slot_discard = [&](int slot) {
+        const int home = slot < MAX_SLOTS4 ? p.slot_home[slot] : SLOT_HOME_L2;
+        if (home != SLOT_HOME_L2) return;
+        const double* slot_base = my_scratch + (size_t)slot * NTT * 64;
+        __syncwarp();
+        for (int line = lane; line < (NTT * 64 * 8) / 128; line += 32)
+            asm volatile("discard.global.L2 [%0], 128;\n" ::"l"(slot_base + line * 16) : "memory");
+    };
 
     // k steps of the last chunk that hold at least one real column (natural k = 16c + 8(q>>1) + (q&1) + 2kk)
     int nq_last = 0;
@@ -457,50 +506,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             __syncwarp();   // the tensor-memory instructions below are warp-wide
             if (op.store_slot >= 0) {
                 // not the last child: park the message (or fold it into the siblings parked so far)
-                if (op.store_slot == p.tmem_slot) {
-                    if (!op.store_first) {
-#pragma unroll
-                        for (int c = 0; c < NTT / 2; ++c) {
-                            uint32_t r[8];
-                            tmem_ld4_issue(t_slot + 8 * c, r);
-                            tmem_wait_ld();
-                            acc[2 * c][0] *= u2d(r[0], r[1]); acc[2 * c][1] *= u2d(r[2], r[3]);
-                            acc[2 * c + 1][0] *= u2d(r[4], r[5]); acc[2 * c + 1][1] *= u2d(r[6], r[7]);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < NTT / 2; ++c)
-                        tmem_st4(t_slot + 8 * c, acc[2 * c][0], acc[2 * c][1], acc[2 * c + 1][0], acc[2 * c + 1][1]);
-                    tmem_wait_st();
-                } else {
-                    double2* sl = reinterpret_cast<double2*>(my_scratch + (size_t)op.store_slot * NTT * 64) + lane;
-                    if (!op.store_first) {
-#pragma unroll
-                        for (int n = 0; n < NTT; ++n) { const double2 v = sl[n * 32]; acc[n][0] *= v.x; acc[n][1] *= v.y; }
-                    }
-#pragma unroll
-                    for (int n = 0; n < NTT; ++n) sl[n * 32] = make_double2(acc[n][0], acc[n][1]);
-                }
+                if (!op.store_first) slot_mul(acc, op.store_slot);
+                slot_store(acc, op.store_slot);
                 { PROF_MARK(4) continue; }
             }
-            if (op.mul_slot >= 0 && op.mul_slot == p.tmem_slot) {
-#pragma unroll
-                for (int c = 0; c < NTT / 2; ++c) {
-                    uint32_t r[8];
-                    tmem_ld4_issue(t_slot + 8 * c, r);
-                    tmem_wait_ld();
-                    acc[2 * c][0] *= u2d(r[0], r[1]); acc[2 * c][1] *= u2d(r[2], r[3]);
-                    acc[2 * c + 1][0] *= u2d(r[4], r[5]); acc[2 * c + 1][1] *= u2d(r[6], r[7]);
-                }
-            } else if (op.mul_slot >= 0) {
-                const double* slot_base = my_scratch + (size_t)op.mul_slot * NTT * 64;
-                const double2* sl = reinterpret_cast<const double2*>(slot_base) + lane;
-#pragma unroll
-                for (int n = 0; n < NTT; ++n) { const double2 v = sl[n * 32]; acc[n][0] *= v.x; acc[n][1] *= v.y; }
-                // the parked product is dead now: drop its lines from L2 instead of letting them be written back to HBM
-                __syncwarp();
-                for (int line = lane; line < (NTT * 64 * 8) / 128; line += 32)
-                    asm volatile("discard.global.L2 [%0], 128;\n" ::"l"(slot_base + line * 16) : "memory");
+            if (op.mul_slot >= 0) {
+                slot_mul(acc, op.mul_slot);
+                slot_discard(op.mul_slot);
             }
             if (!op.last) {
                 // chain: this product is the operand of the parent's branch, which is the next op
