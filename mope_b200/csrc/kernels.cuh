@@ -22,6 +22,12 @@ namespace mope {
 constexpr int TM = 64;        // rows (loci) per tile
 constexpr int KC = 16;        // K chunk in doubles (128 B per row)
 constexpr int NTHREADS = 256; // 8 warps: 4 along M (16 rows each) x 2 along N
+// A matrix block of the per-launch pool: Fp x Fp matrix, then BLK_EXTRA vectors of Fp doubles (natural column order):
+//   row Fp     row sums of the un-normalised blend (row renormalisation of age-scaled branches)
+//   row Fp+1   "low"  sums  sum_{k : freq_k < min_freq}   P[i][k]  = the message P . e0 of an ascertainment pseudo-row
+//   row Fp+2   "high" sums  sum_{k : freq_k > 1-min_freq} P[i][k]  = the message P . eN            (ascertainment.py:178-184)
+constexpr int BLK_EXTRA = 3;
+__host__ __device__ __forceinline__ size_t blk_doubles(int Fp) { return (size_t)Fp * Fp + (size_t)BLK_EXTRA * Fp; }
 
 // One branch of the tree: Y = P . (product of the child messages of the node below the branch).
 // Storage position of natural column `col` (the k index of the GEMMs) in the k-permuted layout used together with
@@ -169,9 +175,10 @@ __global__ void emission_kernel(EmissionParams p) {
 // ------------------------------------------------------------------------------------------------
 // interpolation of transition matrices (transition_data_2d.py:195-238, _interp.pyx:30-35,
 // _util.pyx:129-148).  One warp per matrix row; sequential row sum as in the reference.
-// Output block: Fp x Fp matrix (zero padded) followed by Fp row sums (of the un-normalised blend).
+// Output block: Fp x Fp matrix (zero padded) followed by the BLK_EXTRA vectors described at the top of this file.
 // ------------------------------------------------------------------------------------------------
-__global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* tables, double* pool, int F, int Fp, int perm) {
+__global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* tables, double* pool, int F, int Fp, int perm,
+                              const int8_t* asc_mask /* [2][F]: e0 then eN, may be null */) {
     extern __shared__ double srow[];  // [warps_per_block][Fp]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     double* row = srow + (size_t)wib * Fp;
@@ -186,12 +193,16 @@ __global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* t
     double* dsum = pool + jb.dst + (size_t)Fp * Fp;
     if (i >= F) {  // zero padding rows
         for (int f = lane; f < Fp; f += 32) dst[f] = 0.0;
-        if (lane == 0) dsum[i] = 0.0;
+        if (lane == 0) { dsum[i] = 0.0; dsum[Fp + i] = 0.0; dsum[2 * Fp + i] = 0.0; }
         return;
     }
     if (jb.flags & 2) {  // identity short-cut (transition_data_2d.py:184-187)
         for (int f = lane; f < Fp; f += 32) dst[perm ? kperm(f) : f] = (f == i) ? 1.0 : 0.0;
-        if (lane == 0) dsum[i] = 1.0;
+        if (lane == 0) {
+            dsum[i] = 1.0;
+            dsum[Fp + i] = (asc_mask && asc_mask[i]) ? 1.0 : 0.0;
+            dsum[2 * Fp + i] = (asc_mask && asc_mask[F + i]) ? 1.0 : 0.0;
+        }
         return;
     }
     const double* q11 = tables + jb.src[0] + (size_t)i * F;
@@ -225,7 +236,20 @@ __global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* t
         if (div) v = __ddiv_rn(v, s);
         dst[perm ? kperm(f) : f] = v;
     }
-    if (lane == 0) dsum[i] = s;
+    if (lane == 0) {
+        dsum[i] = s;
+        // low / high sums of the stored (normalised) row, ascending k
+        double lo = 0.0, hi = 0.0;
+        if (asc_mask) {
+            for (int f = 0; f < F; ++f) {
+                const double v = div ? __ddiv_rn(row[f], s) : row[f];
+                if (asc_mask[f]) lo = __dadd_rn(lo, v);
+                if (asc_mask[F + f]) hi = __dadd_rn(hi, v);
+            }
+        }
+        dsum[Fp + i] = lo;
+        dsum[2 * Fp + i] = hi;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -395,8 +419,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
     const int npass = (p.NT + 2 * NTW - 1) / (2 * NTW);
     const int nchunks = Fp / KC;
     const long long n_items = (long long)p.W * p.n_tiles;
-    const size_t blk = (size_t)Fp * Fp + Fp;
-    const int blk_rows = Fp + 1;
+    const size_t blk = blk_doubles(Fp);
+    const int blk_rows = Fp + BLK_EXTRA;
     const int rA = wm * 16 + (lane >> 2);  // tile-local rows of acc[0], acc[1] = rA, rA + 8
 
     if (threadIdx.x == 0) {

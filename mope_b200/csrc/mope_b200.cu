@@ -100,6 +100,7 @@ struct mope_ctx {
     int64_t bot_base = 0;
     double* gens_dev = nullptr;
     int32_t* work_ctr = nullptr;   // item counter of tree_kernel4 (zeroed before every launch)
+    int8_t* asc_mask = nullptr;    // [2][F] e0 (freq < min_freq) then eN (freq > 1 - min_freq)
     // model
     int n_var = 0, ndim = 0, n_ped = 0, asc_total = 0;
     double min_phred = -1, min_freq = 0, genome = 0, penalty = 0;
@@ -410,7 +411,8 @@ int layout_arena(mope_ctx* c, const mope_tables_desc* t, const mope_model_desc* 
     double* tab = bump.take<double>(ntab);
     double* gd = bump.take<double>(t->n_gens);
     int32_t* wc = bump.take<int32_t>(64);
-    if (!dry) { c->tables = tab; c->gens_dev = gd; c->work_ctr = wc; c->bot_base = (int64_t)t->n_gens * t->n_us * FF; }
+    int8_t* am = bump.take<int8_t>(2 * (size_t)t->F);
+    if (!dry) { c->tables = tab; c->gens_dev = gd; c->work_ctr = wc; c->asc_mask = am; c->bot_base = (int64_t)t->n_gens * t->n_us * FF; }
     const int Fp = round_up_i(t->F, 16);
     for (int k = 0; k < m->n_ped; ++k) {
         const mope_pedigree_desc& pd = m->peds[k];
@@ -483,7 +485,7 @@ int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d
     const int wpb = std::max(1, std::min(8, (int)((48 * 1024) / ((size_t)Fp * sizeof(double)))));
     const long long rows = (long long)n_jobs * Fp;
     const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    interp_kernel<<<grid, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, c->F, Fp, perm ? 1 : 0);
+    interp_kernel<<<grid, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, c->F, Fp, perm ? 1 : 0, c->asc_mask);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return 0;
@@ -500,11 +502,11 @@ void place_slots4(const mope_ctx* c, const std::vector<int>& parks, int32_t (&ho
         if (parks[order[r]] > 0) home[order[r]] = r;
 }
 
-template <int NTT, int NFULL, bool SCALAR>
+template <int NTT, int NFULL, bool SCALAR, bool ASCFAST>
 int launch_tree4_t(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(tree_kernel4<NTT, NFULL, SCALAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg4<NTT>::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(tree_kernel4<NTT, NFULL, SCALAR, ASCFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg4<NTT>::SMEM_BYTES));
         attr_set = true;
     }
     CUDA_TRY(cudaMemsetAsync(c->work_ctr, 0, sizeof(int32_t), st));
@@ -512,11 +514,20 @@ int launch_tree4_t(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st
         ScopedTimer timer(c, st, &c->ev_tree);
         Tree4Params tq = tp;
         tq.work_ctr = c->work_ctr;
-        tree_kernel4<NTT, NFULL, SCALAR><<<grid, NTHREADS, Cfg4<NTT>::SMEM_BYTES, st>>>(tq);
+        tree_kernel4<NTT, NFULL, SCALAR, ASCFAST><<<grid, NTHREADS, Cfg4<NTT>::SMEM_BYTES, st>>>(tq);
     }
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return 0;
+}
+
+template <int NTT, int NFULL, bool SCALAR>
+int launch_tree4_a(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st) {
+    // the ascertainment fast path (leaf messages of pure pseudo-row tiles from the low / high sums, no GEMM) is a separate
+    // instance: pedigrees without such tiles (cfg2: two pseudo-rows) keep the leaner code
+    const bool asc_fast = tp.Yout == nullptr && (tp.R_pad - (tp.L + TM - 1) / TM * TM) >= TM && !getenv("MOPE_NO_ASC_FAST");
+    if (asc_fast) return launch_tree4_t<NTT, NFULL, SCALAR, true>(c, tp, grid, st);
+    return launch_tree4_t<NTT, NFULL, SCALAR, false>(c, tp, grid, st);
 }
 
 // n-tiles that go through the tensor pipe: all-padding tiles are skipped, and a last tile with a single real column
@@ -529,14 +540,14 @@ int launch_tree4(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st) 
     const bool generic = getenv("MOPE_TREE4_GENERIC") != nullptr;
     switch (c->ntt) {
         case 10:
-            if (!generic && nf == 8 && sc) return launch_tree4_t<10, 8, true>(c, tp, grid, st);
-            return launch_tree4_t<10, 10, false>(c, tp, grid, st);
+            if (!generic && nf == 8 && sc) return launch_tree4_a<10, 8, true>(c, tp, grid, st);
+            return launch_tree4_a<10, 10, false>(c, tp, grid, st);
         case 16:
-            if (!generic && nf == 15 && !sc) return launch_tree4_t<16, 15, false>(c, tp, grid, st);
-            return launch_tree4_t<16, 16, false>(c, tp, grid, st);
+            if (!generic && nf == 15 && !sc) return launch_tree4_a<16, 15, false>(c, tp, grid, st);
+            return launch_tree4_a<16, 16, false>(c, tp, grid, st);
         default:
-            if (!generic && nf == 25 && sc) return launch_tree4_t<26, 25, true>(c, tp, grid, st);
-            return launch_tree4_t<26, 26, false>(c, tp, grid, st);
+            if (!generic && nf == 25 && sc) return launch_tree4_a<26, 25, true>(c, tp, grid, st);
+            return launch_tree4_a<26, 26, false>(c, tp, grid, st);
     }
 }
 
@@ -604,7 +615,7 @@ bool rate_range(const mope_ctx* c, double min_mult, double max_mult, double len,
 // one non-rate matrix with exact (len, mut); b = block index inside the chunk pool
 void emit_fixed_job(const mope_ctx* c, bool bott, double len, double mut, size_t& b, PlanOut& out) {
     const size_t FF = (size_t)c->F * c->F;
-    const size_t blk = (size_t)c->Fp * c->Fp + c->Fp;
+    const size_t blk = blk_doubles(c->Fp);
     if (!bott && c->N * len < c->gens[0]) {
         // identity short-cut (transition_data_2d.py:184-187): nothing to interpolate, the kernel skips the GEMM
         out.mat_off.push_back(-1);
@@ -661,7 +672,7 @@ void emit_fixed_job(const mope_ctx* c, bool bott, double len, double mut, size_t
 // the time-axis blend is per row and happens inside the tree kernel
 void emit_rate_jobs(const mope_ctx* c, double min_mult, double max_mult, double len, double mut, size_t& b, PlanOut& out) {
     const size_t FF = (size_t)c->F * c->F;
-    const size_t blk = (size_t)c->Fp * c->Fp + c->Fp;
+    const size_t blk = blk_doubles(c->Fp);
     RateInfo ri{};
     ri.len = len;
     ri.off = (int64_t)(b * blk);
@@ -728,7 +739,7 @@ struct WsFixed {
 };
 
 size_t per_walker_bytes(const mope_ctx* c, size_t n_blocks) {
-    const size_t blk = ((size_t)c->Fp * c->Fp + c->Fp) * sizeof(double);
+    const size_t blk = blk_doubles(c->Fp) * sizeof(double);
     size_t b = n_blocks * (blk + sizeof(InterpJob));
     b += c->fixed_keys.size() * sizeof(int64_t) + c->rate_keys.size() * sizeof(RateInfo);
     b += (size_t)c->Fp * sizeof(double);                 // stat
@@ -839,7 +850,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
         // carve the chunk part
         Bump cw = ws;
         cw.used = fixed_used;
-        const size_t blk = (size_t)Fp * Fp + Fp;
+        const size_t blk = blk_doubles(Fp);
         InterpJob* d_jobs = cw.take<InterpJob>(std::max<size_t>(n_blocks, 1));
         int64_t* d_mat_off = cw.take<int64_t>(std::max<size_t>((size_t)Wc * n_mat, 1));
         RateInfo* d_rate = cw.take<RateInfo>(std::max<size_t>((size_t)Wc * n_rate, 1));
@@ -893,7 +904,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
         }
 
         CUtensorMap tmapP;
-        if (int rc = make_tmap(&tmapP, d_pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + 1), Fp, tree_prows(c))) return rc;
+        if (int rc = make_tmap(&tmapP, d_pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + BLK_EXTRA), Fp, tree_prows(c))) return rc;
 
         // pruning + finalize per pedigree
         for (int k = 0; k < c->n_ped; ++k) {
@@ -1130,6 +1141,8 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         e0[f] = fr < m->min_freq;         // ascertainment.py:178-183
         eN[f] = fr > 1 - m->min_freq;
     }
+    CUDA_TRY_C(cudaMemcpyAsync(c->asc_mask, e0.data(), F, cudaMemcpyHostToDevice, st));
+    CUDA_TRY_C(cudaMemcpyAsync(c->asc_mask + F, eN.data(), F, cudaMemcpyHostToDevice, st));
 
     int asc_off = 0;
     for (int k = 0; k < m->n_ped; ++k) {
@@ -1329,7 +1342,7 @@ int mope_b200_transition_matrix(mope_ctx* c, int bottleneck, double x, double sc
         for (int i = 0; i < F; ++i) for (int j = 0; j < F; ++j) out_P[(size_t)i * F + j] = (i == j) ? 1.0 : 0.0;
         return 0;
     }
-    const size_t blk = (size_t)Fp * Fp + Fp;
+    const size_t blk = blk_doubles(Fp);
     const size_t need = align_up(sizeof(InterpJob), 256) + blk * sizeof(double) + (size_t)F * F * sizeof(double) + 1024;
     if (ensure_opbuf(c, need)) return MOPE_E_CUDA;
     InterpJob* d_job = reinterpret_cast<InterpJob*>(c->opbuf);
@@ -1409,7 +1422,7 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
     cudaStream_t st = (cudaStream_t)stream;
     const int F = c->F, Fp = c->Fp;
     const int R_pad = round_up_i(n_rows, TM);
-    const size_t blk = (size_t)Fp * Fp + Fp;
+    const size_t blk = blk_doubles(Fp);
 
     // plan
     PlanOut po;
@@ -1480,7 +1493,7 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
         CUDA_TRY(cudaMemcpyAsync(P.op, &o4, sizeof(Op4), cudaMemcpyHostToDevice, st));
         Tree4Params t4{};
         if (int rc = make_tmap(&t4.tmapE, P.E, (uint64_t)R_pad, Fp, TM)) return rc;
-        if (int rc = make_tmap(&t4.tmapP, P.pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + 1), Fp, tree_prows(c))) return rc;
+        if (int rc = make_tmap(&t4.tmapP, P.pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + BLK_EXTRA), Fp, tree_prows(c))) return rc;
         t4.E = P.E; t4.E_leaf_stride = (int64_t)R_pad * Fp; t4.scratch = P.Y /*unused*/; t4.ops = reinterpret_cast<const Op4*>(P.op);
         t4.n_ops = 1; t4.n_slots = 1; place_slots4(c, std::vector<int>(), t4.slot_home);
         t4.R = n_rows; t4.L = n_rows; t4.R_pad = R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = R_pad / TM; t4.W = 1;
@@ -1492,7 +1505,7 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
     TreeParams tp{};
     if (int rc = make_tmap(&tp.tmapE, P.E, (uint64_t)R_pad, Fp, TM)) return rc;
     if (int rc = make_tmap(&tp.tmapS, P.Y, (uint64_t)R_pad, Fp, TM)) return rc;   // no scratch ring in single-op mode
-    if (int rc = make_tmap(&tp.tmapP, P.pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + 1), Fp, tree_prows(c))) return rc;
+    if (int rc = make_tmap(&tp.tmapP, P.pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + BLK_EXTRA), Fp, tree_prows(c))) return rc;
     tp.E = P.E; tp.E_leaf_stride = (int64_t)R_pad * Fp; tp.scratch = P.Y /*unused*/; tp.ops = P.op; tp.n_ops = 1; tp.n_slots = 0;
     tp.R = n_rows; tp.L = n_rows; tp.R_pad = R_pad; tp.Fp = Fp; tp.F = F; tp.NT = c->NT; tp.n_tiles = R_pad / TM; tp.W = 1;
     tp.tile_block = tp.n_tiles;

@@ -173,7 +173,7 @@ __device__ __forceinline__ void chunk_mma(double (&acc)[NTT][2], double& sacc, c
     }
 }
 
-template <int NTT, int NFULL, bool SCALAR>
+template <int NTT, int NFULL, bool SCALAR, bool ASCFAST>
 __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constant__ Tree4Params p) {
     using Cfg = Cfg4<NTT>;
     extern __shared__ unsigned char smem_raw[];
@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
     const int x = lane >> 2, kk = lane & 3;
     const int Fp = p.Fp;
     const int nchunks = Fp / KC;
-    const int blk_rows = Fp + 1;
-    const size_t blk = (size_t)Fp * Fp + Fp;
+    const int blk_rows = Fp + BLK_EXTRA;
+    const size_t blk = blk_doubles(Fp);
     double* my_scratch = p.scratch + ((size_t)blockIdx.x * 8 + warp) * (p.n_slots + 1) * NTT * 64;
     // fragment addressing inside a stage (128 B swizzle, see kernels.cuh)
     const int z = x ^ ((kk >> 1) << 2);
@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         }
         const int row0 = tile * TM;
         const int my_row = row0 + warp * 8 + x;     // the row this thread's fragments belong to
+        // A tile of ascertainment pseudo-rows only: every leaf starts from e0 (even rows) or eN (odd rows), so the message of
+        // a leaf branch is P . e0 / P . eN -- the low / high sums stored with every matrix block -- and needs no GEMM.
+        const bool asc_tile = ASCFAST && row0 >= p.L && p.Yout == nullptr;
 
         // ---- per-item tables: matrix rows, generation ranges of the rate ops ----
         for (int i = threadIdx.x; i < p.n_ops; i += NTHREADS) {
@@ -322,6 +325,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             for (int i = 0; i < p.n_ops; ++i) {
                 const Op4& o = ts->ops[i];
                 ts->unit_first[i] = n;
+                if (asc_tile && o.leaf >= 0) continue;   // no GEMM: message from the low / high sums
                 n += (o.kind == 0) ? (ts->prow[i] >= 0 ? 1 : 0) : max(0, ts->seg_hi[i] - ts->seg_lo[i] + 1);
             }
             ts->unit_first[p.n_ops] = n;
@@ -398,7 +402,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             double sacc = 0.0;
 
             // ---------------- GEMM(s) ----------------
-            const int nseg = identity ? 0 : (op.kind == 0 ? 1 : max(0, ts->seg_hi[oi] - ts->seg_lo[oi] + 1));
+            const bool asc_leaf = asc_tile && op.leaf >= 0;
+            const int nseg = (identity || asc_leaf) ? 0 : (op.kind == 0 ? 1 : max(0, ts->seg_hi[oi] - ts->seg_lo[oi] + 1));
             for (int si = 0; si < nseg; ++si) {
                 double wgt = 1.0;
                 if (op.kind == 1) {
@@ -453,6 +458,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             PROF_MARK(1)
             // ---------------- post-op (warp local) ----------------
             const bool row_ident = identity || (op.kind == 1 && gi < 0);
+            if (asc_leaf && !row_ident) {
+                const int which = 1 + ((my_row - p.L) & 1);   // block vector Fp + 1: low sums (P . e0), Fp + 2: high sums (P . eN)
+                if (my_row < p.R && op.kind == 0) {
+                    const double* v = p.pool + (size_t)ts->prow[oi] * Fp + (size_t)Fp * Fp + (size_t)which * Fp + 2 * kk;
+#pragma unroll
+                    for (int n = 0; n < NTT; ++n)
+                        if (8 * n < Fp) { acc[n][0] = v[8 * n]; acc[n][1] = v[8 * n + 1]; }
+                } else if (my_row < p.R) {
+                    // blend of the two grid generations the row's time falls between; renormalised below like any other row
+                    const double* v2 = p.pool + ri->off + (size_t)(gi - ri->gbase) * blk + (size_t)Fp * Fp + (size_t)which * Fp + 2 * kk;
+                    const double* v1 = v2 - blk;
+                    const bool two = (gi > 0 && ra != 0.0);
+#pragma unroll
+                    for (int n = 0; n < NTT; ++n) {
+                        if (8 * n < Fp) {
+                            double y0 = 0.0, y1 = 0.0;
+                            if (two) { y0 = ra * v1[8 * n]; y1 = ra * v1[8 * n + 1]; }
+                            acc[n][0] = fma(rd, v2[8 * n], y0);
+                            acc[n][1] = fma(rd, v2[8 * n + 1], y1);
+                        }
+                    }
+                }
+            }
             // identity short-cut (transition_data_2d.py:184-187) or padding row: the message is the operand itself
             if (op.leaf >= 0) {
                 if (row_ident) {
