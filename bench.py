@@ -405,7 +405,7 @@ def run_ours(args):
                 traffic = tj["traffic_bytes_per_launch"]
         except Exception:
             pass
-        roofline = {"bound": "tensor", "kernel": "tree_kernel4<26> (fused pruning pass: TMA ring + mma.sync.m8n8k4.f64, warp-owned rows)", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "tensor", "kernel": "tree_kernel4<26,25,scalar> (fused pruning pass: TMA ring + mma.sync.m8n8k4.f64, warp-owned rows, messages in tensor memory)", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, profiles/r01_traffic.json)",
                     "peak_source": "fp64 DMMA register-only loop measured live in this run (MEASURED_PEAKS.json has no fp64 entry; "
                                    "its dense-bf16 figure does not bound an fp64 kernel)",

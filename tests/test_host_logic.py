@@ -103,6 +103,18 @@ def test_stationary_distribution_bit_identical_to_reference():
         np.testing.assert_array_equal(got[i], orc.get_stationary_distribution_double_beta(TB["breaks"], int(TB["N"]), ab[i], pp[i]))
 
 
+def test_beta_cdf_table_is_scipy_beta_cdf_bit_for_bit():
+    """mope_b200_beta_cdf_table (native threads through SciPy's betainc C entry point) == scipy.stats.beta.cdf, the call
+    likelihoods.discretize_beta_distn makes (mope/likelihoods.py:40), over the whole prior range of ab."""
+    import scipy.stats as st
+    ab = 10 ** np.random.RandomState(3).uniform(-9, 0, 37)
+    edges = np.arange(1, 2 * 998, 2) / (2 * 998)
+    for nt in (1, 3, 16):
+        got = stationary.beta_cdf_table(ab, edges, n_threads=nt)
+        for i in (0, 5, 36):
+            np.testing.assert_array_equal(got[i], st.beta.cdf(edges, ab[i], ab[i]))
+
+
 def test_tables_validation(tmp_path):
     tb = tables.TransitionTables(drift=TB["drift"], gens=TB["gens"], us=TB["us"], N=float(TB["N"]), freqs=TB["freqs"],
                                  breaks=TB["breaks"], bot=TB["bot"], nbs=TB["nbs"], bot_us=TB["bot_us"])
