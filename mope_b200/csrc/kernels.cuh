@@ -92,6 +92,7 @@ struct TreeParams {
     double* asc_dot;         // [W][R - L]
     double* Yout;            // operator-level mode (single op): Y rows go to Yout[w][row][Fp] instead of a slot
     int32_t debug;           // measurement only: 1 = skip the MMAs (data movement only), 2 = skip the copies (MMAs only)
+    int32_t* work_ctr;       // zeroed before the launch: next item to hand out
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -236,17 +237,22 @@ __global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* t
         if (div) v = __ddiv_rn(v, s);
         dst[perm ? kperm(f) : f] = v;
     }
+    // low / high sums of the stored (normalised) row: lane-strided partial sums, then a fixed-order warp reduction
+    double lo = 0.0, hi = 0.0;
+    if (asc_mask) {
+        for (int f = lane; f < F; f += 32) {
+            const double v = div ? __ddiv_rn(row[f], s) : row[f];
+            if (asc_mask[f]) lo = __dadd_rn(lo, v);
+            if (asc_mask[F + f]) hi = __dadd_rn(hi, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = __dadd_rn(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = __dadd_rn(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+    }
     if (lane == 0) {
         dsum[i] = s;
-        // low / high sums of the stored (normalised) row, ascending k
-        double lo = 0.0, hi = 0.0;
-        if (asc_mask) {
-            for (int f = 0; f < F; ++f) {
-                const double v = div ? __ddiv_rn(row[f], s) : row[f];
-                if (asc_mask[f]) lo = __dadd_rn(lo, v);
-                if (asc_mask[F + f]) hi = __dadd_rn(hi, v);
-            }
-        }
         dsum[Fp + i] = lo;
         dsum[2 * Fp + i] = hi;
     }
@@ -283,6 +289,7 @@ struct TreeSmem {
     double row_a[TM], row_d[TM];
     int32_t row_g[TM];      // generation-grid index gi of the row (rate ops); -1 = identity / padding row
     int32_t seg_lo, seg_hi; // tile segment range (absolute grid indices), seg_lo > seg_hi = nothing to do
+    long long cur_item;     // the item the CTA works on (handed out dynamically: items differ in cost)
 };
 
 template <int NTW>
@@ -435,7 +442,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
     unsigned g = 0;       // chunks consumed so far (ring position), identical in every thread
     unsigned epi_n = 0;   // epilogues completed so far (phase of ts->epi)
 
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (;;) {
+        if (threadIdx.x == 0) ts->cur_item = (long long)atomicAdd(p.work_ctr, 1);
+        __syncthreads();
+        const long long item = ts->cur_item;
+        if (item >= n_items) break;
         // item order: tile blocks outermost, then walkers, then the tiles of the block, so that a block of
         // emission tiles is re-used by every walker while it is L2 resident
         int w, tile;

@@ -470,9 +470,12 @@ int launch_tree_t(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) 
         CUDA_TRY(cudaFuncSetAttribute(tree_kernel<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<NTW>::SMEM_BYTES));
         attr_set = true;
     }
+    CUDA_TRY(cudaMemsetAsync(c->work_ctr, 0, sizeof(int32_t), st));
     {
         ScopedTimer timer(c, st, &c->ev_tree);
-        tree_kernel<NTW><<<grid, NTHREADS, TileCfg<NTW>::SMEM_BYTES, st>>>(tp);
+        TreeParams tq = tp;
+        tq.work_ctr = c->work_ctr;
+        tree_kernel<NTW><<<grid, NTHREADS, TileCfg<NTW>::SMEM_BYTES, st>>>(tq);
     }
     CUDA_TRY(cudaGetLastError());
     c->launches++;
