@@ -410,6 +410,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                     const int seg = ts->seg_lo[oi] + si;
                     wgt = (gi >= 0) ? ((seg == gi - 1 ? ra : 0.0) + (seg == gi ? rd : 0.0)) : 0.0;
                 }
+                // a warp none of whose 8 rows blends this grid generation only keeps pace with the ring (its products would
+                // all be zero); the warp it shares the sub-partition's DMMA pipe with then runs the segment at full rate
+                const bool seg_active = (op.kind != 1) || __any_sync(0xffffffffu, wgt != 0.0);
                 uint32_t an[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // chained A values of the coming chunk (tcgen05.ld in flight)
                 if (op.leaf < 0) tmem_ld4_issue(t_chain, an);
                 for (int c = 0; c < nchunks; ++c) {
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                     PROF_MARK(3)   // waiting for the stage
                     const int nq = (c + 1 == nchunks) ? nq_last : 4;
                     const unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
-                    if (!no_mma) {
+                    if (!no_mma && seg_active) {
                         // the four operand flavours get their own straight-line code: nothing but LDS + DMMA between k steps
                         if (op.leaf >= 0) {
                             if (op.kind == 1) chunk_mma<NTT, NFULL, SCALAR, true, true, no_lds>(acc, sacc, st, a_base, b_base, z, bs_base, z0, ac, wgt, nq);
