@@ -67,6 +67,10 @@ def test_cfg3_cfg4_shape_rate_and_bottleneck_branches_vs_oracle():
     I, X, ll = _check_vs_oracle(ds, _tables_small(), 3, shrink=0.25)
     assert I.peds[0].n_asc == I.peds[0].n_fam                   # ages differ per family: no sharing
     I.close()
+    # several frequency bins below min_freq / above 1 - min_freq: the ascertainment tiles take the leaf-branch messages
+    # from multi-column low / high sums of the matrices (no GEMM), the mixed tile still multiplies
+    I, X, ll = _check_vs_oracle(ds, _tables_small(), 2, shrink=0.25, min_freq=0.004)
+    I.close()
 
 
 def test_leaf_minimum_and_unary_chain_trees_vs_oracle():
