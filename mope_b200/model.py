@@ -103,7 +103,8 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
 
     ages = ages.copy()
     fam_ids = ages["family"].values
-    counts = np.array([(family == f).sum() for f in fam_ids], dtype=np.int64)
+    # loci per family (ascertainment.py:173 counts rows per family id); one pass instead of one scan per family
+    counts = pd.Series(family).value_counts().reindex(fam_ids, fill_value=0).values.astype(np.int64)
     ages["count"] = counts
     for m in multipliernames:
         if m not in ages.columns:
@@ -118,7 +119,8 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
             row_mult[j] = data[m].values.astype(np.float64)
         else:
             col = ages[m].values.astype(np.float64)
-            row_mult[j] = [col[first_row_of[f]] for f in family]   # .iloc[0] of the matching rows
+            first_idx = np.array([first_row_of[f] for f in pd.unique(family)], dtype=np.int64)
+            row_mult[j] = col[first_idx[pd.factorize(family)[0]]]   # .iloc[0] of the matching rows
     # distinct ascertainment row pairs: the pruning of the pseudo-rows depends on the family only through its
     # multiplier values, so equal multiplier tuples share one pair (bit-identical results, fewer rows)
     fam_mult = np.zeros((M, len(fam_ids)))
