@@ -33,7 +33,8 @@ def partition_families(family_of_locus: np.ndarray, families: np.ndarray, world:
     """Split the family list into `world` contiguous groups with balanced row counts (loci + 2 ascertainment rows).
     Every family of the ages table lands in exactly one group -- also families without any locus, whose Poisson
     term still counts (inference.py:1113-1129)."""
-    rows = np.array([(family_of_locus == f).sum() + 2 for f in families], dtype=np.float64)
+    import pandas as pd
+    rows = pd.Series(family_of_locus).value_counts().reindex(families, fill_value=0).values.astype(np.float64) + 2.0
     cum = np.cumsum(rows)
     total = cum[-1] if len(cum) else 0.0
     groups, start = [], 0
