@@ -76,6 +76,7 @@ struct Pedigree {
     Op4* ops4 = nullptr;
     std::vector<Op4> ops4_h;
     std::vector<int> slot_parks4;   // how often each slot is written per item
+    int n_uroot4 = 0;               // family-independent subtrees of the ascertainment pass (top branches that are not leaves)
     int n_slots4 = 0;
     int asc_offset = 0;
     CUtensorMap tmapE;
@@ -107,7 +108,7 @@ struct mope_ctx {
     std::vector<Pedigree> peds;
     std::vector<FixedKey> fixed_keys;
     std::vector<RateKey> rate_keys;
-    int max_slots = 0, max_tiles = 0, max_asc2 = 0;
+    int max_slots = 0, max_tiles = 0, max_asc2 = 0, max_uroot = 0;
     // host staging (pinned, grow-only)
     char* pinned = nullptr;
     size_t pinned_cap = 0, pinned_off = 0;
@@ -394,6 +395,23 @@ int compile_schedule4(const mope_pedigree_desc& pd, const std::vector<int>& fixe
     }
     if (out.ops4_h.empty() || !out.ops4_h.back().last) return fail(MOPE_E_INVALID, "schedule does not end at the root");
     out.n_slots4 = std::max(n_slots, 1);
+    // Ascertainment pseudo-rows: a branch whose subtree holds no age-scaled branch carries the same message for every
+    // family (uni != 0); the top branch of such a subtree (uni == 2) is computed once per walker (tree4.cuh, canonical launch)
+    {
+        std::vector<char> uniform(nb, 1);
+        for (int b = 0; b < nb; ++b) {   // postorder: children come before their parent
+            if (out.ops4_h[b].kind != 0) uniform[b] = 0;
+            const int par = pd.br_parent[b];
+            if (par != root && !uniform[b]) uniform[par] = 0;
+        }
+        out.n_uroot4 = 0;
+        for (int b = 0; b < nb; ++b) {
+            Op4& o = out.ops4_h[b];
+            const int par = pd.br_parent[b];
+            o.uni = !uniform[b] ? 0 : ((par == root || !uniform[par]) ? 2 : 1);
+            o.uroot = (o.uni == 2 && o.leaf < 0) ? out.n_uroot4++ : -1;
+        }
+    }
     // parks per slot: the busiest slots get the tensor-memory homes (placement happens at launch, tree4.cuh)
     out.slot_parks4.assign(out.n_slots4, 0);
     for (const Op4& o : out.ops4_h) if (o.store_slot >= 0) out.slot_parks4[o.store_slot]++;
@@ -748,6 +766,7 @@ size_t per_walker_bytes(const mope_ctx* c, size_t n_blocks) {
     b += (size_t)c->Fp * sizeof(double);                 // stat
     b += (size_t)c->max_tiles * sizeof(double);          // tile_ll
     b += (size_t)c->max_asc2 * sizeof(double);           // asc_dot
+    b += (size_t)c->max_uroot * 2 * c->Fp * sizeof(double);   // family-independent ascertainment messages
     return b + 64;
 }
 
@@ -862,6 +881,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
         double* d_pool = cw.take<double>(std::max<size_t>(n_blocks, 1) * blk);
         double* d_tile_ll = cw.take<double>((size_t)Wc * c->max_tiles);
         double* d_asc_dot = cw.take<double>((size_t)Wc * std::max(c->max_asc2, 2));
+        double* d_uni = cw.take<double>(std::max<size_t>((size_t)Wc * c->max_uroot * 2 * Fp, 1));
         if (!cw.ok()) return fail(MOPE_E_NOMEM, "internal: chunk carve exceeded the workspace (%zu > %zu)", cw.used, cw.cap);
 
         // stage host -> device
@@ -936,6 +956,15 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
                 t4.mult = P.mult; t4.gens = c->gens_dev; t4.n_gens = c->n_gens; t4.Npop = c->N; t4.stat = d_stat;
                 t4.tile_ll = d_tile_ll; t4.asc_dot = d_asc_dot; t4.Yout = nullptr;
                 if (const char* e = getenv("MOPE_DEBUG_MODE")) t4.debug = atoi(e);
+                // family-independent messages of the ascertainment pass: one canonical tile per walker first, when the
+                // pedigree has enough pure pseudo-row tiles to pay for it
+                const int pure_asc_tiles = (P.R_pad - (P.L + TM - 1) / TM * TM) / TM;
+                if (P.n_uroot4 > 0 && pure_asc_tiles >= 8 && !getenv("MOPE_NO_ASC_FAST") && !getenv("MOPE_NO_ASC_CSE")) {
+                    t4.uni_msg = d_uni; t4.n_uroot = P.n_uroot4;
+                    Tree4Params tc = t4;
+                    tc.canonical = 1;
+                    if (launch_tree4(c, tc, std::min(Wc, c->num_sms), st)) return MOPE_E_CUDA;
+                }
                 if (launch_tree4(c, t4, grid, st)) return MOPE_E_CUDA;
             } else {
             TreeParams tp{};
@@ -1165,6 +1194,7 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         }
         c->max_tiles = std::max(c->max_tiles, P.n_tiles);
         c->max_asc2 = std::max(c->max_asc2, 2 * P.n_asc);
+        c->max_uroot = std::max(c->max_uroot, P.n_uroot4);
 
         // multipliers per row (real rows then ascertainment pairs, np.repeat(..., 2): ascertainment.py:205-206)
         std::vector<double> mult((size_t)std::max(pd.n_mult, 1) * P.R_pad, 0.0);

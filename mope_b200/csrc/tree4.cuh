@@ -42,6 +42,9 @@ struct Op4 {
     int32_t store_slot;   // >= 0: not the last child: park the message (store_first) or fold it into the parked one
     int32_t store_first;
     int32_t last;         // completes the root: root reduction
+    int32_t uni;          // ascertainment pseudo-rows: 0 the message depends on the family (an age-scaled branch at or below it),
+                          // 1 inside a subtree whose messages are the same for every family, 2 the top branch of such a subtree
+    int32_t uroot;        // uni == 2 and not a leaf: index of the per-walker message in Tree4Params::uni_msg
 };
 
 struct Tree4Params {
@@ -68,6 +71,12 @@ struct Tree4Params {
     int32_t debug;           // measurement only, bit flags: 1 skip the MMAs, 2 skip the copies and ring barriers
     int32_t slot_home[MAX_SLOTS4];   // where a parked slot lives: k >= 0 the k-th tensor-memory slot of the warp,
                                      // SLOT_HOME_L2 the L2 scratch
+    // Messages of ascertainment pseudo-rows that do not depend on the family (no age-scaled branch at or below the branch)
+    // are the same for all even / all odd pseudo-rows of a walker.  A first, one-tile-per-walker launch (canonical = 1)
+    // writes them to uni_msg [W][n_uroot][2][Fp] (natural column order); in the main launch a pure pseudo-row tile skips
+    // the branches inside such subtrees and reads the message of their top branch from there.
+    double* uni_msg;
+    int32_t n_uroot, canonical;
     int32_t* work_ctr;       // zeroed before the launch: next item to hand out (items differ in cost: identity branches)
 };
 
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
 
     unsigned g = 0;   // chunks consumed so far (ring position)
     PROF_DECL
-    const long long n_items = (long long)p.W * p.n_tiles;
+    const long long n_items = p.canonical ? (long long)p.W : (long long)p.W * p.n_tiles;
 
     for (;;) {
         // items are handed out dynamically in the L2-friendly order: a CTA that drew cheap items (walkers with many
@@ -283,11 +292,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             w = (int)(rem / t_count);
             tile = t_first + (int)(rem % t_count);
         }
-        const int row0 = tile * TM;
+        if (p.canonical) { w = (int)item; tile = 0; }
+        // the canonical item of a walker: the first pseudo-row pair (rows L, L + 1 = parities 0, 1) leads the tile
+        const int row0 = p.canonical ? p.L : tile * TM;
         const int my_row = row0 + warp * 8 + x;     // the row this thread's fragments belong to
         // A tile of ascertainment pseudo-rows only: every leaf starts from e0 (even rows) or eN (odd rows), so the message of
         // a leaf branch is P . e0 / P . eN -- the low / high sums stored with every matrix block -- and needs no GEMM.
         const bool asc_tile = ASCFAST && row0 >= p.L && p.Yout == nullptr;
+        const bool asc_cse = asc_tile && !p.canonical && p.uni_msg != nullptr;   // family-independent subtrees come from uni_msg
 
         // ---- per-item tables: matrix rows, generation ranges of the rate ops ----
         for (int i = threadIdx.x; i < p.n_ops; i += NTHREADS) {
@@ -326,6 +338,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 const Op4& o = ts->ops[i];
                 ts->unit_first[i] = n;
                 if (asc_tile && o.leaf >= 0) continue;   // no GEMM: message from the low / high sums
+                if (asc_cse && o.uni != 0) continue;     // no GEMM: inside / on top of a family-independent subtree
                 n += (o.kind == 0) ? (ts->prow[i] >= 0 ? 1 : 0) : max(0, ts->seg_hi[i] - ts->seg_lo[i] + 1);
             }
             ts->unit_first[p.n_ops] = n;
@@ -390,6 +403,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
 
         for (int oi = 0; oi < p.n_ops; ++oi) {
             const Op4 op = ts->ops[oi];
+            if (asc_cse && op.uni == 1) continue;   // inside a family-independent subtree: its top branch supplies the message
             const bool identity = (op.kind == 0 && ts->prow[oi] < 0);
             const RateInfo* ri = (op.kind == 1) ? &p.rate[(size_t)w * p.n_rate + op.key] : nullptr;
             int gi = 0;
@@ -403,7 +417,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
 
             // ---------------- GEMM(s) ----------------
             const bool asc_leaf = asc_tile && op.leaf >= 0;
-            const int nseg = (identity || asc_leaf) ? 0 : (op.kind == 0 ? 1 : max(0, ts->seg_hi[oi] - ts->seg_lo[oi] + 1));
+            const bool asc_uroot = asc_cse && op.uni == 2 && op.leaf < 0;
+            const int nseg = (identity || asc_leaf || asc_uroot) ? 0 : (op.kind == 0 ? 1 : max(0, ts->seg_hi[oi] - ts->seg_lo[oi] + 1));
             for (int si = 0; si < nseg; ++si) {
                 double wgt = 1.0;
                 if (op.kind == 1) {
@@ -460,7 +475,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             }
             PROF_MARK(1)
             // ---------------- post-op (warp local) ----------------
-            const bool row_ident = identity || (op.kind == 1 && gi < 0);
+            const bool row_ident = !asc_uroot && (identity || (op.kind == 1 && gi < 0));
+            if (asc_uroot && my_row < p.R) {
+                // the whole subtree below this branch is the same for every family: its message was computed once per walker
+                const double* v = p.uni_msg + (((size_t)w * p.n_uroot + op.uroot) * 2 + ((my_row - p.L) & 1)) * Fp + 2 * kk;
+#pragma unroll
+                for (int n = 0; n < NTT; ++n)
+                    if (8 * n < Fp) { acc[n][0] = v[8 * n]; acc[n][1] = v[8 * n + 1]; }
+            }
             if (asc_leaf && !row_ident) {
                 const int which = 1 + ((my_row - p.L) & 1);   // block vector Fp + 1: low sums (P . e0), Fp + 2: high sums (P . eN)
                 if (my_row < p.R && op.kind == 0) {
@@ -526,6 +548,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 }
             }
 
+            if (p.canonical) {
+                // canonical launch: rows L, L + 1 (parities 0, 1) of warp 0 publish the family-independent messages
+                if (op.uni == 2 && op.leaf < 0 && warp == 0 && x < 2) {
+                    double* v = p.uni_msg + (((size_t)w * p.n_uroot + op.uroot) * 2 + x) * Fp + 2 * kk;
+#pragma unroll
+                    for (int n = 0; n < NTT; ++n)
+                        if (8 * n < Fp) { v[8 * n] = acc[n][0]; v[8 * n + 1] = acc[n][1]; }
+                }
+            }
             if (p.Yout != nullptr) {
                 double* yo = p.Yout + ((size_t)w * p.R_pad + my_row) * Fp + 2 * kk;
 #pragma unroll
@@ -563,7 +594,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 if (kk == 0) {
                     double v = 0.0;
                     if (my_row < p.L) v = log(dot);
-                    else if (my_row < p.R) p.asc_dot[(size_t)w * (p.R - p.L) + (my_row - p.L)] = dot;
+                    else if (my_row < p.R && !p.canonical) p.asc_dot[(size_t)w * (p.R - p.L) + (my_row - p.L)] = dot;
                     ts->rowval[warp * 8 + x] = v;
                 }
             }
@@ -571,7 +602,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         }  // ops
 
         __syncthreads();   // rowval complete; every warp is done with the item's tables
-        if (p.Yout == nullptr && warp == 0) {
+        if (p.Yout == nullptr && !p.canonical && warp == 0) {
             double part = ts->rowval[lane] + ts->rowval[lane + 32];
 #pragma unroll
             for (int o2 = 16; o2 > 0; o2 >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o2);

@@ -73,6 +73,27 @@ def test_cfg3_cfg4_shape_rate_and_bottleneck_branches_vs_oracle():
     I.close()
 
 
+def test_family_independent_ascertainment_subtrees_vs_oracle():
+    """Fixed leaves under one age-scaled internal branch and one bottleneck branch (the cfg4 shape): on pure pseudo-row
+    tiles the subtrees without an age-scaled branch are taken from the once-per-walker canonical launch.  Enough families
+    for >= 8 such tiles; with MOPE_NO_ASC_CSE the same evaluation goes through the GEMMs and must agree to rounding."""
+    import os
+    from mope_b200 import synth
+    tree = synth.balanced_tree(8, rate_internal=True, bottleneck=True)
+    ds = synth.make_dataset(960, 8, tree=tree, seed=11)
+    I, X, ll = _check_vs_oracle(ds, _tables_small(), 2, shrink=0.25)
+    assert 2 * I.peds[0].n_asc >= 8 * 64
+    I.close()
+    os.environ["MOPE_NO_ASC_CSE"] = "1"
+    try:
+        I2 = _gpu_for(ds, _tables_small())
+        ll2 = I2.loglike_batch(X)
+        I2.close()
+    finally:
+        del os.environ["MOPE_NO_ASC_CSE"]
+    assert (np.abs(ll2 - ll) / np.abs(ll)).max() < 1e-13
+
+
 def test_leaf_minimum_and_unary_chain_trees_vs_oracle():
     from mope_b200 import synth
     for tree in ("(t0:a,t1:b)root;", "((((t0:a)n1:b)n2:c*child_age)n3:d^,t1:a)root;", "(t0:a,t1:a,t2:b,t3:c*mother_age)root;",
