@@ -121,6 +121,21 @@ class _Mat:
     def mm(self, a, b):
         return self.torch.matmul(a, b) if self.torch else a @ b
 
+    def var_n(self, N1: int, N2: int, N0: int, mu: float):
+        """var_n_matrix on the device: the binomial pmf from lgamma (the host version calls scipy.stats.binom.pmf on up
+        to a million cells per factor, which dominated the bottleneck grid's generation time)."""
+        if not self.torch:
+            return var_n_matrix(N1, N2, N0, mu)
+        t = self.torch
+        f = t.arange(N1 + 1, dtype=t.float64, device=self.device) / N1
+        f = (1 - mu) * f + (1 - f) * mu                       # strictly inside (0, 1) for 0 < mu < 1
+        k = t.arange(N2 + 1, dtype=t.float64, device=self.device)
+        lc = t.lgamma(t.tensor(N2 + 1.0, dtype=t.float64, device=self.device)) - t.lgamma(k + 1) - t.lgamma(N2 - k + 1)
+        logpmf = lc[None, :] + k[None, :] * t.log(f)[:, None] + (N2 - k)[None, :] * t.log1p(-f)[:, None]
+        P = t.zeros((N0 + 1, N0 + 1), dtype=t.float64, device=self.device)
+        P[: N1 + 1, : N2 + 1] = t.exp(logpmf)
+        return P
+
 
 def _power_from_cache(mat: _Mat, squares: list, n: int):
     """P^n from cached P^(2^k)."""
@@ -184,7 +199,9 @@ def bottleneck_matrix(N: int, Nb: int, mu: float, mat: Optional[_Mat] = None) ->
     Ns = [N, Nb] + [Nb * 2 ** d for d in range(1, num_doublings + 1)]
     if num_gens > num_doublings:
         Ns.append(N)
-    P = mat.put(var_n_matrix(Ns[0], Ns[1], N, mu))
+    use_dev = mat.torch is not None and 0.0 < mu < 1.0
+    fac = (lambda a, b: mat.var_n(a, b, N, mu)) if use_dev else (lambda a, b: mat.put(var_n_matrix(a, b, N, mu)))
+    P = fac(Ns[0], Ns[1])
     for N1, N2 in zip(Ns[1:-1], Ns[2:]):
-        P = mat.mm(P, mat.put(var_n_matrix(N1, N2, N, mu)))
+        P = mat.mm(P, fac(N1, N2))
     return mat.get(P)
