@@ -121,6 +121,41 @@ class _Mat:
     def mm(self, a, b):
         return self.torch.matmul(a, b) if self.torch else a @ b
 
+    def wright_fisher(self, N: int, s: float, u: float, v: float):
+        """wright_fisher_matrix on the device (binomial log-pmf from lgamma); host SciPy when there is no device or the
+        mutated frequency reaches 0 or 1."""
+        i = np.arange(N + 1)
+        p = i / N
+        pmut = (1 - u) * p + v * (1 - p)
+        pstar = np.minimum(pmut * (1 + s) / (pmut * (1 + s) + 1 - pmut), 1.0)
+        if not self.torch or pstar.min() <= 0.0 or pstar.max() >= 1.0:
+            return self.put(wright_fisher_matrix(N, s, u, v))
+        t = self.torch
+        ps = t.as_tensor(pstar, dtype=t.float64, device=self.device)
+        k = t.arange(N + 1, dtype=t.float64, device=self.device)
+        lc = t.lgamma(t.tensor(N + 1.0, dtype=t.float64, device=self.device)) - t.lgamma(k + 1) - t.lgamma(N - k + 1)
+        return t.exp(lc[None, :] + k[None, :] * t.log(ps)[:, None] + (N - k)[None, :] * t.log1p(-ps)[:, None])
+
+    def binner(self, n_states: int, breaks: np.ndarray):
+        """bin_matrix for device matrices: column sums per bin as one GEMM with the 0/1 membership matrix, then the middle
+        row(s) of every bin; only the F x F result leaves the device."""
+        if not self.torch:
+            return lambda P: bin_matrix(P, breaks)
+        t = self.torch
+        breaks = np.asarray(breaks)
+        lengths = np.concatenate((np.diff(breaks), [n_states - breaks[-1]]))
+        member = np.zeros((n_states, breaks.shape[0]))
+        member[np.arange(n_states), np.repeat(np.arange(breaks.shape[0]), lengths)] = 1.0
+        M = t.as_tensor(member, dtype=t.float64, device=self.device)
+        lo = t.as_tensor(breaks + np.floor((lengths - 1) / 2).astype(np.int64), device=self.device)
+        hi = t.as_tensor(breaks + np.ceil((lengths - 1) / 2).astype(np.int64), device=self.device)
+        even = t.as_tensor((lengths % 2 == 0)[:, None], device=self.device)
+
+        def run(P):
+            colsum = t.matmul(P, M)
+            return t.where(even, (colsum[lo, :] + colsum[hi, :]) / 2, colsum[lo, :]).cpu().numpy()
+        return run
+
     def var_n(self, N1: int, N2: int, N0: int, mu: float):
         """var_n_matrix on the device: the binomial pmf from lgamma (the host version calls scipy.stats.binom.pmf on up
         to a million cells per factor, which dominated the bottleneck grid's generation time)."""
@@ -164,15 +199,16 @@ def generate_tables(N: int = 1000, breaks=(0.5, 0.01), gens: Sequence[int] = DEF
     freqs = get_binned_frequencies(N, br)
     F = br.shape[0]
     drift = np.empty((len(gens), len(us), F, F))
+    binned = mat.binner(N + 1, br)
     for j, u in enumerate(us):
-        P = mat.put(wright_fisher_matrix(N, s, u, u))
+        P = mat.wright_fisher(N, s, u, u)
         squares = [P]
         cur = _power_from_cache(mat, squares, gens[0])
-        drift[0, j] = bin_matrix(mat.get(cur), br)
+        drift[0, j] = binned(cur)
         for i in range(1, len(gens)):
             step = _power_from_cache(mat, squares, gens[i] - gens[i - 1])
             cur = mat.mm(cur, step)
-            drift[i, j] = bin_matrix(mat.get(cur), br)
+            drift[i, j] = binned(cur)
         if progress:
             progress("drift u=%g done" % u)
     kw = {}
@@ -181,7 +217,7 @@ def generate_tables(N: int = 1000, breaks=(0.5, 0.01), gens: Sequence[int] = DEF
         bot = np.empty((len(nbs), len(bot_us), F, F))
         for j, u in enumerate(bot_us):
             for i, Nb in enumerate(nbs):
-                bot[i, j] = bin_matrix(bottleneck_matrix(N, int(Nb), u, mat), br)
+                bot[i, j] = binned(bottleneck_matrix(N, int(Nb), u, mat, on_device=True))
             if progress:
                 progress("bottleneck u=%g done" % u)
         kw = dict(bot=bot, nbs=np.array(nbs, dtype=np.float64), bot_us=np.array(bot_us, dtype=np.float64))
@@ -189,7 +225,7 @@ def generate_tables(N: int = 1000, breaks=(0.5, 0.01), gens: Sequence[int] = DEF
                             freqs=freqs, breaks=br, **kw)
 
 
-def bottleneck_matrix(N: int, Nb: int, mu: float, mat: Optional[_Mat] = None) -> np.ndarray:
+def bottleneck_matrix(N: int, Nb: int, mu: float, mat: Optional[_Mat] = None, on_device: bool = False):
     """Instantaneous bottleneck to Nb followed by doubling back to N (generate_transitions.py:29-54)."""
     if Nb >= N:
         raise ValueError("Nb must be < N")
@@ -204,4 +240,4 @@ def bottleneck_matrix(N: int, Nb: int, mu: float, mat: Optional[_Mat] = None) ->
     P = fac(Ns[0], Ns[1])
     for N1, N2 in zip(Ns[1:-1], Ns[2:]):
         P = mat.mm(P, fac(N1, N2))
-    return mat.get(P)
+    return P if on_device else mat.get(P)
