@@ -3,8 +3,12 @@
 Produces the same tables as the reference's `mope generate-transitions` + `make-master-transitions`:
 Wright-Fisher matrix (mope/generate_transitions.py:57-67), matrix-power chain over the generation list
 (:217-228, :386-414), bottleneck products through the doubling schedule (:29-54, mope/_transition.pyx:6-33),
-symmetric frequency binning (:133-214).  The 1001^3 fp64 matrix products run as plain library GEMMs
-(torch.matmul -> cuBLAS) on the GPU when one is present, NumPy otherwise; everything else is host NumPy.
+symmetric frequency binning (:133-214).  With a GPU everything heavy stays on the device: the binomial rows of the
+Wright-Fisher and bottleneck factors (lgamma log-pmf), the 1001^3 fp64 matrix products (plain library GEMMs,
+torch.matmul -> cuBLAS) and the binning (one GEMM with the bin-membership matrix + a row gather); only the F x F
+tables come back (default 94 x 44 drift grid + 48 x 44 bottleneck grid: ~1.5 minutes, was ~6).  Without a GPU the
+same steps run in NumPy / SciPy.  The two paths agree to ~1e-11 relative (summation order, lgamma vs SciPy's pmf);
+the tables are an input shared by both implementations, so this does not enter the parity of the likelihood.
 Powers of the one-generation matrix are cached by repeated squaring, so a step of d generations costs
 popcount(d)-1 products instead of a fresh matrix_power.
 """
