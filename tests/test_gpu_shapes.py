@@ -94,6 +94,17 @@ def test_family_independent_ascertainment_subtrees_vs_oracle():
     assert (np.abs(ll2 - ll) / np.abs(ll)).max() < 1e-13
 
 
+def test_empty_batch_and_single_locus_vs_oracle():
+    """W = 0 walkers is an empty answer; one locus in one family (R = 3 rows, one ragged tile) matches the oracle."""
+    from mope_b200 import synth
+    ds = synth.make_dataset(1, 2, tree="(t0:a,t1:b*child_age)root;", seed=12)
+    I, X, ll = _check_vs_oracle(ds, _tables_small(), 3, shrink=0.25)
+    assert I.num_loci[0] <= 1
+    empty = I.loglike_batch(np.zeros((0, I.ndim)))
+    assert empty.shape == (0,)
+    I.close()
+
+
 def test_leaf_minimum_and_unary_chain_trees_vs_oracle():
     from mope_b200 import synth
     for tree in ("(t0:a,t1:b)root;", "((((t0:a)n1:b)n2:c*child_age)n3:d^,t1:a)root;", "(t0:a,t1:a,t2:b,t3:c*mother_age)root;",
