@@ -8,11 +8,13 @@
 //     go through warp-private TENSOR MEMORY columns (tcgen05.st / tcgen05.ld, thread i <-> TMEM lane i) -- no global
 //     round trip, no proxy fence, no CTA-wide synchronisation;
 //   * only the message of a non-last child is parked (fragment layout) and multiplied in when the last sibling
-//     arrives: the busiest slot of the schedule lives in tensor memory too, the others in an L2-resident scratch
-//     (coalesced 16-byte accesses by the thread that later reads them back);
+//     arrives: the busiest slots of the schedule live in tensor memory too (as many as fit the warp's 256 columns),
+//     the others in an L2-resident scratch (coalesced 16-byte accesses by the thread that later reads them back);
 //   * the only shared resource is the TMA ring with the P chunks (and emission chunks for leaf branches); since no
-//     copy depends on an epilogue any more, one lane streams the whole item PF chunks ahead without ever stalling
-//     on a dependency.
+//     copy depends on an epilogue, lane 0 of warp k streams chunks k, k+8, ... of the item PF chunks ahead without
+//     ever stalling on a dependency;
+//   * items (walker, 64-row tile) are drawn from an atomic counter; tiles that hold only ascertainment pseudo-rows
+//     take the messages of leaf branches and of family-independent subtrees from precomputed vectors (ASCFAST).
 // K layout: the transition matrices and the emission tensor are stored with their k (column) index permuted inside
 // every 16-wide chunk, kperm() below, so that the chained k sets land on the bank-conflict-free fragment positions
 // {2q, 2q+1, 2q+8, 2q+9} of the 128-byte swizzled chunk.
@@ -49,10 +51,10 @@ struct Op4 {
 
 struct Tree4Params {
     CUtensorMap tmapE;      // emissions [n_leaves*R_pad][Fp] (k-permuted columns), box 16 x 64
-    CUtensorMap tmapP;      // matrix pool [n_blocks*(Fp+1)][Fp] (k-permuted columns), box 16 x 8*NTT
+    CUtensorMap tmapP;      // matrix pool [n_blocks*(Fp+BLK_EXTRA)][Fp] (k-permuted columns), box 16 x 8*NTT
     const double* E;
     int64_t E_leaf_stride;
-    double* scratch;        // [gridDim.x][8 warps][n_slots + 1][NTT][32][2]; the last slot of a warp is its chain buffer
+    double* scratch;        // [gridDim.x][8 warps][n_slots + 1][NTT][32][2]: parked slots without a tensor-memory home
     const Op4* ops;
     int32_t n_ops, n_slots;
     int32_t R, L, R_pad, Fp, F, NT, n_tiles, W, tile_block;
@@ -68,7 +70,7 @@ struct Tree4Params {
     double* tile_ll;
     double* asc_dot;
     double* Yout;
-    int32_t debug;           // measurement only, bit flags: 1 skip the MMAs, 2 skip the copies and ring barriers
+    int32_t debug;           // unused by tree_kernel4 (ablations are compile-time: -DMOPE_ABL); kept for the wide-grid kernel's launcher
     int32_t slot_home[MAX_SLOTS4];   // where a parked slot lives: k >= 0 the k-th tensor-memory slot of the warp,
                                      // SLOT_HOME_L2 the L2 scratch
     // Messages of ascertainment pseudo-rows that do not depend on the family (no age-scaled branch at or below the branch)
@@ -268,8 +270,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
     // k steps of the last chunk that hold at least one real column (natural k = 16c + 8(q>>1) + (q&1) + 2kk)
     int nq_last = 0;
     for (int q = 0; q < 4; ++q) nq_last += (16 * (nchunks - 1) + 8 * (q >> 1) + (q & 1) < p.F) ? 1 : 0;
-    const bool no_mma = p.debug & 1, no_copy = p.debug & 2;
+#ifdef MOPE_ABL   // compile-time ablations for kernel tuning (results are garbage): 1 skip the MMAs, 2 skip the copies and
+                  // ring barriers, 8 skip the shared-memory B loads
+    constexpr bool no_mma = MOPE_ABL & 1, no_copy = MOPE_ABL & 2;
+#else
+    constexpr bool no_mma = false, no_copy = false;
+#endif
+#ifdef MOPE_ABL
+    constexpr bool no_lds = MOPE_ABL & 8;
+#else
     constexpr bool no_lds = false;
+#endif
 
     unsigned g = 0;   // chunks consumed so far (ring position)
     PROF_DECL
