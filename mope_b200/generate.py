@@ -4,7 +4,7 @@ Produces the same tables as the reference's `mope generate-transitions` + `make-
 Wright-Fisher matrix (mope/generate_transitions.py:57-67), matrix-power chain over the generation list
 (:217-228, :386-414), bottleneck products through the doubling schedule (:29-54, mope/_transition.pyx:6-33),
 symmetric frequency binning (:133-214).  With a GPU everything heavy stays on the device: the binomial rows of the
-Wright-Fisher and bottleneck factors (lgamma log-pmf), the 1001^3 fp64 matrix products (plain library GEMMs,
+Wright-Fisher and bottleneck factors (log-pmf from host-computed log binomial coefficients), the 1001^3 fp64 matrix products (plain library GEMMs,
 torch.matmul -> cuBLAS) and the binning (one GEMM with the bin-membership matrix + a row gather); only the F x F
 tables come back (default 94 x 44 drift grid + 48 x 44 bottleneck grid: ~1.5 minutes, was ~6).  Without a GPU the
 same steps run in NumPy / SciPy.  The two paths agree to ~1e-11 relative (summation order, lgamma vs SciPy's pmf);
@@ -18,6 +18,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 import scipy.stats as st
+from scipy.special import gammaln
 
 from .tables import TransitionTables
 
@@ -137,8 +138,18 @@ class _Mat:
         t = self.torch
         ps = t.as_tensor(pstar, dtype=t.float64, device=self.device)
         k = t.arange(N + 1, dtype=t.float64, device=self.device)
-        lc = t.lgamma(t.tensor(N + 1.0, dtype=t.float64, device=self.device)) - t.lgamma(k + 1) - t.lgamma(N - k + 1)
+        lc = self._log_binom(N)
         return t.exp(lc[None, :] + k[None, :] * t.log(ps)[:, None] + (N - k)[None, :] * t.log1p(-ps)[:, None])
+
+    def _log_binom(self, n: int):
+        """log C(n, k), k = 0..n, from SciPy's gammaln on the host (n + 1 values; keeps torch's JIT-compiled lgamma out of
+        the device path)."""
+        cache = self.__dict__.setdefault("_lc_cache", {})
+        if n not in cache:
+            k = np.arange(n + 1, dtype=np.float64)
+            cache[n] = self.torch.as_tensor(gammaln(n + 1.0) - gammaln(k + 1.0) - gammaln(n - k + 1.0), dtype=self.torch.float64,
+                                            device=self.device)
+        return cache[n]
 
     def binner(self, n_states: int, breaks: np.ndarray):
         """bin_matrix for device matrices: column sums per bin as one GEMM with the 0/1 membership matrix, then the middle
@@ -169,7 +180,7 @@ class _Mat:
         f = t.arange(N1 + 1, dtype=t.float64, device=self.device) / N1
         f = (1 - mu) * f + (1 - f) * mu                       # strictly inside (0, 1) for 0 < mu < 1
         k = t.arange(N2 + 1, dtype=t.float64, device=self.device)
-        lc = t.lgamma(t.tensor(N2 + 1.0, dtype=t.float64, device=self.device)) - t.lgamma(k + 1) - t.lgamma(N2 - k + 1)
+        lc = self._log_binom(N2)
         logpmf = lc[None, :] + k[None, :] * t.log(f)[:, None] + (N2 - k)[None, :] * t.log1p(-f)[:, None]
         P = t.zeros((N0 + 1, N0 + 1), dtype=t.float64, device=self.device)
         P[: N1 + 1, : N2 + 1] = t.exp(logpmf)
