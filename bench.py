@@ -46,6 +46,10 @@ def parse_args():
     ap.add_argument("--tree", default="fixed", choices=["fixed", "rates", "bottleneck"],
                     help="fixed: cfg2 (default); rates: cfg3 (age-scaled leaf branches + one age-scaled internal); "
                          "bottleneck: cfg4 (one ^ branch + age-scaled internal)")
+    ap.add_argument("--shard", default="walker", choices=["walker", "locus"],
+                    help="N > 1 only.  walker (default, the bench contract): every GPU owns its own --walkers walkers, weak scaling; "
+                         "locus: the families are partitioned over the GPUs, every GPU evaluates all --walkers walkers on its rows "
+                         "and the per-walker partial sums are combined by ONE NCCL all-reduce (strong scaling; BASELINE config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-walkers", type=int, default=0, help="walkers per step of the CPU sample (default: host cores)")
     return ap.parse_args()
@@ -451,10 +455,86 @@ def run_ours(args):
     inf.close()
 
 
+def run_ours_locus(args):
+    """Locus-sharded evaluation over the ranks (mope_b200.dist): not the default bench line, a measured demonstration of
+    the path's only collective.  value = walkers x ALL loci / step time (strong scaling in the rows)."""
+    import torch
+    import torch.distributed as dist
+    from mope_b200 import Inference, synth
+    from mope_b200 import dist as mdist
+
+    rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    tb = make_tables(args, "cuda:%d" % local_rank)
+    ds = make_workload(args)
+    inf = mdist.build_locus_sharded([ds.data_tsv], [ds.tree], [ds.ages_tsv], tb, rank, world, log_unif_drift=True, device=local_rank)
+    W = args.walkers
+    X = synth.walkers_in_prior_box(inf.lower, inf.upper, W, seed=1)     # the same ensemble on every rank
+    Lt = torch.tensor([inf.num_loci[0]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(Lt)
+    L_total = int(Lt.item())
+    dev = "cuda:%d" % local_rank
+    stat_dev = torch.as_tensor(inf.stationary_distributions(X), device=dev)
+    out_dev = torch.empty(W, dtype=torch.float64, device=dev)
+
+    def step():
+        inf.engine.loglike_device(X, stat_dev, out_dev)
+        dist.all_reduce(out_dev, op=dist.ReduceOp.SUM)     # the path's only collective: W float64 partial sums
+
+    for _ in range(args.warmup):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ll_dev = out_dev.cpu().numpy()
+    # end to end through the public API (host vectors in, host log-likelihoods out, all-reduce inside)
+    mdist.loglike_locus_sharded(inf, X)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ll_host, st = mdist.loglike_locus_sharded(inf, X)
+    torch.cuda.synchronize()
+    te = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    parity = None
+    if rank == 0:
+        # the sharded sum against the whole dataset on one GPU
+        full = Inference([ds.data_tsv], [ds.tree], [ds.ages_tsv], tb, log_unif_drift=True, device=local_rank, _inputs_are_text=True)
+        ref = full.loglike_batch(X[:32], raise_on_error=False)
+        full.close()
+        fin = np.isfinite(ref) & np.isfinite(ll_host[:32])
+        parity = float((np.abs(ll_host[:32][fin] - ref[fin]) / np.abs(ref[fin])).max())
+        assert parity < 1e-11, parity
+        line = {"metric": METRIC, "value": W * L_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args, tb.F), "walkers_total": W, "loci_total": L_total,
+                           "parallelism": "locus-sharded x%d (families partitioned; one NCCL all-reduce of %d doubles per evaluation)" % (world, W),
+                           "finite_walkers": int(np.isfinite(ll_dev).sum())},
+                "e2e": {"value": W * L_total / float(te.item()), "unit": UNIT, "ms_per_step": float(te.item()) * 1e3},
+                "parity_max_rel_err_vs_single_gpu": parity, "clocks": clocks.summary()}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    inf.close()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.shard == "locus" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        run_ours_locus(args)
     else:
         run_ours(args)
 
