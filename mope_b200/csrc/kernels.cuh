@@ -278,7 +278,7 @@ __global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* t
 constexpr int NS = 5;   // ring stages
 constexpr int PF = 3;   // prefetch distance in chunks
 
-constexpr int MAX_OPS = 96;  // branch ops staged in shared memory (trees with more branches are rejected at create)
+constexpr int MAX_OPS = 192;  // branch ops staged in shared memory (trees with more branches are rejected at create)
 
 struct TreeSmem {
     unsigned long long full[NS], empty[NS], epi;
@@ -299,6 +299,7 @@ struct TileCfg {
     static constexpr int P_BYTES = PROWS * KC * 8;
     static constexpr int STAGE_BYTES = 2 * V_BYTES + P_BYTES;    // V0 | V1 | P, each 1024-aligned
     static constexpr size_t SMEM_BYTES = (size_t)NS * STAGE_BYTES + sizeof(TreeSmem) + 1024 /*alignment slack*/;
+    static_assert(SMEM_BYTES <= 227 * 1024, "ring + tables exceed the 227 KB of shared memory a CTA can have");
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

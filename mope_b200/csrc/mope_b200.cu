@@ -233,6 +233,27 @@ int validate(const mope_tables_desc* t, const mope_model_desc* m) {
         return fail(MOPE_E_INVALID, "drift tables need F>=2 and a grid of at least 2x2");
     if (t->bot && (t->n_nbs < 2 || t->n_bot_us < 2 || !t->nbs || !t->bot_us))
         return fail(MOPE_E_INVALID, "bottleneck tables need a grid of at least 2x2");
+    // The clamp of _util.check_transition_matrix (mope/_util.pyx:140-143) is a no-op on blends of entries in [0,1]; the
+    // factored age-scaled branches rely on that, so the drift tables are checked here, whoever the caller is.
+    {
+        const size_t n = (size_t)t->n_gens * t->n_us * t->F * t->F;
+        const unsigned nth = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)std::thread::hardware_concurrency(), n >> 22}));
+        std::vector<double> mn(nth, 0.0), mx(nth, 0.0);
+        std::vector<char> bad(nth, 0);
+        auto scan = [&](unsigned k) {
+            const size_t lo = n * k / nth, hi = n * (k + 1) / nth;
+            double a = 0.0, b = 0.0;
+            bool nan = false;
+            for (size_t i = lo; i < hi; ++i) { const double v = t->drift[i]; a = v < a ? v : a; b = v > b ? v : b; nan |= (v != v); }
+            mn[k] = a; mx[k] = b; bad[k] = nan;
+        };
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < nth; ++k) th.emplace_back(scan, k);
+        scan(0);
+        for (auto& x : th) x.join();
+        for (unsigned k = 0; k < nth; ++k)
+            if (mn[k] < 0.0 || mx[k] > 1.0 || bad[k]) return fail(MOPE_E_INVALID, "drift tables hold entries outside [0, 1]");
+    }
     for (int i = 1; i < t->n_gens; ++i) if (!(t->gens[i] > t->gens[i - 1])) return fail(MOPE_E_INVALID, "gens not ascending");
     for (int i = 1; i < t->n_us; ++i) if (!(t->us[i] > t->us[i - 1])) return fail(MOPE_E_INVALID, "us not ascending");
     if (m->n_var < 1 || m->n_ped < 1 || !m->peds) return fail(MOPE_E_INVALID, "model needs >=1 variable and >=1 pedigree");
@@ -251,6 +272,18 @@ int validate(const mope_tables_desc* t, const mope_model_desc* m) {
         }
         for (int f = 0; f < p.n_fam; ++f)
             if (p.fam_asc[f] < 0 || p.fam_asc[f] >= p.n_asc) return fail(MOPE_E_INVALID, "pedigree %d: bad fam_asc", k);
+        // a multiplier (age) that is NA on a row an age-scaled branch uses: the reference raises
+        // ValueError('scaled_time is not finite') at the first evaluation (transition_data_2d.py:135-136)
+        for (int b = 0; b < p.n_branches; ++b) {
+            const int mc = p.br_mult[b];
+            if (mc < 0) continue;
+            for (int r = 0; r < p.n_loci; ++r)
+                if (!std::isfinite(p.row_mult[(size_t)mc * p.n_loci + r]))
+                    return fail(MOPE_E_INVALID, "pedigree %d: multiplier column %d is not finite on locus row %d (scaled_time is not finite)", k, mc, r);
+            for (int u = 0; u < p.n_asc; ++u)
+                if (!std::isfinite(p.asc_mult[(size_t)mc * p.n_asc + u]))
+                    return fail(MOPE_E_INVALID, "pedigree %d: multiplier column %d is not finite for family group %d (scaled_time is not finite)", k, mc, u);
+        }
     }
     return 0;
 }

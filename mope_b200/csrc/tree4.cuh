@@ -110,6 +110,7 @@ struct Cfg4 {
     static constexpr int MSG_COLS = NTT * 4;
     static constexpr int TM_SLOTS = 256 / MSG_COLS - 1;
     static constexpr size_t SMEM_BYTES = (size_t)NS * STAGE_BYTES + sizeof(Tree4Smem) + 1024;
+    static_assert(SMEM_BYTES <= 227 * 1024, "ring + tables exceed the 227 KB of shared memory a CTA can have");
 };
 
 // per-row time weights of an age-scaled branch (transition_data_2d.py:183-224)

@@ -53,6 +53,10 @@ def shard_pedigree_text(data_tsv: str, ages_tsv: str, world: int, rank: int) -> 
     data = _model.read_table(data_tsv, True)
     ages = _model.read_table(ages_tsv, True)
     groups = partition_families(data["family"].values, ages["family"].values, world)
+    if any(len(g) == 0 for g in groups):
+        # every rank computes the same partition, so every rank raises here -- before any collective could hang
+        raise ValueError("cannot shard {} families over {} ranks: some rank would own no family".format(
+            len(ages["family"].values), world))
     mine = set(groups[rank].tolist())
     d = data[data["family"].isin(mine)]
     a = ages[ages["family"].isin(mine)]

@@ -380,8 +380,14 @@ class GpuPool(object):
         xs = [np.asarray(x, dtype=np.float64) for x in iterable]
         if not xs:
             return []
-        name = getattr(func, "__name__", None)
-        mod = getattr(func, "__module__", "")
+        # emcee never hands over the bare function: EnsembleSampler wraps it in emcee.ensemble._function_wrapper (2.x) /
+        # _FunctionWrapper (3.x), an object with .f, .args, .kwargs whose __call__ is f(x, *args, **kwargs)
+        inner = func
+        if not hasattr(func, "__name__") and callable(getattr(func, "f", None)) \
+                and not getattr(func, "args", None) and not getattr(func, "kwargs", None):
+            inner = func.f
+        name = getattr(inner, "__name__", None)
+        mod = getattr(inner, "__module__", "") or ""
         if mod.endswith("inference") and name in ("post_clone", "logl", "logp"):
             X = np.stack(xs)
             if name == "post_clone":

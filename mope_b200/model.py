@@ -137,7 +137,7 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
                 keys[k] = len(uniq)
                 uniq.append(fam_mult[:, i])
             fam_asc_l.append(keys[k])
-        asc_mult = np.ascontiguousarray(np.array(uniq).T)
+        asc_mult = np.ascontiguousarray(np.array(uniq).T) if uniq else np.zeros((M, 0))
         fam_asc = np.array(fam_asc_l, dtype=np.int32)
 
     if M > 0 and sort_rows and len(fam_ids) > 1:

@@ -15,12 +15,29 @@ import os
 import numpy as np
 from scipy.special import betainc, cython_special
 
-_MAX_THREADS = int(os.environ.get("MOPE_B200_HOST_THREADS", "0")) or max(1, min(16, (os.cpu_count() or 1)))
+
+
+def _default_threads() -> int:
+    """Native threads of the root-prior table: the host cores divided by the ranks sharing the box (torchrun exports
+    LOCAL_WORLD_SIZE), at most 16 -- eight ranks spinning 16 threads each on a 32-core host slowed every rank down."""
+    env = int(os.environ.get("MOPE_B200_HOST_THREADS", "0"))
+    if env > 0:
+        return env
+    cores = os.cpu_count() or 1
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, min(16, cores // local_world))
+
+
+_MAX_THREADS = _default_threads()
 
 
 def _betainc_entry():
-    """Address of SciPy's own double-precision betainc (the function behind the ufunc and scipy.stats.beta.cdf)."""
-    cap = cython_special.__pyx_capi__["__pyx_fuse_0betainc"]
+    """Address of SciPy's own double-precision betainc (the function behind the ufunc and scipy.stats.beta.cdf).
+    The capsule name is private to SciPy (checked with 1.18); None when it is missing or has another signature --
+    beta_cdf_table then evaluates the ufunc itself (same values bit for bit, single-threaded)."""
+    cap = getattr(cython_special, "__pyx_capi__", {}).get("__pyx_fuse_0betainc")
+    if cap is None:
+        return None
     api = ctypes.pythonapi
     api.PyCapsule_GetName.restype = ctypes.c_char_p
     api.PyCapsule_GetName.argtypes = [ctypes.py_object]
@@ -28,11 +45,11 @@ def _betainc_entry():
     api.PyCapsule_GetPointer.argtypes = [ctypes.py_object, ctypes.c_char_p]
     name = api.PyCapsule_GetName(cap)
     if name is None or b"double (double, double, double" not in name:
-        raise RuntimeError("unexpected signature of scipy.special.cython_special betainc: %r" % (name,))
+        return None
     return api.PyCapsule_GetPointer(cap, name)
 
 
-_ENTRY = None
+_ENTRY = False   # not looked up yet
 
 
 def beta_cdf_table(ab: np.ndarray, edges: np.ndarray, n_threads: int = _MAX_THREADS) -> np.ndarray:
@@ -40,10 +57,12 @@ def beta_cdf_table(ab: np.ndarray, edges: np.ndarray, n_threads: int = _MAX_THRE
     library through SciPy's own C entry point (mope_b200_beta_cdf_table): no interpreter lock, no Python thread pool."""
     global _ENTRY
     from . import _lib
-    if _ENTRY is None:
+    if _ENTRY is False:
         _ENTRY = _betainc_entry()
     ab = np.ascontiguousarray(ab, dtype=np.float64)
     edges = np.ascontiguousarray(edges, dtype=np.float64)
+    if _ENTRY is None:
+        return betainc(ab[:, None], ab[:, None], edges[None, :])
     out = np.empty((ab.shape[0], edges.shape[0]))
     _lib.check(_lib.lib().mope_b200_beta_cdf_table(_ENTRY, _lib.dptr(ab), ab.shape[0], _lib.dptr(edges), edges.shape[0],
                                                    _lib.dptr(out), int(n_threads)), "mope_b200_beta_cdf_table")

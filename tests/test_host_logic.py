@@ -141,3 +141,115 @@ def test_engine_fails_loudly_without_cuda():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Inference([case["peds"][0]["data"]], [case["peds"][0]["tree"]], [case["peds"][0]["ages"]], tb,
                   log_unif_drift=True, _inputs_are_text=True)
+
+
+class _FakeInf:
+    """Counts the batched entry points GpuPool.map must use (no device involved)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def log_posterior_batch(self, X):
+        self.calls.append(("post", X.shape))
+        return np.arange(X.shape[0], dtype=np.float64)
+
+    def loglike_batch(self, X):
+        self.calls.append(("ll", X.shape))
+        return np.arange(X.shape[0], dtype=np.float64) + 100
+
+    def logprior(self, x):
+        self.calls.append(("prior", x.shape))
+        return -1.0
+
+
+class _EmceeStyleWrapper:
+    """What emcee hands to pool.map: emcee.ensemble._function_wrapper (2.x) / _FunctionWrapper (3.x) -- an object without
+    __name__ that calls f(x, *args, **kwargs)."""
+
+    def __init__(self, f, args=(), kwargs=None):
+        self.f, self.args, self.kwargs = f, list(args), dict(kwargs or {})
+
+    def __call__(self, x):
+        return self.f(x, *self.args, **self.kwargs)
+
+
+def test_gpu_pool_batches_through_emcee_style_wrappers():
+    from mope_b200 import inference as inf_mod
+    fake = _FakeInf()
+    pool = inf_mod.GpuPool(fake)
+    xs = [np.full(4, float(i)) for i in range(6)]
+    # bare trampoline and emcee-wrapped trampoline: ONE batched call each, never the serial fallback
+    assert pool.map(inf_mod.post_clone, xs) == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
+    assert pool.map(_EmceeStyleWrapper(inf_mod.post_clone), xs) == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
+    assert pool.map(_EmceeStyleWrapper(inf_mod.logl), xs)[0] == 100.0
+    assert fake.calls == [("post", (6, 4)), ("post", (6, 4)), ("ll", (6, 4))]
+    # the reference's own module-level trampolines (module name mope.inference) are recognised too
+    ref_like = type(inf_mod.post_clone)(inf_mod.post_clone.__code__, {"__name__": "mope.inference"}, "post_clone")
+    ref_like.__module__ = "mope.inference"
+    assert pool.map(_EmceeStyleWrapper(ref_like), xs[:2]) == [0.0, 1.0]
+    assert fake.calls[-1] == ("post", (2, 4))
+    # a wrapper that carries extra arguments, or any other function, is mapped serially
+    fake.calls.clear()
+    assert pool.map(_EmceeStyleWrapper(lambda x, k: k * x[0], args=(2.0,)), xs[:3]) == [0.0, 2.0, 4.0]
+    assert pool.map(lambda x: x.sum(), xs[:2]) == [0.0, 4.0]
+    assert fake.calls == []
+    assert pool.map(inf_mod.post_clone, []) == []
+
+
+def test_beta_cdf_table_falls_back_to_the_ufunc(monkeypatch):
+    """Without SciPy's private capsule the table comes from scipy.special.betainc itself: same values bit for bit."""
+    ab = 10 ** np.random.RandomState(4).uniform(-9, 0, 9)
+    edges = np.arange(1, 2 * 998, 2) / (2 * 998)
+    want = stationary.beta_cdf_table(ab, edges)
+    monkeypatch.setattr(stationary, "_ENTRY", None)
+    np.testing.assert_array_equal(stationary.beta_cdf_table(ab, edges), want)
+
+
+def _descs(drift, ped_kw=None):
+    """Minimal C-ABI descriptions (one 2-leaf pedigree) for the host-only validation entry point."""
+    import ctypes as C
+    F = drift.shape[-1]
+    keep = dict(drift=np.ascontiguousarray(drift), gens=np.array([1.0, 10.0]), us=np.array([1e-8, 1e-6]),
+                freqs=np.linspace(0, 1, F), counts=np.array([[1.0, 2.0]]), coverage=np.array([[10.0, 10.0]]),
+                row_mult=np.array([[30.0]]), asc_mult=np.array([[30.0]]), fam_count=np.array([1.0]), fam_lgamma=np.array([0.0]),
+                fam_asc=np.array([0], dtype=np.int32), br_parent=np.array([2, 2], dtype=np.int32),
+                br_leaf=np.array([0, 1], dtype=np.int32), br_var=np.array([0, 0], dtype=np.int32),
+                br_mult=np.array([0, -1], dtype=np.int32), br_bottleneck=np.array([0, 0], dtype=np.int32))
+    keep.update(ped_kw or {})
+    td = _lib.TablesDesc()
+    td.F, td.n_gens, td.n_us = F, 2, 2
+    td.drift, td.gens, td.us, td.freqs = (_lib.dptr(keep[k]) for k in ("drift", "gens", "us", "freqs"))
+    td.n_nbs = td.n_bot_us = 0
+    td.N = 100.0
+    pd_ = (_lib.PedigreeDesc * 1)()
+    d = pd_[0]
+    d.n_leaves, d.n_branches, d.n_loci, d.n_fam, d.n_mult, d.n_asc = 2, 2, 1, 1, 1, 1
+    for k in ("counts", "coverage", "row_mult", "asc_mult", "fam_count", "fam_lgamma"):
+        setattr(d, k, _lib.dptr(keep[k]))
+    for k in ("fam_asc", "br_parent", "br_leaf", "br_var", "br_mult", "br_bottleneck"):
+        setattr(d, k, _lib.iptr(keep[k]))
+    md = _lib.ModelDesc()
+    md.n_var, md.n_ped, md.peds = 1, 1, pd_
+    md.min_phred_score, md.min_freq, md.genome_size, md.poisson_like_penalty = -1.0, 0.001, 16569.0, 1.0
+    return td, md, (keep, pd_)
+
+
+def test_c_abi_validates_tables_and_multipliers():
+    """The [0,1] range of the drift tables and finite multipliers are enforced at the C ABI (mope_b200_arena_bytes runs
+    the same validation as mope_b200_create and needs no device)."""
+    import ctypes as C
+    L = _lib.lib()
+    F = 4
+    good = np.full((2, 2, F, F), 0.25)
+    n = C.c_size_t(0)
+    td, md, keep = _descs(good)
+    assert L.mope_b200_arena_bytes(C.byref(td), C.byref(md), C.byref(n)) == 0 and n.value > 0
+    for bad_value in (1.0 + 1e-12, -1e-300, np.nan):
+        bad = good.copy()
+        bad[1, 0, 2, 3] = bad_value
+        td, md, keep = _descs(bad)
+        assert L.mope_b200_arena_bytes(C.byref(td), C.byref(md), C.byref(n)) == -1
+        assert b"outside [0, 1]" in L.mope_b200_last_error()
+    td, md, keep = _descs(good, dict(row_mult=np.array([[np.nan]])))
+    assert L.mope_b200_arena_bytes(C.byref(td), C.byref(md), C.byref(n)) == -1
+    assert b"not finite" in L.mope_b200_last_error()
