@@ -145,6 +145,12 @@ int mope_b200_eval_device(mope_ctx* ctx, const double* params_host, const double
 /* Number of kernels this library launched since the context was created. */
 int64_t mope_b200_launch_count(const mope_ctx* ctx);
 
+/* Host-only query (no device): where the pruning kernel keeps the parked messages of pedigree `ped` at grid size F.
+ * The pass walks the tree in the reference's postorder (likelihoods.py:352-397); the message of every child but the last
+ * waits ("is parked") until its siblings are done.  out[0..3] = parks per 64-row tile living in the chain buffer, in a
+ * tensor-memory slot, in the L2 scratch, and the number of L2 scratch slots. */
+int mope_b200_schedule_stats(const mope_model_desc* model, int F, int ped, int32_t* out);
+
 /* Branch updates of the last eval, counted per (walker, branch): GEMMs executed, and branches that took the
  * reference's identity short-cut (N*t below the first table generation, transition_data_2d.py:184-187), for which
  * the message is forwarded without a GEMM.  For age-scaled branches every (walker, branch) counts as one GEMM. */

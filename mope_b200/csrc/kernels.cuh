@@ -174,87 +174,150 @@ __global__ void emission_kernel(EmissionParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// interpolation of transition matrices (transition_data_2d.py:195-238, _interp.pyx:30-35,
-// _util.pyx:129-148).  One warp per matrix row; sequential row sum as in the reference.
+// interpolation of transition matrices (transition_data_2d.py:195-238, _interp.pyx:30-35, _util.pyx:129-148).
+// HBM-bound: per matrix 4 (or 2) F x F source matrices are read once and one Fp x Fp block is written once.
 // Output block: Fp x Fp matrix (zero padded) followed by the BLK_EXTRA vectors described at the top of this file.
+//
+// One CTA per (matrix, tile of `rows` consecutive matrix rows).  The rows of a tile are one contiguous run of
+// rows * F doubles in every source matrix, so
+//   phase 1  all threads stream the run of each source with fully coalesced loads (16 independent loads per thread in
+//            flight), blend in the reference's evaluation order, clamp, and park the tile in shared memory;
+//   phase 2  thread r walks row r of the parked tile: the reference's left-to-right row sum (_util.pyx:144-145) is a
+//            dependent chain of F additions that cannot be re-associated, so the tile runs `rows` independent chains side by
+//            side (row stride odd in doubles: no bank conflicts) while the other CTAs of the SM are in their memory phases;
+//   phase 3  one warp per row divides (when the sum exceeds 1), writes the row coalesced in the (optionally k-permuted)
+//            layout, and forms the low / high column sums of the stored row.
 // ------------------------------------------------------------------------------------------------
-__global__ void interp_kernel(const InterpJob* jobs, int n_jobs, const double* tables, double* pool, int F, int Fp, int perm,
-                              const int8_t* asc_mask /* [2][F]: e0 then eN, may be null */) {
-    extern __shared__ double srow[];  // [warps_per_block][Fp]
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    double* row = srow + (size_t)wib * Fp;
-    const int rows_per_job = Fp;
-    const long long gw = (long long)blockIdx.x * wpb + wib;
-    const long long total = (long long)n_jobs * rows_per_job;
-    if (gw >= total) return;
-    const int j = (int)(gw / rows_per_job);
-    const int i = (int)(gw % rows_per_job);
+constexpr int INTERP_THREADS = 256;
+__host__ __device__ __forceinline__ int interp_row_stride(int F) { return F | 1; }   // doubles, odd
+// rows per tile: as many as fit ~51 KB of shared memory (4 CTAs per SM), at most 32
+__host__ __device__ __forceinline__ int interp_rows_per_tile(int F) {
+    int rows = 32;
+    while (rows > 1 && (size_t)rows * interp_row_stride(F) * sizeof(double) > 52 * 1024) rows >>= 1;
+    return rows;
+}
+
+__global__ void __launch_bounds__(INTERP_THREADS, 4)
+interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __restrict__ tables, double* __restrict__ pool, int F, int Fp,
+              int perm, const int8_t* __restrict__ asc_mask /* [2][F]: e0 then eN, may be null */, int rows, int tiles_per_job,
+              unsigned div_magic /* ceil(2^32 / F) */) {
+    extern __shared__ double tile[];          // [rows][FS]
+    __shared__ double s_sum[32];
+    const int FS = interp_row_stride(F);
+    const int j = blockIdx.x / tiles_per_job;
+    const int i0 = (blockIdx.x - j * tiles_per_job) * rows;   // first matrix row of the tile
     const InterpJob jb = jobs[j];
-    double* dst = pool + jb.dst + (size_t)i * Fp;
-    double* dsum = pool + jb.dst + (size_t)Fp * Fp;
-    if (i >= F) {  // zero padding rows
-        for (int f = lane; f < Fp; f += 32) dst[f] = 0.0;
-        if (lane == 0) { dsum[i] = 0.0; dsum[Fp + i] = 0.0; dsum[2 * Fp + i] = 0.0; }
-        return;
-    }
-    if (jb.flags & 2) {  // identity short-cut (transition_data_2d.py:184-187)
-        for (int f = lane; f < Fp; f += 32) dst[perm ? kperm(f) : f] = (f == i) ? 1.0 : 0.0;
-        if (lane == 0) {
-            dsum[i] = 1.0;
-            dsum[Fp + i] = (asc_mask && asc_mask[i]) ? 1.0 : 0.0;
-            dsum[2 * Fp + i] = (asc_mask && asc_mask[F + i]) ? 1.0 : 0.0;
-        }
-        return;
-    }
-    const double* q11 = tables + jb.src[0] + (size_t)i * F;
-    const double* q12 = tables + jb.src[1] + (size_t)i * F;
-    const double* q21 = tables + jb.src[2] + (size_t)i * F;
-    const double* q22 = tables + jb.src[3] + (size_t)i * F;
+    double* dst0 = pool + jb.dst;
+    double* dsum = dst0 + (size_t)Fp * Fp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nreal = min(rows, F - i0);      // real (non-padding) rows of the tile, may be <= 0
+    const bool ident = (jb.flags & 2) != 0;   // identity short-cut (transition_data_2d.py:184-187)
     const bool two = (jb.flags & 4) != 0;
     const bool check = (jb.flags & 1) != 0;
-    for (int f = lane; f < F; f += 32) {
-        double v;
-        if (two) {
-            v = __dadd_rn(__dmul_rn(q11[f], jb.w[0]), __dmul_rn(q12[f], jb.w[1]));
-        } else {
-            // ((q11*w11 + q21*w21) + q12*w12) + q22*w22
-            v = __dadd_rn(__dmul_rn(q11[f], jb.w[0]), __dmul_rn(q21[f], jb.w[2]));
-            v = __dadd_rn(v, __dmul_rn(q12[f], jb.w[1]));
-            v = __dadd_rn(v, __dmul_rn(q22[f], jb.w[3]));
-        }
-        if (check) {
-            if (v > 1.0) v = 1.0;
-            else if (v < 0.0) v = 0.0;
-        }
-        row[f] = v;
-    }
-    __syncwarp();
-    double s = 0.0;
-    for (int f = 0; f < F; ++f) s = __dadd_rn(s, row[f]);  // same left-to-right order as the reference loop
-    const bool div = check && (s > 1.0);
-    for (int f = lane; f < Fp; f += 32) {
-        double v = (f < F) ? row[f] : 0.0;
-        if (div) v = __ddiv_rn(v, s);
-        dst[perm ? kperm(f) : f] = v;
-    }
-    // low / high sums of the stored (normalised) row: lane-strided partial sums, then a fixed-order warp reduction
-    double lo = 0.0, hi = 0.0;
-    if (asc_mask) {
-        for (int f = lane; f < F; f += 32) {
-            const double v = div ? __ddiv_rn(row[f], s) : row[f];
-            if (asc_mask[f]) lo = __dadd_rn(lo, v);
-            if (asc_mask[F + f]) hi = __dadd_rn(hi, v);
-        }
+
+    if (nreal > 0 && !ident) {
+        // ---- phase 1: stream, blend, clamp ----
+        const int n = nreal * F;
+        const size_t off = (size_t)i0 * F;
+        const double* __restrict__ q11 = tables + jb.src[0] + off;
+        const double* __restrict__ q12 = tables + jb.src[1] + off;
+        const double* __restrict__ q21 = tables + jb.src[2] + off;
+        const double* __restrict__ q22 = tables + jb.src[3] + off;
+        const double w11 = jb.w[0], w12 = jb.w[1], w21 = jb.w[2], w22 = jb.w[3];
+        constexpr int U = 4;
+        for (int base = threadIdx.x; base < n; base += U * INTERP_THREADS) {
+            double a[U], b[U], c[U], d[U];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = __dadd_rn(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = __dadd_rn(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            for (int u = 0; u < U; ++u) {
+                const int e = base + u * INTERP_THREADS;
+                if (e < n) {
+                    a[u] = __ldg(q11 + e);
+                    b[u] = __ldg(q12 + e);
+                    if (!two) { c[u] = __ldg(q21 + e); d[u] = __ldg(q22 + e); }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = base + u * INTERP_THREADS;
+                if (e < n) {
+                    double v;
+                    if (two) {
+                        v = __dadd_rn(__dmul_rn(a[u], w11), __dmul_rn(b[u], w12));
+                    } else {
+                        // ((q11*w11 + q21*w21) + q12*w12) + q22*w22
+                        v = __dadd_rn(__dmul_rn(a[u], w11), __dmul_rn(c[u], w21));
+                        v = __dadd_rn(v, __dmul_rn(b[u], w12));
+                        v = __dadd_rn(v, __dmul_rn(d[u], w22));
+                    }
+                    if (check) {
+                        if (v > 1.0) v = 1.0;
+                        else if (v < 0.0) v = 0.0;
+                    }
+                    const int r = (int)__umulhi((unsigned)e, div_magic);   // e / F (exact for e < 2^16)
+                    tile[r * FS + (e - r * F)] = v;
+                }
+            }
         }
+        __syncthreads();
+        // ---- phase 2: the reference's sequential row sums, one chain per thread ----
+        if (threadIdx.x < nreal) {
+            const double* row = tile + threadIdx.x * FS;
+            double s = 0.0;
+#pragma unroll 8
+            for (int f = 0; f < F; ++f) s = __dadd_rn(s, row[f]);
+            s_sum[threadIdx.x] = s;
+        }
+        __syncthreads();
     }
-    if (lane == 0) {
-        dsum[i] = s;
-        dsum[Fp + i] = lo;
-        dsum[2 * Fp + i] = hi;
+
+    // ---- phase 3: one warp per row ----
+    for (int r = warp; r < rows; r += INTERP_THREADS / 32) {
+        const int i = i0 + r;
+        if (i >= Fp) break;
+        double* dst = dst0 + (size_t)i * Fp;
+        if (i >= F) {  // zero padding rows
+            for (int f = lane; f < Fp; f += 32) dst[f] = 0.0;
+            if (lane == 0) { dsum[i] = 0.0; dsum[Fp + i] = 0.0; dsum[2 * Fp + i] = 0.0; }
+            continue;
+        }
+        if (ident) {
+            for (int f = lane; f < Fp; f += 32) dst[perm ? kperm(f) : f] = (f == i) ? 1.0 : 0.0;
+            if (lane == 0) {
+                dsum[i] = 1.0;
+                dsum[Fp + i] = (asc_mask && asc_mask[i]) ? 1.0 : 0.0;
+                dsum[2 * Fp + i] = (asc_mask && asc_mask[F + i]) ? 1.0 : 0.0;
+            }
+            continue;
+        }
+        const double* row = tile + r * FS;
+        const double s = s_sum[r];
+        const bool div = check && (s > 1.0);
+        // low / high sums of the stored (normalised) row: lane-strided partial sums, then a fixed-order warp reduction
+        double lo = 0.0, hi = 0.0;
+        for (int f = lane; f < Fp; f += 32) {
+            double v = 0.0;
+            if (f < F) {
+                v = row[f];
+                if (div) v = __ddiv_rn(v, s);
+                if (asc_mask) {
+                    if (asc_mask[f]) lo = __dadd_rn(lo, v);
+                    if (asc_mask[F + f]) hi = __dadd_rn(hi, v);
+                }
+            }
+            dst[perm ? kperm(f) : f] = v;
+        }
+        if (asc_mask) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = __dadd_rn(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = __dadd_rn(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+        }
+        if (lane == 0) {
+            dsum[i] = s;
+            dsum[Fp + i] = lo;
+            dsum[2 * Fp + i] = hi;
+        }
     }
 }
 

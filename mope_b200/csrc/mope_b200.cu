@@ -75,7 +75,7 @@ struct Pedigree {
     // warp-owned-rows kernel (tree4.cuh): postorder schedule with chained messages
     Op4* ops4 = nullptr;
     std::vector<Op4> ops4_h;
-    std::vector<int> slot_parks4;   // how often each slot is written per item
+    int parks_chain4 = 0, parks_tm4 = 0, parks_l2_4 = 0;   // homes of the parked messages per item (tree4.cuh, HOME_*)
     int n_uroot4 = 0;               // family-independent subtrees of the ascertainment pass (top branches that are not leaves)
     int n_slots4 = 0;
     int asc_offset = 0;
@@ -388,7 +388,7 @@ int compile_schedule(const mope_pedigree_desc& pd, const std::vector<int>& fixed
 // warp's fragments when b runs).  Messages of non-last children are parked in a slot; a node never holds more than
 // one parked product (later siblings fold into it).
 int compile_schedule4(const mope_pedigree_desc& pd, const std::vector<int>& fixed_key_of_branch,
-                      const std::vector<int>& rate_key_of_branch, Pedigree& out) {
+                      const std::vector<int>& rate_key_of_branch, int tm_slots, Pedigree& out) {
     const int nb = pd.n_branches, root = pd.n_branches;
     std::vector<int> nchild(nb + 1, 0), seen(nb + 1, 0), slot(nb + 1, -1);
     for (int b = 0; b < nb; ++b) nchild[pd.br_parent[b]]++;
@@ -445,9 +445,61 @@ int compile_schedule4(const mope_pedigree_desc& pd, const std::vector<int>& fixe
             o.uroot = (o.uni == 2 && o.leaf < 0) ? out.n_uroot4++ : -1;
         }
     }
-    // parks per slot: the busiest slots get the tensor-memory homes (placement happens at launch, tree4.cuh)
-    out.slot_parks4.assign(out.n_slots4, 0);
-    for (const Op4& o : out.ops4_h) if (o.store_slot >= 0) out.slot_parks4[o.store_slot]++;
+    // Homes of the parked products (tree4.cuh, HOME_*).  A park lives from the post-op of the op that opens it (store_first)
+    // to the post-op of the parent's last child (mul_slot).
+    struct Park { int open, close, home; };
+    std::vector<Park> parks;
+    {
+        std::vector<int> open_of_slot(n_slots, -1);
+        for (int b = 0; b < nb; ++b) {
+            const Op4& o = out.ops4_h[b];
+            if (o.store_slot >= 0 && o.store_first) open_of_slot[o.store_slot] = b;
+            if (o.mul_slot >= 0) { parks.push_back({open_of_slot[o.mul_slot], b, HOME_L2}); open_of_slot[o.mul_slot] = -1; }
+        }
+    }
+    std::vector<Park*> rest;
+    for (Park& pk : parks) {
+        // the chain buffer is idle while only leaf branches run (they take their operand from the emission tensor and,
+        // not being a last child before `close`, do not write it either)
+        bool leaves_only = true;
+        for (int b = pk.open + 1; b <= pk.close; ++b) if (out.ops4_h[b].leaf < 0) leaves_only = false;
+        if (leaves_only) pk.home = HOME_CHAIN; else rest.push_back(&pk);
+    }
+    // interval scheduling on tm_slots tensor-memory slots: earliest close first, best fit -- parks the largest possible
+    // number of messages there; what is left goes to the L2 scratch (slots recycled most-recently-freed first)
+    std::sort(rest.begin(), rest.end(), [](const Park* a, const Park* b) { return a->close < b->close; });
+    std::vector<int> tm_busy_until(std::max(tm_slots, 0), -1);
+    std::vector<Park*> l2;
+    for (Park* pk : rest) {
+        int best = -1;
+        for (int k = 0; k < (int)tm_busy_until.size(); ++k)
+            if (tm_busy_until[k] < pk->open && (best < 0 || tm_busy_until[k] > tm_busy_until[best])) best = k;
+        if (best >= 0) { pk->home = best; tm_busy_until[best] = pk->close; } else l2.push_back(pk);
+    }
+    std::sort(l2.begin(), l2.end(), [](const Park* a, const Park* b) { return a->open < b->open; });
+    int n_l2 = 0;
+    {
+        std::vector<int> busy_until;   // per L2 slot
+        for (Park* pk : l2) {
+            int best = -1;
+            for (int k = 0; k < (int)busy_until.size(); ++k)
+                if (busy_until[k] < pk->open && (best < 0 || busy_until[k] > busy_until[best])) best = k;
+            if (best < 0) { busy_until.push_back(-1); best = (int)busy_until.size() - 1; }
+            busy_until[best] = pk->close;
+            pk->home = HOME_L2 - best;
+        }
+        n_l2 = (int)busy_until.size();
+    }
+    out.n_slots4 = std::max(n_l2, 1);
+    out.parks_chain4 = out.parks_tm4 = out.parks_l2_4 = 0;
+    for (const Park& pk : parks) {
+        if (pk.home == HOME_CHAIN) out.parks_chain4++; else if (pk.home >= 0) out.parks_tm4++; else out.parks_l2_4++;
+        for (int b = pk.open; b <= pk.close; ++b) {
+            Op4& o = out.ops4_h[b];
+            // every op that touches this park: the opener and folders (store_slot) and the closer (mul_slot)
+            if ((o.store_slot >= 0 && pd.br_parent[b] == pd.br_parent[pk.open]) || b == pk.close) o.home = pk.home;
+        }
+    }
     return 0;
 }
 
@@ -533,27 +585,27 @@ int launch_tree_t(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) 
     return 0;
 }
 
-// one warp per matrix row; warps per block bounded by the 48 KB default dynamic shared memory (Fp doubles per warp)
+// one CTA per (matrix, tile of rows): see interp_kernel
 int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d_pool, cudaStream_t st, bool perm) {
-    const int Fp = c->Fp;
-    const int wpb = std::max(1, std::min(8, (int)((48 * 1024) / ((size_t)Fp * sizeof(double)))));
-    const long long rows = (long long)n_jobs * Fp;
-    const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-    interp_kernel<<<grid, wpb * 32, (size_t)wpb * Fp * sizeof(double), st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, c->F, Fp, perm ? 1 : 0, c->asc_mask);
+    const int F = c->F, Fp = c->Fp;
+    const int rows = interp_rows_per_tile(F);
+    const int tiles = (Fp + rows - 1) / rows;
+    const size_t smem = (size_t)rows * interp_row_stride(F) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_set = true;
+    }
+    if ((size_t)rows * F >= 65536) return fail(MOPE_E_INVALID, "interp: tile of %d x %d elements exceeds the index range of the fast division", rows, F);
+    const unsigned magic = (unsigned)((0x100000000ull + (unsigned long long)F - 1) / (unsigned long long)F);
+    const unsigned long long grid = (unsigned long long)n_jobs * tiles;
+    if (grid > 0x7fffffffull) return fail(MOPE_E_INVALID, "interp: too many matrices in one launch (%zu)", n_jobs);
+    interp_kernel<<<(unsigned)grid, INTERP_THREADS, smem, st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, F, Fp, perm ? 1 : 0, c->asc_mask,
+                                                                rows, tiles, magic);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return 0;
-}
-
-// homes of the parked-message slots: the busiest ones get the warp's whole tensor-memory slots, the rest the L2 scratch
-void place_slots4(const mope_ctx* c, const std::vector<int>& parks, int32_t (&home)[MAX_SLOTS4]) {
-    for (int i = 0; i < MAX_SLOTS4; ++i) home[i] = SLOT_HOME_L2;
-    const int tm_slots = 256 / (c->ntt * 4) - 1;
-    std::vector<int> order;
-    for (int i = 0; i < (int)parks.size() && i < MAX_SLOTS4; ++i) order.push_back(i);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return parks[a] > parks[b]; });
-    for (int r = 0; r < (int)order.size() && r < tm_slots; ++r)
-        if (parks[order[r]] > 0) home[order[r]] = r;
 }
 
 template <int NTT, int NFULL, bool SCALAR, bool ASCFAST>
@@ -981,7 +1033,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
                 t4.tmapE = P.tmapE; t4.tmapP = tmapP;
                 t4.E = P.E; t4.E_leaf_stride = (int64_t)P.R_pad * Fp;
                 t4.scratch = scratch;
-                t4.ops = P.ops4; t4.n_ops = (int)P.ops4_h.size(); t4.n_slots = c->max_slots4; place_slots4(c, P.slot_parks4, t4.slot_home);
+                t4.ops = P.ops4; t4.n_ops = (int)P.ops4_h.size(); t4.n_slots = c->max_slots4;
                 t4.R = P.R; t4.L = P.L; t4.R_pad = P.R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = P.n_tiles; t4.W = Wc;
                 t4.tile_block = tile_block_default;
                 if (const char* e = getenv("MOPE_TILE_BLOCK")) t4.tile_block = std::max(1, std::min(P.n_tiles, atoi(e)));
@@ -1222,7 +1274,7 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         if (int rc = compile_schedule(pd, fk[k], rk[k], P)) return cleanup_fail(rc);
         c->max_slots = std::max(c->max_slots, P.n_slots);
         if (c->use_v4) {
-            if (int rc = compile_schedule4(pd, fk[k], rk[k], P)) return cleanup_fail(rc);
+            if (int rc = compile_schedule4(pd, fk[k], rk[k], 256 / (c->ntt * 4) - 1, P)) return cleanup_fail(rc);
             c->max_slots4 = std::max(c->max_slots4, P.n_slots4);
         }
         c->max_tiles = std::max(c->max_tiles, P.n_tiles);
@@ -1319,6 +1371,20 @@ int mope_b200_eval_device(mope_ctx* c, const double* params_host, const double* 
 }
 
 int64_t mope_b200_launch_count(const mope_ctx* c) { return c ? c->launches : 0; }
+
+int mope_b200_schedule_stats(const mope_model_desc* m, int F, int ped, int32_t* out) {
+    if (!m || !out || ped < 0 || ped >= m->n_ped || F < 2) return fail(MOPE_E_INVALID, "schedule_stats: bad argument");
+    const int Fp = round_up_i(F, 16), NT = (F + 7) / 8;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (Fp > 208) return 0;   // wide grids use tree_kernel, whose messages all go through its L2 scratch ring
+    const int ntt = NT <= 10 ? 10 : (NT <= 16 ? 16 : 26);
+    const mope_pedigree_desc& pd = m->peds[ped];
+    std::vector<int> fk(pd.n_branches, 0), rk(pd.n_branches, 0);
+    Pedigree P;
+    if (int rc = compile_schedule4(pd, fk, rk, 256 / (ntt * 4) - 1, P)) return rc;
+    out[0] = P.parks_chain4; out[1] = P.parks_tm4; out[2] = P.parks_l2_4; out[3] = P.n_slots4;
+    return 0;
+}
 
 int mope_b200_last_eval_stats(const mope_ctx* c, int64_t* gemm_ops, int64_t* identity_ops) {
     if (!c) return fail(MOPE_E_INVALID, "null ctx");
@@ -1554,14 +1620,14 @@ int mope_b200_branch_update(mope_ctx* c, int kind, const double* child, double* 
     }
     if (c->use_v4) {
         Op4 o4{};
-        o4.leaf = 0; o4.kind = (kind == 1) ? 1 : 0; o4.key = 0; o4.mult = 0; o4.mul_slot = -1; o4.store_slot = -1; o4.store_first = 0; o4.last = 0;
+        o4.leaf = 0; o4.kind = (kind == 1) ? 1 : 0; o4.key = 0; o4.mult = 0; o4.mul_slot = -1; o4.store_slot = -1; o4.store_first = 0; o4.last = 0; o4.home = HOME_L2;
         static_assert(sizeof(Op4) <= sizeof(TreeOp), "the single-op staging buffer is sized for TreeOp");
         CUDA_TRY(cudaMemcpyAsync(P.op, &o4, sizeof(Op4), cudaMemcpyHostToDevice, st));
         Tree4Params t4{};
         if (int rc = make_tmap(&t4.tmapE, P.E, (uint64_t)R_pad, Fp, TM)) return rc;
         if (int rc = make_tmap(&t4.tmapP, P.pool, (uint64_t)std::max<size_t>(n_blocks, 1) * (Fp + BLK_EXTRA), Fp, tree_prows(c))) return rc;
         t4.E = P.E; t4.E_leaf_stride = (int64_t)R_pad * Fp; t4.scratch = P.Y /*unused*/; t4.ops = reinterpret_cast<const Op4*>(P.op);
-        t4.n_ops = 1; t4.n_slots = 1; place_slots4(c, std::vector<int>(), t4.slot_home);
+        t4.n_ops = 1; t4.n_slots = 1;
         t4.R = n_rows; t4.L = n_rows; t4.R_pad = R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = R_pad / TM; t4.W = 1;
         t4.tile_block = t4.n_tiles;
         t4.pool = P.pool; t4.mat_off = P.mo; t4.n_mat = 1; t4.n_rate = 1; t4.rate = P.rate; t4.mult = P.mult; t4.gens = c->gens_dev;

@@ -32,8 +32,15 @@ namespace mope {
 #endif
 
 constexpr int NS4_MAX = 6;   // most ring stages of any configuration (Cfg4<NTT>::NS)
-constexpr int MAX_SLOTS4 = 16;  // parked-message slots with a placement entry (further slots live in the L2 scratch)
-constexpr int SLOT_HOME_L2 = -1;
+// Homes of parked messages (Op4::home), chosen per park when the schedule is compiled (mope_b200.cu, compile_schedule4):
+//   * HOME_CHAIN: the chain buffer itself.  It is only live from the post-op of a node's last child to the GEMM of the
+//     node's own branch, so a park whose whole lifetime is spanned by leaf branches (the first leaf of a cherry, the usual
+//     case) can sit there for free;
+//   * k >= 0: one of the warp's whole tensor-memory slots, handed out by interval scheduling (earliest end first), which
+//     parks as many messages as possible there;
+//   * <= HOME_L2: the L2-resident scratch, for the parks that are left.
+constexpr int HOME_CHAIN = -1;
+constexpr int HOME_L2 = -2;
 
 struct Op4 {
     int32_t leaf;         // >= 0: leaf column, A operand = emission rows (TMA ring); -1: A operand chained from the previous op
@@ -43,6 +50,8 @@ struct Op4 {
     int32_t mul_slot;     // >= 0: this op is the LAST child of its parent: multiply the parked sibling product in
     int32_t store_slot;   // >= 0: not the last child: park the message (store_first) or fold it into the parked one
     int32_t store_first;
+    int32_t home;         // where the parked product of mul_slot / store_slot lives (HOME_*): k >= 0 the k-th tensor-memory slot
+                          // of the warp, HOME_CHAIN the chain buffer, <= HOME_L2 slot (HOME_L2 - home) of the L2 scratch
     int32_t last;         // completes the root: root reduction
     int32_t uni;          // ascertainment pseudo-rows: 0 the message depends on the family (an age-scaled branch at or below it),
                           // 1 inside a subtree whose messages are the same for every family, 2 the top branch of such a subtree
@@ -54,7 +63,7 @@ struct Tree4Params {
     CUtensorMap tmapP;      // matrix pool [n_blocks*(Fp+BLK_EXTRA)][Fp] (k-permuted columns), box 16 x 8*NTT
     const double* E;
     int64_t E_leaf_stride;
-    double* scratch;        // [gridDim.x][8 warps][n_slots + 1][NTT][32][2]: parked slots without a tensor-memory home
+    double* scratch;        // [gridDim.x][8 warps][n_slots + 1][NTT][32][2]: parked messages whose home is the L2 scratch
     const Op4* ops;
     int32_t n_ops, n_slots;
     int32_t R, L, R_pad, Fp, F, NT, n_tiles, W, tile_block;
@@ -71,8 +80,6 @@ struct Tree4Params {
     double* asc_dot;
     double* Yout;
     int32_t debug;           // unused by tree_kernel4 (ablations are compile-time: -DMOPE_ABL); kept for the wide-grid kernel's launcher
-    int32_t slot_home[MAX_SLOTS4];   // where a parked slot lives: k >= 0 the k-th tensor-memory slot of the warp,
-                                     // SLOT_HOME_L2 the L2 scratch
     // Messages of ascertainment pseudo-rows that do not depend on the family (no age-scaled branch at or below the branch)
     // are the same for all even / all odd pseudo-rows of a walker.  A first, one-tile-per-walker launch (canonical = 1)
     // writes them to uni_msg [W][n_uroot][2][Fp] (natural column order); in the main launch a pure pseudo-row tile skips
@@ -225,10 +232,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
     // slots with a tensor-memory home: warp-private tensor-memory columns
     const uint32_t t_chain = ts->tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * TMEM_WARP_COLS);
     static_assert(Cfg::TM_SLOTS >= 1 && NTT % 2 == 0, "chain buffer + one slot must fit the warp's TMEM columns");
-    // acc *= slot, or slot = acc, chunk by chunk (a chunk = two n-tiles = 4 doubles per thread), wherever the slot lives
-    auto slot_mul = [&](double (&acc)[NTT][2], int slot) {
-        const int home = slot < MAX_SLOTS4 ? p.slot_home[slot] : SLOT_HOME_L2;
-        if (home != SLOT_HOME_L2) {
+    // acc *= parked, or parked = acc, chunk by chunk (a chunk = two n-tiles = 4 doubles per thread), wherever the park lives
+    auto slot_mul = [&](double (&acc)[NTT][2], int home) {
+        if (home > HOME_L2) {
             const uint32_t tb = t_chain + (uint32_t)((home + 1) * Cfg::MSG_COLS);
 #pragma unroll
             for (int c = 0; c < NTT / 2; ++c) {
@@ -239,30 +245,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 acc[2 * c + 1][0] *= u2d(r[4], r[5]); acc[2 * c + 1][1] *= u2d(r[6], r[7]);
             }
         } else {
-            const double2* sl = reinterpret_cast<const double2*>(my_scratch + (size_t)slot * NTT * 64) + lane;
+            const double2* sl = reinterpret_cast<const double2*>(my_scratch + (size_t)(HOME_L2 - home) * NTT * 64) + lane;
 #pragma unroll
             for (int n = 0; n < NTT; ++n) { const double2 v = sl[n * 32]; acc[n][0] *= v.x; acc[n][1] *= v.y; }
         }
     };
-    auto slot_store = [&](const double (&acc)[NTT][2], int slot) {
-        const int home = slot < MAX_SLOTS4 ? p.slot_home[slot] : SLOT_HOME_L2;
-        if (home != SLOT_HOME_L2) {
+    auto slot_store = [&](const double (&acc)[NTT][2], int home) {
+        if (home > HOME_L2) {
             const uint32_t tb = t_chain + (uint32_t)((home + 1) * Cfg::MSG_COLS);
 #pragma unroll
             for (int c = 0; c < NTT / 2; ++c)
                 tmem_st4(tb + 8 * c, acc[2 * c][0], acc[2 * c][1], acc[2 * c + 1][0], acc[2 * c + 1][1]);
             tmem_wait_st();
         } else {
-            double2* sl = reinterpret_cast<double2*>(my_scratch + (size_t)slot * NTT * 64) + lane;
+            double2* sl = reinterpret_cast<double2*>(my_scratch + (size_t)(HOME_L2 - home) * NTT * 64) + lane;
 #pragma unroll
             for (int n = 0; n < NTT; ++n) sl[n * 32] = make_double2(acc[n][0], acc[n][1]);
         }
     };
-    // a consumed slot of the L2 scratch is dead: drop its lines from L2 instead of letting them be written back to HBM
-    auto slot_discard = [&](int slot) {
-        const int home = slot < MAX_SLOTS4 ? p.slot_home[slot] : SLOT_HOME_L2;
-        if (home != SLOT_HOME_L2) return;
-        const double* slot_base = my_scratch + (size_t)slot * NTT * 64;
+    // a consumed park of the L2 scratch is dead: drop its lines from L2 instead of letting them be written back to HBM
+    auto slot_discard = [&](int home) {
+        if (home > HOME_L2) return;
+        const double* slot_base = my_scratch + (size_t)(HOME_L2 - home) * NTT * 64;
         __syncwarp();
         for (int line = lane; line < (NTT * 64 * 8) / 128; line += 32)
             asm volatile("discard.global.L2 [%0], 128;\n" ::"l"(slot_base + line * 16) : "memory");
@@ -580,13 +584,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             __syncwarp();   // the tensor-memory instructions below are warp-wide
             if (op.store_slot >= 0) {
                 // not the last child: park the message (or fold it into the siblings parked so far)
-                if (!op.store_first) slot_mul(acc, op.store_slot);
-                slot_store(acc, op.store_slot);
+                if (!op.store_first) slot_mul(acc, op.home);
+                slot_store(acc, op.home);
                 { PROF_MARK(4) continue; }
             }
             if (op.mul_slot >= 0) {
-                slot_mul(acc, op.mul_slot);
-                slot_discard(op.mul_slot);
+                slot_mul(acc, op.home);
+                slot_discard(op.home);
             }
             if (!op.last) {
                 // chain: this product is the operand of the parent's branch, which is the next op

@@ -253,3 +253,49 @@ def test_c_abi_validates_tables_and_multipliers():
     td, md, keep = _descs(good, dict(row_mult=np.array([[np.nan]])))
     assert L.mope_b200_arena_bytes(C.byref(td), C.byref(md), C.byref(n)) == -1
     assert b"not finite" in L.mope_b200_last_error()
+
+
+def _schedule_stats(tree_str, F):
+    """Park homes of the pruning kernel for a tree (host-only query of the C ABI)."""
+    import ctypes as C
+    t = newick.loads(tree_str)[0]
+    nodes = [nd for nd in t.postorder() if nd is not t]
+    idx = {id(nd): i for i, nd in enumerate(nodes)}
+    idx[id(t)] = len(nodes)
+    leaves = [nd for nd in nodes if nd.is_leaf]
+    keep = dict(br_parent=np.array([idx[id(nd.parent)] for nd in nodes], dtype=np.int32),
+                br_leaf=np.array([leaves.index(nd) if nd.is_leaf else -1 for nd in nodes], dtype=np.int32),
+                br_var=np.zeros(len(nodes), dtype=np.int32),
+                br_mult=np.array([0 if nd.multipliername else -1 for nd in nodes], dtype=np.int32),
+                br_bottleneck=np.zeros(len(nodes), dtype=np.int32))
+    pd_ = (_lib.PedigreeDesc * 1)()
+    d = pd_[0]
+    d.n_leaves, d.n_branches, d.n_loci, d.n_fam, d.n_mult, d.n_asc = len(leaves), len(nodes), 0, 1, 1, 1
+    for k, a in keep.items():
+        setattr(d, k, _lib.iptr(a))
+    md = _lib.ModelDesc()
+    md.n_var, md.n_ped, md.peds = 1, 1, pd_
+    out = np.zeros(4, dtype=np.int32)
+    assert _lib.lib().mope_b200_schedule_stats(C.byref(md), F, 0, _lib.iptr(out)) == 0
+    return tuple(int(v) for v in out)
+
+
+def test_park_homes_of_the_pruning_schedule():
+    """Parked messages: a cherry's first leaf waits in the (idle) chain buffer, interval scheduling fills the warp's
+    tensor-memory slots, only the rest goes through the L2 scratch."""
+    from mope_b200 import synth
+    bal16 = synth.balanced_tree(16)
+    # 15 parks per tile: 8 cherries -> chain buffer; F = 201 has one tensor-memory slot: the 4 depth-2 parks (disjoint
+    # lifetimes) share it; 2 depth-1 parks + the root's stay in L2 (2 slots live at once)
+    assert _schedule_stats(bal16, 201) == (8, 4, 3, 2)
+    # F = 115: three tensor-memory slots hold everything else
+    assert _schedule_stats(bal16, 115) == (8, 7, 0, 1)
+    # the reference's example tree (chains of unary nodes below three forks): one park per fork, all in tensor memory at F = 115
+    both = CASES["example_both"]["peds"][0]["tree"]
+    forks = sum(1 for nd in newick.loads(both)[0].postorder() if len(nd.children) >= 2)
+    assert sum(_schedule_stats(both, 201)[:3]) == forks
+    assert _schedule_stats(both, 115)[2] == 0
+    # a star tree folds every later sibling into one park; its lifetime holds only leaf branches
+    assert _schedule_stats("(a:x,b:x,c:x,d:x)r;", 201) == (1, 0, 0, 1)
+    # wide grids use the other kernel
+    assert _schedule_stats(bal16, 1001) == (0, 0, 0, 0)
