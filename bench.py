@@ -1,13 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: walker x locus log-likelihoods per second (BASELINE.json metric).
 
-Workload (configs[1] of BASELINE.json, "cfg2" in SURVEY.md section 8d): synthetic heteroplasmy data, L = 10 000
+Headline workload (configs[1] of BASELINE.json, "cfg2" in SURVEY.md section 8d): synthetic heteroplasmy data, L = 10 000
 loci x S = 16 tissues, balanced 16-leaf tree (30 fixed-length branches, 8 parameter names), F = 201 frequency
 bins (WF N = 1000, --breaks 0.5 0.005), the reference's default 94 x 44 drift grid generated locally, W = 256
 walkers drawn uniformly in the prior box.  A step = one evaluation of Inference.loglike for all W walkers.
 Multi-GPU: walkers are sharded, W = 256 per GPU (weak scaling), no data-path collective.
 
+The same JSON line carries a `configs` array with the other BASELINE.json configurations at their named sizes, each
+with its own ms/step, e2e, roofline (executed and useful flops) and -- on one GPU -- parity against the reference's own
+code on a stated sample:
+    cfg3  100 000 loci, 16 age-scaled leaf branches + 1 age-scaled internal branch, 32 walkers per GPU (walker-sharded)
+    cfg4  1 000 000 loci, one bottleneck (^) branch + ascertainment, 64 walkers; with N > 1 the FAMILIES are partitioned
+          over the ranks and the per-walker partial sums are combined by ONE NCCL all-reduce (strong scaling)
+    cfg5  F = 1001 (five N passes per branch, wide-grid kernel), 1000 loci, 512 walkers per GPU
+
     python bench.py [--gpus N --steps K --warmup W]          our arm (one JSON line on rank 0)
+    python bench.py --configs cfg2                           headline only (quick)
     python bench.py --impl reference [...]                   the reference's own CPU implementation (baseline/_ref
                                                              if installed, else the oracle port), same metric
 """
@@ -30,6 +39,14 @@ sys.path.insert(0, ROOT)
 METRIC = "walker_x_locus_loglikelihoods_per_sec"
 UNIT = "walker*locus/s"
 
+SMALL_GENS = [1, 2, 5, 10, 20, 50, 100, 200, 500, 1000, 2000, 3000]
+SMALL_US = [1e-9, 1e-7, 1e-5, 1e-3]
+# reduced grids of the extra configurations (grid extent does not enter the cost of an evaluation)
+CFG5_GENS = [1, 2, 5, 10, 20, 50, 100, 200, 400, 700, 1000, 1500, 2000, 3000, 5000, 10000]
+CFG5_US = [1e-12, 1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4]
+CFG4_NBS = [2, 5, 10, 20, 50, 100, 200, 350, 500]
+CFG4_BOT_US = [1e-12, 1e-10, 1e-8, 1e-6, 1e-5, 1e-4, 1e-3]
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -37,7 +54,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    # workload overrides (defaults are the BASELINE config)
+    # workload overrides of the headline (defaults are the BASELINE config)
     ap.add_argument("--loci", type=int, default=10000)
     ap.add_argument("--leaves", type=int, default=16)
     ap.add_argument("--walkers", type=int, default=256, help="walkers per GPU")
@@ -47,10 +64,12 @@ def parse_args():
                     help="fixed: cfg2 (default); rates: cfg3 (age-scaled leaf branches + one age-scaled internal); "
                          "bottleneck: cfg4 (one ^ branch + age-scaled internal)")
     ap.add_argument("--shard", default="walker", choices=["walker", "locus"],
-                    help="N > 1 only.  walker (default, the bench contract): every GPU owns its own --walkers walkers, weak scaling; "
-                         "locus: the families are partitioned over the GPUs, every GPU evaluates all --walkers walkers on its rows "
-                         "and the per-walker partial sums are combined by ONE NCCL all-reduce (strong scaling; BASELINE config 4)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+                    help="N > 1 only, headline workload.  walker (default, the bench contract): every GPU owns its own --walkers "
+                         "walkers, weak scaling; locus: the families are partitioned over the GPUs (strong scaling)")
+    ap.add_argument("--configs", default="all",
+                    help="all (default): the headline plus cfg3, cfg4, cfg5 in the `configs` array; or a comma list, e.g. cfg2 "
+                         "(headline only) or cfg2,cfg4.  The extra configurations run only with the default headline workload.")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip every CPU leg (cpu_baseline and the parity samples)")
     ap.add_argument("--cpu-walkers", type=int, default=0, help="walkers per step of the CPU sample (default: host cores)")
     return ap.parse_args()
 
@@ -58,13 +77,14 @@ def parse_args():
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
-def make_tables(args, device=None):
+def make_tables(args, device=None, with_bottleneck=None):
     from mope_b200 import generate
     if args.grid == "default":
         gens, us = generate.DEFAULT_GENS, generate.DEFAULT_MUTS
     else:
-        gens, us = [1, 2, 5, 10, 20, 50, 100, 200, 500, 1000, 2000, 3000], [1e-9, 1e-7, 1e-5, 1e-3]
-    nbs = generate.DEFAULT_BOTS if args.tree == "bottleneck" else None
+        gens, us = SMALL_GENS, SMALL_US
+    want_bot = (args.tree == "bottleneck") if with_bottleneck is None else with_bottleneck
+    nbs = generate.DEFAULT_BOTS if want_bot else None
     return generate.generate_tables(N=1000, breaks=(0.5, args.breaks), gens=gens, us=us, nbs=nbs, device=device)
 
 
@@ -72,14 +92,18 @@ def make_workload(args):
     from mope_b200 import synth
     tree = synth.balanced_tree(args.leaves, rate_leaves=(args.tree == "rates"), rate_internal=(args.tree != "fixed"),
                                bottleneck=(args.tree == "bottleneck"))
-    ds = synth.make_dataset(args.loci, args.leaves, tree=tree)
-    return ds
+    return synth.make_dataset(args.loci, args.leaves, tree=tree)
 
 
 def workload_name(args, F):
     kind = {"fixed": "cfg2", "rates": "cfg3-like", "bottleneck": "cfg4-like"}[args.tree]
     return "%s: synthetic L=%d loci x S=%d tissues, balanced %d-leaf tree (B=%d branches, %s), F=%d, W=%d walkers/GPU" % (
         kind, args.loci, args.leaves, args.leaves, 2 * args.leaves - 2, args.tree, F, args.walkers)
+
+
+def is_default_headline(args):
+    return (args.loci, args.leaves, args.walkers, args.breaks, args.grid, args.tree, args.shard) == \
+        (10000, 16, 256, 0.005, "default", "fixed", "walker")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -168,7 +192,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU reference arm
+# CPU reference arm (test infrastructure: the only code here that touches oracle/ and baseline/_ref)
 # ------------------------------------------------------------------------------------------------
 _REF_INF = None
 
@@ -177,25 +201,52 @@ def _ref_logl(x):
     return _REF_INF.loglike(np.array(x, dtype=np.float64))
 
 
-def _write_shim_h5(path, tb):
-    """Tables in the pickle format of oracle/ref_shims/h5py.py (what the installed reference reads as HDF5)."""
+def _write_shim_h5(path, tb, bottleneck=False):
+    """Tables in the pickle format of oracle/ref_shims/h5py.py (what the installed reference reads as HDF5): one dataset
+    per grid point with the attributes the reference's loaders read (transition_data_2d.py:78-111,
+    transition_data_bottleneck.py:74-96)."""
     import pickle
     datasets = {}
     k = 0
-    for gi, g in enumerate(tb.gens):
-        for ui, u in enumerate(tb.us):
-            datasets["D%d" % k] = (tb.drift[gi, ui], {"N": int(tb.N), "s": 0.0, "u": float(u), "v": float(u), "gen": int(g)})
-            k += 1
+    if bottleneck:
+        for bi, nb in enumerate(tb.nbs):
+            for ui, u in enumerate(tb.bot_us):
+                datasets["D%d" % k] = (tb.bot[bi, ui], {"N": int(tb.N), "Nb": int(nb), "u": float(u)})
+                k += 1
+    else:
+        for gi, g in enumerate(tb.gens):
+            for ui, u in enumerate(tb.us):
+                datasets["D%d" % k] = (tb.drift[gi, ui], {"N": int(tb.N), "s": 0.0, "u": float(u), "v": float(u), "gen": int(g)})
+                k += 1
     blob = {"attrs": {"frequencies": tb.freqs, "breaks": tb.breaks, "N": int(tb.N)}, "datasets": datasets}
     with open(path, "wb") as f:
         pickle.dump(blob, f, protocol=4)
 
 
-def build_cpu_inference(ds, tb, workdir):
+class RefTables:
+    """The shim-HDF5 files of one table set, written once per bench run and shared by the CPU legs that use it."""
+
+    def __init__(self, tb, workdir, tag):
+        self.tb = tb
+        self.drift = os.path.join(workdir, "drift_%s.h5" % tag)
+        self.bot = os.path.join(workdir, "bot_%s.h5" % tag) if tb.bot is not None else None
+        self._written = False
+
+    def ensure(self):
+        if not self._written:
+            _write_shim_h5(self.drift, self.tb)
+            if self.bot:
+                _write_shim_h5(self.bot, self.tb, bottleneck=True)
+            self._written = True
+
+
+def build_cpu_inference(ds, ref_tables, workdir):
     """The reference's own Inference when baseline/_ref is installed (kind 'reference'), else the oracle port."""
     global _REF_INF
     from oracle import install_ref
+    tb = ref_tables.tb
     kind = "port"
+    _REF_INF = None
     if install_ref.activate():
         try:
             import warnings
@@ -206,30 +257,28 @@ def build_cpu_inference(ds, tb, workdir):
                 paths[key] = os.path.join(workdir, key + ".txt")
                 with open(paths[key], "w") as f:
                     f.write(text)
-            h5 = os.path.join(workdir, "drift.h5")
-            _write_shim_h5(h5, tb)
+            ref_tables.ensure()
             _REF_INF = refinf.Inference(data_files=[paths["data"]], tree_files=[paths["tree"]], age_files=[paths["ages"]],
-                                        transitions_file=h5, true_parameters=None, start_from="prior", data_are_freqs=False,
-                                        genome_size=16569, bottleneck_file=None, min_freq=0.001, poisson_like_penalty=1.0,
+                                        transitions_file=ref_tables.drift, true_parameters=None, start_from="prior", data_are_freqs=False,
+                                        genome_size=16569, bottleneck_file=ref_tables.bot, min_freq=0.001, poisson_like_penalty=1.0,
                                         log_unif_drift=True, lower_drift_limit=1e-3, upper_drift_limit=3, min_phred_score=None)
             kind = "reference"
         except Exception as e:  # pragma: no cover
-            print("# reference install unusable (%s); using the oracle port" % (e,), file=sys.stderr)
+            print("# reference install unusable (%r); using the oracle port" % (e,), file=sys.stderr)
             _REF_INF = None
     if _REF_INF is None:
         from oracle import mope_oracle as orc
-        from mope_b200 import model
         drift = orc.TransitionData(tb.drift, tb.gens, tb.us, int(tb.N), tb.freqs, tb.breaks)
-        d = model.read_table(ds.data_tsv, True)
-        a = model.read_table(ds.ages_tsv, True)
-        _REF_INF = orc.Inference([({c: d[c].values for c in d.columns}, ds.tree, {c: a[c].values for c in a.columns})], drift, None,
+        bot = orc.TransitionDataBottleneck(tb.bot, tb.nbs, tb.bot_us, int(tb.N)) if tb.bot is not None else None
+        d, a = ds.data, ds.ages
+        _REF_INF = orc.Inference([({c: d[c].values for c in d.columns}, ds.tree, {c: a[c].values for c in a.columns})], drift, bot,
                                  log_unif_drift=True)
     return kind
 
 
 def cpu_throughput(X, n_loci, cores, steps, warmup):
     """pool.map(logl, X) with a fork pool, as Inference._get_pool does (mope/inference.py:1197-1239); the workers
-    inherit the parent's Inference.  Returns (walker*locus/s, seconds per step)."""
+    inherit the parent's Inference.  Returns (walker*locus/s, seconds per step, values)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     os.environ["OMP_NUM_THREADS"] = "1"
@@ -245,16 +294,32 @@ def cpu_throughput(X, n_loci, cores, steps, warmup):
     return X.shape[0] * n_loci / dt, dt, np.array(vals)
 
 
-def subset_dataset(ds, n_loci):
-    """First n_loci loci (whole families) of a synthetic dataset, same tree."""
-    from mope_b200 import synth
-    lines = ds.data_tsv.splitlines()
-    n_loci = min(n_loci, len(lines) - 1)
-    data = "\n".join(lines[: n_loci + 1]) + "\n"
-    fams = {l.split("\t")[-1] for l in lines[1: n_loci + 1]}
-    alines = ds.ages_tsv.splitlines()
-    ages = "\n".join([alines[0]] + [l for l in alines[1:] if l.split("\t")[0] in fams]) + "\n"
-    return synth.SyntheticPedigree(data, ds.tree, ages, ds.leaf_names, n_loci, len(fams))
+def reference_parity(ds, tb, ref_tables, X, n_loci_sample, workdir, device, label):
+    """Parity of the GPU path against the reference's own code on a sample: the first `n_loci_sample` loci (whole
+    families) of the configuration's dataset, the configuration's tables, the first walkers of its ensemble.  Both
+    implementations evaluate the same sample; returns the dict that goes into the bench line."""
+    from mope_b200 import Inference
+    cores = os.cpu_count() or 1
+    nw = int(min(X.shape[0], max(8, min(cores, 16))))
+    sub = ds.subset(n_loci_sample)
+    t0 = time.perf_counter()
+    kind = build_cpu_inference(sub, ref_tables, workdir)
+    Xs = np.ascontiguousarray(X[:nw])
+    n_loci = int(_REF_INF.num_loci[0]) if kind == "reference" else _REF_INF.peds[0].num_loci
+    val, dt, ref_ll = cpu_throughput(Xs, n_loci, min(cores, nw), 1, 0)
+    g = Inference([sub.data], [sub.tree], [sub.ages], tb, log_unif_drift=True, device=device, _inputs_are_text=True)
+    try:
+        gpu_ll = g.loglike_batch(Xs, raise_on_error=False)
+    finally:
+        g.close()
+    fin = np.isfinite(ref_ll) & np.isfinite(gpu_ll)
+    rel = np.abs(gpu_ll[fin] - ref_ll[fin]) / np.abs(ref_ll[fin])
+    return {"max_rel_err": float(rel.max()) if rel.size else None, "walkers_compared": int(fin.sum()), "walkers": nw,
+            "against": "baseline/_ref (the reference's own Cython/NumPy code)" if kind == "reference" else "oracle port",
+            "sample": "%s: first %d loci (%d families) of the dataset, same tables, first %d walkers of the ensemble" % (
+                label, n_loci, sub.n_fam, nw),
+            "nonfinite_mismatch": bool(np.any(np.isfinite(ref_ll) != np.isfinite(gpu_ll))),
+            "cpu_value": val, "cpu_seconds": dt, "cpu_cores": min(cores, nw), "wall_s": time.perf_counter() - t0}
 
 
 def run_reference(args):
@@ -272,8 +337,9 @@ def run_reference(args):
     from mope_b200 import synth
     nw = args.cpu_walkers or cores
     with tempfile.TemporaryDirectory() as wd:
+        rt = RefTables(tb, wd, "main")
         # probe: per-core rate on a small subset, to bound the sample so the whole run ends within minutes
-        kind = build_cpu_inference(subset_dataset(ds, 150), tb, wd)
+        kind = build_cpu_inference(ds.subset(150), rt, wd)
         Xp = synth.walkers_in_prior_box(np.asarray(_REF_INF.lower), np.asarray(_REF_INF.upper), max(args.walkers, nw), seed=1)
         t0 = time.perf_counter()
         _ref_logl(Xp[0])
@@ -281,7 +347,7 @@ def run_reference(args):
         budget = 150.0 / max(args.steps + args.warmup, 1)
         n_sample = int(min(args.loci, max(300, rate_core * budget * 0.7)))
         n_sample -= n_sample % 3
-        kind = build_cpu_inference(subset_dataset(ds, n_sample), tb, wd)
+        kind = build_cpu_inference(ds.subset(n_sample), rt, wd)
         X = Xp[:nw]
         n_loci = int(_REF_INF.num_loci[0]) if kind == "reference" else _REF_INF.peds[0].num_loci
         val, dt, _ = cpu_throughput(X, n_loci, min(cores, nw), args.steps, args.warmup)
@@ -302,239 +368,424 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Dist:
+    """torch.distributed plumbing of one bench process (one process per GPU)."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+        torch.cuda.set_device(self.local_rank)
+        self.device = "cuda:%d" % self.local_rank
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
 
-    from mope_b200 import Inference, synth
-    tb = make_tables(args, "cuda:%d" % local_rank)
-    ds = make_workload(args)
-    inf = Inference([ds.data_tsv], [ds.tree], [ds.ages_tsv], tb, log_unif_drift=True, device=local_rank, _inputs_are_text=True)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather(self, v):
+        """[value of every rank] on every rank."""
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        if self.world == 1:
+            return [float(v)]
+        parts = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t)
+        return [float(p.item()) for p in parts]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def measure(D, inf, X, steps, warmup, locus_sharded=False, sample_clocks=True):
+    """Time `steps` evaluations of all walkers in X on this rank's Inference.
+    value leg: everything resident (tables, emissions, the walkers' root prior already in HBM), CUDA events on the launching
+    stream, bracketed by barrier + synchronize, max over ranks.  With locus_sharded the step ends with the all-reduce of
+    the per-walker partial sums, enqueued on the same stream.
+    e2e leg: the public API with host NumPy vectors in and host log-likelihoods out (root prior on the host, H2D of
+    parameters / root prior / plans, D2H of the result inside the timed region)."""
+    torch, dist = D.torch, D.dist
+    from mope_b200 import dist as mdist
     eng = inf.engine
-    W = args.walkers
-    # walker-sharded: every rank owns its own W walkers of one global ensemble of W*world
-    Xall = synth.walkers_in_prior_box(inf.lower, inf.upper, W * world, seed=1)
-    X = np.ascontiguousarray(Xall[rank * W:(rank + 1) * W])
-    L = inf.num_loci[0]
-    R = L + 2 * inf.peds[0].n_asc
-    B = inf.num_branches[0]
-    F = tb.F
+    W = X.shape[0]
+    stat_dev = torch.as_tensor(inf.stationary_distributions(X), device=D.device)
+    out_dev = torch.empty(W, dtype=torch.float64, device=D.device)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput (`value`): root distributions already in HBM ----
-    stat_dev = torch.as_tensor(inf.stationary_distributions(X), device="cuda:%d" % local_rank)
-    out_dev = torch.empty(W, dtype=torch.float64, device="cuda:%d" % local_rank)
-    for _ in range(args.warmup):
+    def step():
         eng.loglike_device(X, stat_dev, out_dev)
-    barrier()
+        if locus_sharded and D.world > 1:
+            dist.all_reduce(out_dev, op=dist.ReduceOp.SUM)     # the path's only collective: W float64 partial sums
+
+    for _ in range(warmup):
+        step()
+    D.barrier()
     eng.set_profiling(True)
     eng.kernel_times()
     launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            eng.loglike_device(X, stat_dev, out_dev)
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = (eng.launch_count() - launches0) // max(args.steps, 1)
+    clocks = ClockSampler(D.local_rank) if sample_clocks else None
+    if clocks:
+        clocks.__enter__()
+    D.barrier()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    D.barrier()
+    if clocks:
+        clocks.__exit__()
+    ms_local = e0.elapsed_time(e1) / steps
+    launches = (eng.launch_count() - launches0) // max(steps, 1)
     tree_ms, tree_n, interp_ms, interp_n = eng.kernel_times()
     gemm_ops, identity_ops = eng.last_eval_stats()
+    unit_rows = eng.last_eval_unit_rows()
     eng.set_profiling(False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = W * world * L / (ms_max * 1e-3)
+    ms = D.max_over_ranks(ms_local)
     ll_dev = out_dev.cpu().numpy()
 
-    # ---- end to end through the public API: host parameter vectors in, host log-likelihoods out ----
-    for _ in range(max(1, args.warmup // 2)):
-        ll_host = inf.loglike_batch(X, raise_on_error=False)
-    barrier()
+    def e2e_step():
+        if locus_sharded and D.world > 1:
+            return mdist.loglike_locus_sharded(inf, X)[0]
+        return inf.loglike_batch(X, raise_on_error=False)
+
+    for _ in range(max(1, warmup // 2)):
+        ll_host = e2e_step()
+    D.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ll_host = inf.loglike_batch(X, raise_on_error=False)
+    for _ in range(steps):
+        ll_host = e2e_step()
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = W * world * L / float(t.item())
-    n_keys = len({(inf.peds[0].varname_of[b], bool(inf.peds[0].br_bottleneck[i])) for i, b in enumerate(inf.peds[0].branch_names)})
-    h2d = W * inf.ndim * 8 + W * F * 8 + W * n_keys * (88 + 8) + W * 4
-    d2h = W * 8
+    e2e_local = (time.perf_counter() - t0) / steps
+    e2e_s = D.max_over_ranks(e2e_local)
     if not os.environ.get("MOPE_DEBUG_MODE"):
-        assert np.array_equal(np.isnan(ll_host), np.isnan(ll_dev)) and np.allclose(ll_host[np.isfinite(ll_host)], ll_dev[np.isfinite(ll_dev)], rtol=1e-12)
-
-    if rank == 0:
-        # ---- roofline of the dominant kernel (the fused pruning kernel), fp64 tensor pipe ----
-        # algorithmic flops of the GEMMs the kernel actually executes: 2 F^2 per (row, branch), minus the branches
-        # that take the reference's identity short-cut (those are forwarded without a product)
-        flops_per_launch = 2.0 * F * F * R * gemm_ops
-        tree_avg_ms = tree_ms / max(tree_n, 1)
-        achieved = flops_per_launch / (tree_avg_ms * 1e-3) * 1e-12
-        peak = eng.fp64_peak_tflops(300.0)
-        hbm = None
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                hbm = json.load(f).get("hbm_gbs")
-        except Exception:
-            pass
-        # compulsory HBM bytes per launch (fused ideal): emissions once per walker pass + matrices + outputs
-        n_leaves = len(inf.leaf_names[0])
-        alg_bytes = (R * n_leaves * 208 * 8) * 1.0 + W * n_keys * (5 * F * F * 8)
-        traffic = None
-        try:
-            # DRAM bytes of the dominant kernel from the committed ncu capture of this same workload (per launch)
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                tj = json.load(f)
-            if args.loci == 10000 and args.leaves == 16 and W == 256 and F == 201:
-                traffic = tj["traffic_bytes_per_launch"]
-        except Exception:
-            pass
-        roofline = {"bound": "tensor", "kernel": "tree_kernel4<26,25,scalar> (fused pruning pass: TMA ring + mma.sync.m8n8k4.f64, warp-owned rows, messages in tensor memory)", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, profiles/r01_traffic.json)",
-                    "peak_source": "fp64 DMMA register-only loop measured live in this run (MEASURED_PEAKS.json has no fp64 entry; "
-                                   "its dense-bf16 figure does not bound an fp64 kernel)",
-                    "flops_per_launch": flops_per_launch, "branch_gemms_per_launch": int(gemm_ops),
-                    "identity_branches_per_launch": int(identity_ops), "avg_launch_ms": tree_avg_ms, "launches_timed": int(tree_n),
-                    "share_of_step": tree_avg_ms * (tree_n / max(args.steps, 1)) / ms,
-                    "hbm_frac_if_memory_bound": (alg_bytes / (tree_avg_ms * 1e-3) * 1e-9 / hbm) if hbm else None,
-                    "interp_avg_ms": interp_ms / max(interp_n, 1)}
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            with tempfile.TemporaryDirectory() as wd:
-                kind = build_cpu_inference(ds, tb, wd)
-                cores = os.cpu_count() or 1
-                nw = args.cpu_walkers or cores
-                Xc = X[:nw]
-                val, dt, ref_ll = cpu_throughput(Xc, L, min(cores, nw), 1, 0)
-            fin = np.isfinite(ref_ll) & np.isfinite(ll_host[:nw])
-            rel = np.abs(ll_host[:nw][fin] - ref_ll[fin]) / np.abs(ref_ll[fin])
-            cpu = {"value": val, "unit": UNIT, "cores": min(cores, nw), "kind": kind,
-                   "sample": "%d walkers x all %d loci, one pass (%.1f s), fork pool of %d processes" % (nw, L, dt, min(cores, nw)),
-                   "parity_max_rel_err_vs_gpu": float(rel.max()) if rel.size else None,
-                   "parity_walkers_compared": int(fin.sum())}
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload_name(args, F), "walkers_total": W * world, "rows_per_walker": R, "branches": B,
-                       "drift_grid": "%dx%d" % (tb.drift.shape[0], tb.drift.shape[1]), "parallelism": "walker-sharded x%d" % world,
-                       "l2_policy": "inputs larger than L2 (emissions %.0f MB + per-walker matrices %.0f MB per step)" % (
-                           R * n_leaves * 208 * 8 / 1e6, W * n_keys * 208 * 209 * 8 / 1e6),
-                       "finite_walkers": int(np.isfinite(ll_host).sum())},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": float(t.item()) * 1e3},
-            "gpu_launches": int(launches * args.steps),
-            "clocks": clocks.summary(),
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    inf.close()
+        assert np.array_equal(np.isnan(ll_host), np.isnan(ll_dev)) and \
+            np.allclose(ll_host[np.isfinite(ll_host)], ll_dev[np.isfinite(ll_dev)], rtol=1e-12), "device-resident and e2e results differ"
+    steps_per_eval = tree_n / max(steps, 1)
+    return {"ms": ms, "ms_local": ms_local, "e2e_s": e2e_s, "e2e_local_s": e2e_local, "launches_per_step": int(launches),
+            "tree_ms_per_step": tree_ms / max(steps, 1), "tree_launches_per_step": steps_per_eval,
+            "interp_ms_per_step": interp_ms / max(steps, 1), "interp_launches_per_step": interp_n / max(steps, 1),
+            "gemm_ops": int(gemm_ops), "identity_ops": int(identity_ops), "unit_rows": int(unit_rows),
+            "ll_host": ll_host, "clocks": clocks.summary() if clocks else None}
 
 
-def run_ours_locus(args):
-    """Locus-sharded evaluation over the ranks (mope_b200.dist): not the default bench line, a measured demonstration of
-    the path's only collective.  value = walkers x ALL loci / step time (strong scaling in the rows)."""
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f).get("hbm_gbs"), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback of B200_PROFILING.md (of fallback)"
+
+
+def committed_traffic(key):
+    """DRAM bytes per launch of a kernel from the committed ncu capture of the same workload (profiles/r02_traffic.json);
+    ncu cannot run inside the timed process, so this figure is read, not measured, in this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+def tree_roofline(m, F, R_exec, R_ref, B, W, peak, kernel):
+    """Roofline of the pruning kernel of one configuration (fp64 tensor pipe).
+    executed: 2 F^2 x (real rows x GEMM units the kernel ran, counted by the kernel itself);
+    useful:   2 F^2 B R W with R = L + 2 n_fam, the branch updates the reference performs for the same evaluation."""
+    t = m["tree_ms_per_step"] * 1e-3
+    executed = 2.0 * F * F * m["unit_rows"]
+    useful = 2.0 * F * F * B * R_ref * W
+    return {"bound": "tensor", "kernel": kernel, "achieved": executed / t * 1e-12, "peak": peak, "unit": "TFLOP/s",
+            "frac": executed / t * 1e-12 / peak, "executed_flops_per_step": executed,
+            "useful_flops_per_step": useful, "useful_tflops": useful / t * 1e-12, "useful_frac": useful / t * 1e-12 / peak,
+            "tree_kernel_ms_per_step": m["tree_ms_per_step"], "tree_launches_per_step": m["tree_launches_per_step"],
+            "share_of_step": m["tree_ms_per_step"] / m["ms_local"], "interp_ms_per_step": m["interp_ms_per_step"],
+            "branch_gemms_per_step": m["gemm_ops"], "identity_branches_per_step": m["identity_ops"],
+            "rows_per_walker_executed": R_exec, "rows_per_walker_reference": R_ref}
+
+
+def interp_roofline(m, F, Fp, n_fixed_blocks, n_rate_blocks):
+    """HBM roofline of interp_kernel: per matrix block 4 (shared-matrix branches) or 2 (age-scaled: mutation axis only)
+    F x F source matrices read, one Fp x (Fp + 3) block written."""
+    hbm, src = hbm_peak()
+    if m["interp_ms_per_step"] <= 0:
+        return None
+    bytes_ = n_fixed_blocks * (4 * F * F * 8 + Fp * (Fp + 3) * 8) + n_rate_blocks * (2 * F * F * 8 + Fp * (Fp + 3) * 8)
+    gbs = bytes_ / (m["interp_ms_per_step"] * 1e-3) * 1e-9
+    return {"bound": "hbm", "kernel": "interp_kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+            "bytes_per_step": bytes_, "ms_per_step": m["interp_ms_per_step"], "peak_source": src,
+            "traffic": committed_traffic("interp_kernel_bytes_per_step_cfg2")}
+
+
+def run_extra_config(D, name, base_tb, workdir, peak, do_cpu, steps_cap):
+    """One of cfg3 / cfg4 / cfg5 at its BASELINE.json size -> dict for the `configs` array (rank 0), None elsewhere."""
     import torch
-    import torch.distributed as dist
+    from mope_b200 import Inference, synth, generate
+    from mope_b200 import dist as mdist
+    t_begin = time.perf_counter()
+    locus = False
+    if name == "cfg3":
+        loci, W, tree = 100000, 32, synth.balanced_tree(16, rate_leaves=True, rate_internal=True)
+        tb, tag, n_sample = base_tb, "main", 600
+        desc = "cfg3: L=100000 loci x 16 tissues, 16 age-scaled leaf branches + 1 age-scaled internal branch (17 of B=30), F=201, W=32 walkers/GPU, walker-sharded"
+    elif name == "cfg4":
+        loci, W, tree = 1000000, 64, synth.balanced_tree(16, rate_internal=True, bottleneck=True)
+        locus = D.world > 1
+        from mope_b200.tables import TransitionTables
+        b = generate.generate_tables(N=1000, breaks=(0.5, 0.005), gens=[1, 2], us=[1e-9, 1e-8], nbs=CFG4_NBS, bot_us=CFG4_BOT_US,
+                                     device=D.device)
+        tb = TransitionTables(drift=base_tb.drift, gens=base_tb.gens, us=base_tb.us, N=base_tb.N, freqs=base_tb.freqs,
+                              breaks=base_tb.breaks, bot=b.bot, nbs=b.nbs, bot_us=b.bot_us)
+        tag, n_sample = "cfg4", 600
+        desc = ("cfg4: L=1000000 loci x 16 tissues, one bottleneck (^) branch + one age-scaled internal branch, ascertainment on, F=201, "
+                "W=64 walkers, " + ("locus-sharded over %d GPUs (families partitioned, ONE NCCL all-reduce of 64 doubles per evaluation, "
+                                    "enqueued on the compute stream)" % D.world if locus else "one GPU (emissions 35 GB resident)"))
+    elif name == "cfg5":
+        loci, W, tree = 1000, 512, synth.balanced_tree(16)
+        tb = generate.generate_tables(N=1000, breaks=(0.5, 1e-9), gens=CFG5_GENS, us=CFG5_US, device=D.device)
+        tag, n_sample = "cfg5", 30
+        desc = "cfg5: F=1001 (WF N=1000, every count its own bin), L=1000 loci x 16 tissues, B=30 fixed-length branches, W=512 walkers/GPU, walker-sharded, 16x8 drift grid"
+    else:
+        raise ValueError(name)
+    ds = synth.make_dataset(loci, 16, tree=tree)
+    t_data = time.perf_counter() - t_begin
+    if locus:
+        inf = mdist.build_locus_sharded([ds.data], [ds.tree], [ds.ages], tb, D.rank, D.world, log_unif_drift=True, device=D.local_rank)
+        X = synth.walkers_in_prior_box(inf.lower, inf.upper, W, seed=1)       # the same ensemble on every rank
+        L_total = int(round(D.sum_over_ranks(inf.num_loci[0])))
+        W_total = W
+    else:
+        inf = Inference([ds.data], [ds.tree], [ds.ages], tb, log_unif_drift=True, device=D.local_rank, _inputs_are_text=True)
+        if name == "cfg4":
+            X = synth.walkers_in_prior_box(inf.lower, inf.upper, W, seed=1)
+            W_total = W
+        else:
+            Xall = synth.walkers_in_prior_box(inf.lower, inf.upper, W * D.world, seed=1)
+            X = np.ascontiguousarray(Xall[D.rank * W:(D.rank + 1) * W])
+            W_total = W * D.world
+        L_total = inf.num_loci[0]
+    t_setup = time.perf_counter() - t_begin
+    # steps: about 3 s of timed work, at least 2
+    probe = measure(D, inf, X, 1, 1, locus_sharded=locus, sample_clocks=False)
+    steps = int(max(2, min(steps_cap, round(3000.0 / max(probe["ms"], 1e-3)))))
+    m = measure(D, inf, X, steps, 1, locus_sharded=locus)
+    ped = inf.peds[0]
+    F, Fp = tb.F, (tb.F + 15) // 16 * 16
+    R_exec = ped.num_loci + 2 * ped.n_asc
+    R_ref = ped.num_loci + 2 * ped.n_fam
+    B = inf.num_branches[0]
+    kernel = ("tree_kernel<13> (F > 208: five N passes per branch, messages through the L2 scratch ring)" if F > 208 else
+              "tree_kernel4<26,25,scalar" + (",ascfast>" if R_exec - ped.num_loci >= 64 else ">") +
+              (" + canonical launch (family-independent ascertainment subtrees once per walker)" if m["tree_launches_per_step"] > 1.5 else ""))
+    roof = tree_roofline(m, F, R_exec, R_ref, B, X.shape[0], peak, kernel)
+    per_rank = {"ms_per_step": D.gather(m["ms_local"]), "e2e_ms_per_step": D.gather(m["e2e_local_s"] * 1e3),
+                "tree_kernel_ms_per_step": D.gather(m["tree_ms_per_step"]), "loci": D.gather(inf.num_loci[0]),
+                "rows_per_walker": D.gather(R_exec)}
+    value = W_total * L_total / (m["ms"] * 1e-3)
+    e2e_value = W_total * L_total / m["e2e_s"]
+    ll_host = m["ll_host"]
+
+    parity = None
+    sharded_parity = None
+    if locus:
+        # the sharded sum against the whole dataset on ONE GPU, 8 walkers (rank 0 builds the unsharded model; the others wait)
+        if D.rank == 0:
+            full = Inference([ds.data], [ds.tree], [ds.ages], tb, log_unif_drift=True, device=D.local_rank, _inputs_are_text=True)
+            ref = full.loglike_batch(X[:8], raise_on_error=False)
+            full.close()
+            fin = np.isfinite(ref) & np.isfinite(ll_host[:8])
+            sharded_parity = {"max_rel_err": float((np.abs(ll_host[:8][fin] - ref[fin]) / np.abs(ref[fin])).max()),
+                              "walkers_compared": int(fin.sum()), "against": "the same 1 000 000 loci evaluated unsharded on one GPU"}
+        D.barrier()
+    inf.close()
+    del inf
+    torch.cuda.empty_cache()
+    if do_cpu and D.world == 1 and D.rank == 0:
+        parity = reference_parity(ds, tb, RefTables(tb, workdir, tag) if tag != "main" else run_extra_config.main_ref_tables,
+                                  X, n_sample, workdir, D.local_rank, name)
+    if D.rank != 0:
+        return None
+    out = {"name": name, "workload": desc, "n_gpus": D.world, "scaling": "strong" if name == "cfg4" else "weak",
+           "walkers_total": W_total, "loci_total": int(L_total), "steps": steps, "warmup": 1,
+           "ms_per_step": m["ms"], "value": value, "unit": UNIT,
+           "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": m["e2e_s"] * 1e3},
+           "gpu_launches_per_step": m["launches_per_step"], "finite_walkers": int(np.isfinite(ll_host).sum()),
+           "roofline": roof, "per_rank": per_rank, "parity_vs_reference": parity, "clocks": m["clocks"],
+           "setup_s": {"data": t_data, "model_and_tables": t_setup - t_data, "total_wall": time.perf_counter() - t_begin}}
+    if sharded_parity is not None:
+        out["parity_sharded_vs_single_gpu"] = sharded_parity
+    return out
+
+
+def run_ours(args):
+    import torch
+    D = Dist()
+    rank, local_rank, world = D.rank, D.local_rank, D.world
     from mope_b200 import Inference, synth
     from mope_b200 import dist as mdist
 
-    rank, local_rank, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(local_rank)
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    tb = make_tables(args, "cuda:%d" % local_rank)
+    tb = make_tables(args, D.device)
     ds = make_workload(args)
-    inf = mdist.build_locus_sharded([ds.data_tsv], [ds.tree], [ds.ages_tsv], tb, rank, world, log_unif_drift=True, device=local_rank)
     W = args.walkers
-    X = synth.walkers_in_prior_box(inf.lower, inf.upper, W, seed=1)     # the same ensemble on every rank
-    Lt = torch.tensor([inf.num_loci[0]], dtype=torch.int64, device="cuda")
-    dist.all_reduce(Lt)
-    L_total = int(Lt.item())
-    dev = "cuda:%d" % local_rank
-    stat_dev = torch.as_tensor(inf.stationary_distributions(X), device=dev)
-    out_dev = torch.empty(W, dtype=torch.float64, device=dev)
+    locus = (args.shard == "locus" and world > 1)
+    if locus:
+        inf = mdist.build_locus_sharded([ds.data], [ds.tree], [ds.ages], tb, rank, world, log_unif_drift=True, device=local_rank)
+        X = synth.walkers_in_prior_box(inf.lower, inf.upper, W, seed=1)
+        W_total, L = W, int(round(D.sum_over_ranks(inf.num_loci[0])))
+    else:
+        inf = Inference([ds.data], [ds.tree], [ds.ages], tb, log_unif_drift=True, device=local_rank, _inputs_are_text=True)
+        # walker-sharded: every rank owns its own W walkers of one global ensemble of W*world
+        Xall = synth.walkers_in_prior_box(inf.lower, inf.upper, W * world, seed=1)
+        X = np.ascontiguousarray(Xall[rank * W:(rank + 1) * W])
+        W_total, L = W * world, inf.num_loci[0]
+    eng = inf.engine
+    ped = inf.peds[0]
+    R = L + 2 * ped.n_asc if not locus else None
+    R_local = inf.num_loci[0] + 2 * ped.n_asc
+    B = inf.num_branches[0]
+    F, Fp = tb.F, (tb.F + 15) // 16 * 16
 
-    def step():
-        inf.engine.loglike_device(X, stat_dev, out_dev)
-        dist.all_reduce(out_dev, op=dist.ReduceOp.SUM)     # the path's only collective: W float64 partial sums
+    m = measure(D, inf, X, args.steps, args.warmup, locus_sharded=locus)
+    value = W_total * L / (m["ms"] * 1e-3)
+    e2e_value = W_total * L / m["e2e_s"]
+    ll_host = m["ll_host"]
+    n_keys = len({(ped.varname_of[b], bool(ped.br_bottleneck[i])) for i, b in enumerate(ped.branch_names)})
+    h2d = W * inf.ndim * 8 + W * F * 8 + W * n_keys * (88 + 8) + W * 4
+    d2h = W * 8
+    per_rank = {"ms_per_step": D.gather(m["ms_local"]), "e2e_ms_per_step": D.gather(m["e2e_local_s"] * 1e3),
+                "tree_kernel_ms_per_step": D.gather(m["tree_ms_per_step"]), "interp_ms_per_step": D.gather(m["interp_ms_per_step"])}
 
-    for _ in range(args.warmup):
-        step()
-    dist.barrier(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        e0.record()
-        for _ in range(args.steps):
-            step()
-        e1.record()
-        dist.barrier(); torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ll_dev = out_dev.cpu().numpy()
-    # end to end through the public API (host vectors in, host log-likelihoods out, all-reduce inside)
-    mdist.loglike_locus_sharded(inf, X)
-    dist.barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ll_host, st = mdist.loglike_locus_sharded(inf, X)
-    torch.cuda.synchronize()
-    te = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device="cuda")
-    dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    parity = None
+    line = None
+    workdir = tempfile.mkdtemp(prefix="mope_bench_")
+    main_ref = RefTables(tb, workdir, "main")
+    run_extra_config.main_ref_tables = main_ref
+    peak = None
     if rank == 0:
-        # the sharded sum against the whole dataset on one GPU
-        full = Inference([ds.data_tsv], [ds.tree], [ds.ages_tsv], tb, log_unif_drift=True, device=local_rank, _inputs_are_text=True)
-        ref = full.loglike_batch(X[:32], raise_on_error=False)
-        full.close()
-        fin = np.isfinite(ref) & np.isfinite(ll_host[:32])
-        parity = float((np.abs(ll_host[:32][fin] - ref[fin]) / np.abs(ref[fin])).max())
-        assert parity < 1e-11, parity
-        line = {"metric": METRIC, "value": W * L_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args, tb.F), "walkers_total": W, "loci_total": L_total,
-                           "parallelism": "locus-sharded x%d (families partitioned; one NCCL all-reduce of %d doubles per evaluation)" % (world, W),
-                           "finite_walkers": int(np.isfinite(ll_dev).sum())},
-                "e2e": {"value": W * L_total / float(te.item()), "unit": UNIT, "ms_per_step": float(te.item()) * 1e3},
-                "parity_max_rel_err_vs_single_gpu": parity, "clocks": clocks.summary()}
-        print(json.dumps(line))
-    dist.barrier()
-    dist.destroy_process_group()
+        # ---- roofline of the dominant kernel (the fused pruning kernel), fp64 tensor pipe ----
+        # executed flops: 2 F^2 per (real row, GEMM unit) the kernel ran, counted by the kernel; branches that take the
+        # reference's identity short-cut are forwarded without a product and do not count
+        peak = eng.fp64_peak_tflops(300.0)
+        kernel = ("tree_kernel4<26,25,scalar> (fused pruning pass: TMA ring + mma.sync.m8n8k4.f64, warp-owned rows, messages in tensor memory)"
+                  if F == 201 else "tree_kernel4 / tree_kernel instance for F=%d" % F)
+        roofline = tree_roofline(m, F, R_local, inf.num_loci[0] + 2 * ped.n_fam, B, W, peak, kernel)
+        hbm, _src = hbm_peak()
+        n_leaves = len(inf.leaf_names[0])
+        alg_bytes = (R_local * n_leaves * Fp * 8) * 1.0 + W * n_keys * (5 * F * F * 8)
+        roofline.update({
+            "peak_source": "fp64 DMMA register-only loop measured live in this run (MEASURED_PEAKS.json has no fp64 entry; "
+                           "its dense-bf16 figure does not bound an fp64 kernel)",
+            "flops_per_launch": roofline["executed_flops_per_step"] / max(m["tree_launches_per_step"], 1),
+            "avg_launch_ms": m["tree_ms_per_step"] / max(m["tree_launches_per_step"], 1),
+            "launches_timed": int(round(m["tree_launches_per_step"] * args.steps)),
+            "traffic": committed_traffic("tree_kernel4_bytes_per_launch_cfg2") if is_default_headline(args) else None,
+            "traffic_unit": "bytes/launch (ncu dram__bytes_read+write of the same workload, committed in profiles/r02_traffic.json; "
+                            "not measured in this run -- ncu cannot run inside the timed process)",
+            "hbm_frac_if_memory_bound": (alg_bytes / (m["tree_ms_per_step"] * 1e-3) * 1e-9 / hbm) if hbm else None,
+            "interp_avg_ms": m["interp_ms_per_step"] / max(m["interp_launches_per_step"], 1),
+        })
+    # number of matrix blocks the interpolation kernel wrote in the last step: shared-matrix keys that were not identity
+    # (age-scaled keys: one block per generation-grid index touched; counted as two-source blocks)
+    if rank == 0:
+        keys_fixed = [(ped.varname_of[b], bool(ped.br_bottleneck[i])) for i, b in enumerate(ped.branch_names) if ped.br_mult[i] < 0]
+        uniq_fixed = sorted(set(keys_fixed))
+        N = tb.N
+        nblocks = 0
+        for x in X:
+            for (v, bott) in uniq_fixed:
+                ln = 10 ** x[inf.var_indices[v]]
+                if bott or not (N * ln < tb.gens[0]):
+                    nblocks += 1
+        roofline["interp"] = interp_roofline(m, F, Fp, nblocks, 0) if args.tree == "fixed" else None
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        kind = build_cpu_inference(ds, main_ref, workdir)
+        cores = os.cpu_count() or 1
+        nw = args.cpu_walkers or cores
+        Xc = X[:nw]
+        val, dt, ref_ll = cpu_throughput(Xc, L, min(cores, nw), 1, 0)
+        fin = np.isfinite(ref_ll) & np.isfinite(ll_host[:nw])
+        rel = np.abs(ll_host[:nw][fin] - ref_ll[fin]) / np.abs(ref_ll[fin])
+        cpu = {"value": val, "unit": UNIT, "cores": min(cores, nw), "kind": kind,
+               "sample": "%d walkers x all %d loci, one pass (%.1f s), fork pool of %d processes" % (nw, L, dt, min(cores, nw)),
+               "parity_max_rel_err_vs_gpu": float(rel.max()) if rel.size else None,
+               "parity_walkers_compared": int(fin.sum())}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["ms"], "higher_is_better": True, "scaling": "strong" if locus else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args, F), "walkers_total": W_total, "rows_per_walker": R_local, "branches": B,
+                       "drift_grid": "%dx%d" % (tb.drift.shape[0], tb.drift.shape[1]),
+                       "parallelism": ("locus-sharded x%d (families partitioned; one NCCL all-reduce of %d doubles per evaluation)" % (world, W)
+                                       if locus else "walker-sharded x%d" % world),
+                       "l2_policy": "inputs larger than L2 (emissions %.0f MB + per-walker matrices %.0f MB per step)" % (
+                           R_local * len(inf.leaf_names[0]) * Fp * 8 / 1e6, W * n_keys * Fp * (Fp + 3) * 8 / 1e6),
+                       "value_note": "value = device-resident step: tables, emissions and the walkers' root prior (a function of two "
+                                     "parameters, computed on the host by SciPy's betainc) already in HBM; e2e includes the root prior, "
+                                     "pipelined against the device work",
+                       "finite_walkers": int(np.isfinite(ll_host).sum())},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": m["e2e_s"] * 1e3},
+            "gpu_launches": int(m["launches_per_step"] * args.steps),
+            "clocks": m["clocks"],
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "per_rank": per_rank,
+        }
     inf.close()
+    del inf, eng
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations ----
+    wanted = [c.strip() for c in args.configs.split(",")] if args.configs != "all" else ["cfg2", "cfg3", "cfg4", "cfg5"]
+    extras = []
+    if is_default_headline(args):
+        pk = D.max_over_ranks(peak if peak is not None else 0.0)     # every rank needs the same call sequence; rank 0 measured it
+        for name in ("cfg3", "cfg4", "cfg5"):
+            if name not in wanted:
+                continue
+            try:
+                r = run_extra_config(D, name, tb, workdir, pk, not args.no_cpu_baseline, args.steps)
+            except Exception as e:   # an extra configuration must never cost the headline line
+                import traceback
+                traceback.print_exc(file=sys.stderr)
+                r = {"name": name, "error": repr(e)} if rank == 0 else None
+                if world > 1:
+                    raise
+            if r is not None:
+                extras.append(r)
+    if rank == 0:
+        line["configs"] = extras
+        print(json.dumps(line))
+    import shutil
+    shutil.rmtree(workdir, ignore_errors=True)
+    D.close()
 
 
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.shard == "locus" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        run_ours_locus(args)
     else:
         run_ours(args)
 

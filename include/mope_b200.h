@@ -156,6 +156,12 @@ int mope_b200_schedule_stats(const mope_model_desc* model, int F, int ped, int32
  * the message is forwarded without a GEMM.  For age-scaled branches every (walker, branch) counts as one GEMM. */
 int mope_b200_last_eval_stats(const mope_ctx* ctx, int64_t* gemm_ops, int64_t* identity_ops);
 
+/* Executed work of the last eval, counted by the pruning kernel itself: the sum over all GEMM units it ran through the
+ * tensor pipe (a unit = one branch, or one generation segment of an age-scaled branch, on one tile) of the unit's real
+ * rows.  2 * F^2 * unit_rows = executed flops.  Branches forwarded by the identity short-cut, generation segments no
+ * row of a warp blends, and the ascertainment short-cuts do not count.  Synchronises the stream of the last eval. */
+int mope_b200_last_eval_unit_rows(mope_ctx* ctx, int64_t* unit_rows);
+
 /* Measurement support (bench.py).  With profiling on, every pruning-kernel launch is bracketed by CUDA events on
  * its stream; mope_b200_kernel_times synchronises, returns the accumulated device time (ms) and launch count of the
  * pruning kernel and of the interpolation kernel since the last call, and resets the accumulators. */

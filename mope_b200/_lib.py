@@ -56,7 +56,7 @@ class ModelDesc(C.Structure):
 
 # every symbol include/mope_b200.h declares
 SYMBOLS = ["mope_b200_arena_bytes", "mope_b200_create", "mope_b200_destroy", "mope_b200_workspace_bytes",
-           "mope_b200_eval", "mope_b200_eval_device", "mope_b200_launch_count", "mope_b200_schedule_stats", "mope_b200_last_eval_stats", "mope_b200_set_profiling",
+           "mope_b200_eval", "mope_b200_eval_device", "mope_b200_launch_count", "mope_b200_schedule_stats", "mope_b200_last_eval_stats", "mope_b200_last_eval_unit_rows", "mope_b200_set_profiling",
            "mope_b200_kernel_times", "mope_b200_fp64_peak", "mope_b200_transition_matrix",
            "mope_b200_leaf_likelihoods", "mope_b200_branch_update", "mope_b200_non_asc_probs", "mope_b200_beta_cdf_table",
            "mope_b200_last_error", "mope_b200_version"]
@@ -95,6 +95,7 @@ def lib():
     L.mope_b200_launch_count.restype = C.c_int64
     L.mope_b200_schedule_stats.argtypes = [C.POINTER(ModelDesc), C.c_int, C.c_int, ip]
     L.mope_b200_last_eval_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.mope_b200_last_eval_unit_rows.argtypes = [vp, C.POINTER(C.c_int64)]
     L.mope_b200_set_profiling.argtypes = [vp, C.c_int]
     L.mope_b200_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_int64), dp, C.POINTER(C.c_int64)]
     L.mope_b200_fp64_peak.argtypes = [vp, C.c_double, vp, dp]

@@ -93,6 +93,7 @@ struct TreeParams {
     double* Yout;            // operator-level mode (single op): Y rows go to Yout[w][row][Fp] instead of a slot
     int32_t debug;           // measurement only: 1 = skip the MMAs (data movement only), 2 = skip the copies (MMAs only)
     int32_t* work_ctr;       // zeroed before the launch: next item to hand out
+    unsigned long long* unit_rows;   // statistics: += real rows x GEMM units (branch x generation segment) executed (may be null)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -106,11 +107,13 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // ------------------------------------------------------------------------------------------------
 // leaf emissions (mope/_binom.pyx:20-23,49-92; GSL gsl_ran_binomial_pdf algorithm)
 // ------------------------------------------------------------------------------------------------
-// One warp per (leaf, row).  logp / log1mp / p-class per frequency come from the host (libm), so the
-// only device transcendental calls are lgamma (3 per row) and exp (1 per element).
+// One warp per (leaf, row).  logp / log1mp / p-class per frequency and ln C(n, k) per (row, leaf) come from the host
+// (libm log / log1p / lgamma, the calls the reference's GSL routine makes), so the only device transcendental is one
+// exp per element and an emission differs from the reference's by the rounding of that exp alone.
 struct EmissionParams {
     const double* counts;    // [L][S]
     const double* coverage;  // [L][S]
+    const double* lnchoose;  // [L][S] ln C(coverage, count) (gsl_sf_lnchoose on the host); unused where count is NaN or > coverage
     const double* logp;      // [F]
     const double* log1mp;    // [F]
     const int8_t* pclass;    // [F] 0: 0<p<1, 1: p==0, 2: p==1
@@ -120,12 +123,6 @@ struct EmissionParams {
     int32_t L, S, R, R_pad, F, Fp;
     int32_t perm;            // 1: write columns in the k-permuted layout
 };
-
-__device__ __forceinline__ double lnchoose_dev(unsigned n, unsigned m) {
-    if (m == n || m == 0) return 0.0;
-    if (m * 2u > n) m = n - m;
-    return __dsub_rn(__dsub_rn(lgamma((double)n + 1.0), lgamma((double)m + 1.0)), lgamma((double)(n - m) + 1.0));
-}
 
 __global__ void emission_kernel(EmissionParams p) {
     const int lane = threadIdx.x & 31;
@@ -155,7 +152,7 @@ __global__ void emission_kernel(EmissionParams p) {
         for (int f = lane; f < p.Fp; f += 32) out[f] = 0.0;
         return;
     }
-    const double lc = lnchoose_dev(un, uk);
+    const double lc = p.lnchoose[(size_t)r * p.S + s];
     const double dk = (double)uk, dnk = (double)(un - uk);
     for (int f = lane; f < p.Fp; f += 32) {
         double v = 0.0;
@@ -271,6 +268,14 @@ interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __re
     }
 
     // ---- phase 3: one warp per row ----
+    // column masks of the low / high sums for this lane's columns f = lane + 32 k (bit k), the same for every row
+    unsigned m_lo = 0, m_hi = 0;
+    if (asc_mask)
+        for (int f = lane, k = 0; f < F; f += 32, ++k) {
+            m_lo |= (asc_mask[f] ? 1u : 0u) << (k & 31);
+            m_hi |= (asc_mask[F + f] ? 1u : 0u) << (k & 31);
+        }
+    const bool masks_in_regs = F <= 1024;   // 32 columns per lane
     for (int r = warp; r < rows; r += INTERP_THREADS / 32) {
         const int i = i0 + r;
         if (i >= Fp) break;
@@ -294,14 +299,16 @@ interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __re
         const bool div = check && (s > 1.0);
         // low / high sums of the stored (normalised) row: lane-strided partial sums, then a fixed-order warp reduction
         double lo = 0.0, hi = 0.0;
-        for (int f = lane; f < Fp; f += 32) {
+        for (int f = lane, k = 0; f < Fp; f += 32, ++k) {
             double v = 0.0;
             if (f < F) {
                 v = row[f];
                 if (div) v = __ddiv_rn(v, s);
                 if (asc_mask) {
-                    if (asc_mask[f]) lo = __dadd_rn(lo, v);
-                    if (asc_mask[F + f]) hi = __dadd_rn(hi, v);
+                    const bool is_lo = masks_in_regs ? ((m_lo >> k) & 1u) : (asc_mask[f] != 0);
+                    const bool is_hi = masks_in_regs ? ((m_hi >> k) & 1u) : (asc_mask[F + f] != 0);
+                    if (is_lo) lo = __dadd_rn(lo, v);
+                    if (is_hi) hi = __dadd_rn(hi, v);
                 }
             }
             dst[perm ? kperm(f) : f] = v;
@@ -661,6 +668,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                     }
                 }
 
+                if (pass == 0 && threadIdx.x == 0 && p.unit_rows != nullptr) {
+                    const int nun = (op.kind == 0) ? (identity ? 0 : 1) : max(0, ts->seg_hi - ts->seg_lo + 1);
+                    const int real = max(0, min(TM, p.R - row0));
+                    if (nun > 0 && real > 0) atomicAdd(p.unit_rows, (unsigned long long)nun * (unsigned)real);
+                }
                 if (op.kind == 0) {
                     if (!identity) {
                         u.p_row = ts->prow[oi] + t0 * 8;

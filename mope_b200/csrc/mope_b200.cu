@@ -125,6 +125,7 @@ struct mope_ctx {
     int max_slots4 = 1;
     // statistics of the last eval: branch GEMMs executed / skipped by the identity short-cut (per walker x branch)
     int64_t last_gemm_ops = 0, last_identity_ops = 0;
+    cudaStream_t last_stream = nullptr;
     // profiling
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_tree, ev_interp;
@@ -180,6 +181,33 @@ int ensure_opbuf(mope_ctx* c, size_t bytes) {
     CUDA_TRY(cudaMalloc(&c->opbuf, cap));
     c->opbuf_cap = cap;
     return 0;
+}
+
+// ln C(n, k) per cell exactly as the reference's GSL call chain evaluates it (mope/_binom.pyx:20-31 -> gsl_ran_binomial_pdf ->
+// gsl_sf_lnchoose): counts and coverage cast to unsigned, m := min(k, n - k), lgamma(n+1) - lgamma(m+1) - lgamma(n-m+1) with
+// libm's lgamma.  Host threads; cells with a NaN count or k > n are not read by the kernel.
+void host_lnchoose(const double* counts, const double* coverage, size_t cells, double* out) {
+    auto run = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            const double x = counts[i], nn = coverage[i];
+            double v = 0.0;
+            if (!(x != x)) {
+                const unsigned un = (unsigned)nn;
+                unsigned um = (unsigned)x;
+                if (um <= un && um != un && um != 0) {
+                    if (um * 2u > un) um = un - um;
+                    int sg;
+                    v = lgamma_r((double)un + 1.0, &sg) - lgamma_r((double)um + 1.0, &sg) - lgamma_r((double)(un - um) + 1.0, &sg);
+                }
+            }
+            out[i] = v;
+        }
+    };
+    const unsigned nth = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)std::thread::hardware_concurrency(), cells >> 14}));
+    std::vector<std::thread> th;
+    for (unsigned k = 1; k < nth; ++k) th.emplace_back(run, cells * k / nth, cells * (k + 1) / nth);
+    run(0, cells / nth);
+    for (auto& t : th) t.join();
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -540,6 +568,7 @@ int layout_arena(mope_ctx* c, const mope_tables_desc* t, const mope_model_desc* 
     if (dry) {
         bump.take<double>(max_cells);
         bump.take<double>(max_cells);
+        bump.take<double>(max_cells);
         bump.take<double>(t->F);
         bump.take<double>(t->F);
         bump.take<int8_t>(t->F);
@@ -578,6 +607,7 @@ int launch_tree_t(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) 
         ScopedTimer timer(c, st, &c->ev_tree);
         TreeParams tq = tp;
         tq.work_ctr = c->work_ctr;
+        tq.unit_rows = reinterpret_cast<unsigned long long*>(c->work_ctr + 8);
         tree_kernel<NTW><<<grid, NTHREADS, TileCfg<NTW>::SMEM_BYTES, st>>>(tq);
     }
     CUDA_TRY(cudaGetLastError());
@@ -620,6 +650,7 @@ int launch_tree4_t(mope_ctx* c, const Tree4Params& tp, int grid, cudaStream_t st
         ScopedTimer timer(c, st, &c->ev_tree);
         Tree4Params tq = tp;
         tq.work_ctr = c->work_ctr;
+        tq.unit_rows = reinterpret_cast<unsigned long long*>(c->work_ctr + 8);
         tree_kernel4<NTT, NFULL, SCALAR, ASCFAST><<<grid, NTHREADS, Cfg4<NTT>::SMEM_BYTES, st>>>(tq);
     }
     CUDA_TRY(cudaGetLastError());
@@ -918,6 +949,8 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
 
     c->last_gemm_ops = 0;
     c->last_identity_ops = 0;
+    CUDA_TRY(cudaMemsetAsync(c->work_ctr + 8, 0, sizeof(unsigned long long), st));   // executed row x unit counter of this eval
+    c->last_stream = st;
     hp_mark("fill_nan");
     // 3. chunk the valid walkers
     size_t gi0 = 0;
@@ -1303,15 +1336,19 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         const size_t cells = (size_t)pd.n_loci * pd.n_leaves;
         double* d_counts = tail.take<double>(std::max<size_t>(cells, 1));
         double* d_cov = tail.take<double>(std::max<size_t>(cells, 1));
+        double* d_lnc = tail.take<double>(std::max<size_t>(cells, 1));
         double* d_logp = tail.take<double>(F);
         double* d_log1mp = tail.take<double>(F);
         int8_t* d_cls = tail.take<int8_t>(F);
         int8_t* d_e0 = tail.take<int8_t>(F);
         int8_t* d_eN = tail.take<int8_t>(F);
         if (!tail.ok()) return cleanup_fail(fail(MOPE_E_NOMEM, "arena too small for the emission inputs"));
+        std::vector<double> lnc(cells);
         if (cells) {
+            host_lnchoose(pd.counts, pd.coverage, cells, lnc.data());
             CUDA_TRY_C(cudaMemcpyAsync(d_counts, pd.counts, cells * sizeof(double), cudaMemcpyHostToDevice, st));
             CUDA_TRY_C(cudaMemcpyAsync(d_cov, pd.coverage, cells * sizeof(double), cudaMemcpyHostToDevice, st));
+            CUDA_TRY_C(cudaMemcpyAsync(d_lnc, lnc.data(), cells * sizeof(double), cudaMemcpyHostToDevice, st));
         }
         CUDA_TRY_C(cudaMemcpyAsync(d_logp, logp.data(), F * sizeof(double), cudaMemcpyHostToDevice, st));
         CUDA_TRY_C(cudaMemcpyAsync(d_log1mp, log1mp.data(), F * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1319,7 +1356,7 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         CUDA_TRY_C(cudaMemcpyAsync(d_e0, e0.data(), F, cudaMemcpyHostToDevice, st));
         CUDA_TRY_C(cudaMemcpyAsync(d_eN, eN.data(), F, cudaMemcpyHostToDevice, st));
         EmissionParams ep{};
-        ep.counts = d_counts; ep.coverage = d_cov; ep.logp = d_logp; ep.log1mp = d_log1mp; ep.pclass = d_cls;
+        ep.counts = d_counts; ep.coverage = d_cov; ep.lnchoose = d_lnc; ep.logp = d_logp; ep.log1mp = d_log1mp; ep.pclass = d_cls;
         ep.asc_e0 = d_e0; ep.asc_eN = d_eN; ep.E = P.E;
         ep.L = P.L; ep.S = P.n_leaves; ep.R = P.R; ep.R_pad = P.R_pad; ep.F = F; ep.Fp = Fp;
         ep.perm = c->use_v4 ? 1 : 0;
@@ -1390,6 +1427,16 @@ int mope_b200_last_eval_stats(const mope_ctx* c, int64_t* gemm_ops, int64_t* ide
     if (!c) return fail(MOPE_E_INVALID, "null ctx");
     if (gemm_ops) *gemm_ops = c->last_gemm_ops;
     if (identity_ops) *identity_ops = c->last_identity_ops;
+    return 0;
+}
+
+int mope_b200_last_eval_unit_rows(mope_ctx* c, int64_t* unit_rows) {
+    if (!c || !unit_rows) return fail(MOPE_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->last_stream));
+    unsigned long long v = 0;
+    CUDA_TRY(cudaMemcpy(&v, c->work_ctr + 8, sizeof v, cudaMemcpyDeviceToHost));
+    *unit_rows = (int64_t)v;
     return 0;
 }
 
@@ -1510,8 +1557,9 @@ int mope_b200_leaf_likelihoods(mope_ctx* c, const double* counts, const double* 
     }
     Bump b;
     b.dry = true;
+    double* dlc = nullptr;
     auto carve = [&](Bump& bb, double*& dc, double*& dn, double*& dl, double*& dl1, int8_t*& cls, int8_t*& z, double*& E, double*& o) {
-        dc = bb.take<double>((size_t)L * S); dn = bb.take<double>((size_t)L * S);
+        dc = bb.take<double>((size_t)L * S); dn = bb.take<double>((size_t)L * S); dlc = bb.take<double>((size_t)L * S);
         dl = bb.take<double>(F); dl1 = bb.take<double>(F); cls = bb.take<int8_t>(F); z = bb.take<int8_t>(F);
         E = bb.take<double>((size_t)S * R_pad * Fp); o = bb.take<double>((size_t)L * S * F);
     };
@@ -1523,12 +1571,15 @@ int mope_b200_leaf_likelihoods(mope_ctx* c, const double* counts, const double* 
     carve(r, dc, dn, dl, dl1, cls, z, E, o);
     CUDA_TRY(cudaMemcpyAsync(dc, counts, (size_t)L * S * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dn, coverage, (size_t)L * S * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<double> lnc((size_t)L * S);
+    host_lnchoose(counts, coverage, (size_t)L * S, lnc.data());
+    CUDA_TRY(cudaMemcpyAsync(dlc, lnc.data(), (size_t)L * S * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dl, logp.data(), F * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dl1, log1mp.data(), F * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(cls, pclass.data(), F, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(z, zeros.data(), F, cudaMemcpyHostToDevice, st));
     EmissionParams ep{};
-    ep.counts = dc; ep.coverage = dn; ep.logp = dl; ep.log1mp = dl1; ep.pclass = cls; ep.asc_e0 = z; ep.asc_eN = z; ep.E = E;
+    ep.counts = dc; ep.coverage = dn; ep.lnchoose = dlc; ep.logp = dl; ep.log1mp = dl1; ep.pclass = cls; ep.asc_e0 = z; ep.asc_eN = z; ep.E = E;
     ep.L = L; ep.S = S; ep.R = L; ep.R_pad = R_pad; ep.F = F; ep.Fp = Fp;
     ep.perm = 0;
     const long long warps = (long long)S * R_pad;

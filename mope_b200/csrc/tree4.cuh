@@ -87,6 +87,7 @@ struct Tree4Params {
     double* uni_msg;
     int32_t n_uroot, canonical;
     int32_t* work_ctr;       // zeroed before the launch: next item to hand out (items differ in cost: identity branches)
+    unsigned long long* unit_rows;   // statistics: += real rows x GEMM units actually run through the tensor pipe (may be null)
 };
 
 struct Tree4Smem {
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         if (!no_copy && lane == 0 && warp < PF4 && warp < total_chunks) issue_next();
         __syncwarp();
         int crel = 0;   // chunks of this item consumed so far
+        int my_units = 0;   // GEMM units (branch x generation segment) this warp ran through the tensor pipe
         PROF_MARK(0)   // item setup
 
         for (int oi = 0; oi < p.n_ops; ++oi) {
@@ -444,6 +446,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 // a warp none of whose 8 rows blends this grid generation only keeps pace with the ring (its products would
                 // all be zero); the warp it shares the sub-partition's DMMA pipe with then runs the segment at full rate
                 const bool seg_active = (op.kind != 1) || __any_sync(0xffffffffu, wgt != 0.0);
+                my_units += seg_active ? 1 : 0;
                 uint32_t an[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // chained A values of the coming chunk (tcgen05.ld in flight)
                 if (op.leaf < 0) tmem_ld4_issue(t_chain, an);
                 for (int c = 0; c < nchunks; ++c) {
@@ -617,6 +620,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             PROF_MARK(4)   // post-op
         }  // ops
 
+        if (p.unit_rows != nullptr && lane == 0 && my_units > 0) {
+            const int real = max(0, min(8, p.R - (row0 + warp * 8)));
+            if (real > 0) atomicAdd(p.unit_rows, (unsigned long long)my_units * (unsigned)real);
+        }
         __syncthreads();   // rowval complete; every warp is done with the item's tables
         if (p.Yout == nullptr && !p.canonical && warp == 0) {
             double part = ts->rowval[lane] + ts->rowval[lane + 32];

@@ -7,8 +7,8 @@ The path shards two ways, both without any exchange insid
   of the per-walker results only if every rank needs the whole vector.
 * by LOCUS (large datasets) -- rows are independent given a walker's parameters.  Families are partitioned over the
   ranks (a family's loci, its ascertainment pseudo-rows and its count/Poisson terms stay together), every rank
-  evaluates ALL walkers on its rows, and the per-walker partial sums are combined with ONE all-reduce(sum) of
-  W float64 values (NCCL over NVLink on GPUs, gloo in the CPU tests).
+  evaluates ALL walkers on its rows, and the per-walker partial sums (with the walkers' status bits packed behind them)
+  are combined with ONE all-reduce(sum) (NCCL over NVLink on GPUs, gloo in the CPU tests).
 
 The prior box depends on the multiplier (age) range of ALL families (inference.py:154-258), so locus shards are
 built with the global range (`mult_bounds`).
@@ -48,18 +48,25 @@ def partition_families(family_of_locus: np.ndarray, families: np.ndarray, world:
     return groups
 
 
-def shard_pedigree_text(data_tsv: str, ages_tsv: str, world: int, rank: int) -> Tuple[str, str]:
-    """The rows of one pedigree's data / ages tables that belong to `rank` under the family partition."""
-    data = _model.read_table(data_tsv, True)
-    ages = _model.read_table(ages_tsv, True)
+def shard_pedigree(data, ages, world: int, rank: int):
+    """The rows of one pedigree's data / ages tables (DataFrames, or TSV text) that belong to `rank` under the family
+    partition, as DataFrames."""
+    data = _model.read_table(data, True)
+    ages = _model.read_table(ages, True)
     groups = partition_families(data["family"].values, ages["family"].values, world)
     if any(len(g) == 0 for g in groups):
         # every rank computes the same partition, so every rank raises here -- before any collective could hang
         raise ValueError("cannot shard {} families over {} ranks: some rank would own no family".format(
             len(ages["family"].values), world))
-    mine = set(groups[rank].tolist())
-    d = data[data["family"].isin(mine)]
-    a = ages[ages["family"].isin(mine)]
+    mine = groups[rank]
+    d = data[data["family"].isin(mine)].reset_index(drop=True)
+    a = ages[ages["family"].isin(mine)].reset_index(drop=True)
+    return d, a
+
+
+def shard_pedigree_text(data_tsv: str, ages_tsv: str, world: int, rank: int) -> Tuple[str, str]:
+    """shard_pedigree with TSV text out (the reference's file format)."""
+    d, a = shard_pedigree(data_tsv, ages_tsv, world, rank)
     dbuf, abuf = io.StringIO(), io.StringIO()
     d.to_csv(dbuf, sep="\t", index=False, na_rep="NA")
     a.to_csv(abuf, sep="\t", index=False, na_rep="NA")
@@ -86,10 +93,10 @@ def global_mult_bounds(tree_strs: Sequence[str], ages_tsvs: Sequence[str]):
 
 def build_locus_sharded(data_tsvs: Sequence[str], tree_strs: Sequence[str], ages_tsvs: Sequence[str], tables, rank: int, world: int,
                         **kw):
-    """An Inference over this rank's families (texts in, as `_inputs_are_text`), with the GLOBAL prior box."""
+    """An Inference over this rank's families (TSV texts or DataFrames in), with the GLOBAL prior box."""
     from .inference import Inference
     _names, lo, hi = global_mult_bounds(tree_strs, ages_tsvs)
-    local = [shard_pedigree_text(d, a, world, rank) for d, a in zip(data_tsvs, ages_tsvs)]
+    local = [shard_pedigree(d, a, world, rank) for d, a in zip(data_tsvs, ages_tsvs)]
     return Inference([l[0] for l in local], list(tree_strs), [l[1] for l in local], tables, _inputs_are_text=True,
                      mult_bounds=(lo, hi), **kw)
 
@@ -101,27 +108,55 @@ def _dist_device(group=None):
     return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
 
 
-def allreduce_partials(ll_partial: np.ndarray, status: Optional[np.ndarray] = None, group=None):
-    """Sum of the per-walker partial log-likelihoods over the ranks (the path's only collective): all-reduce(sum)
-    of W float64 values; walker status bits are OR-ed (max) the same way."""
+N_STATUS_BITS = 7   # MOPE_ST_* bits of include/mope_b200.h
+_PINNED, _PINNED_BUSY = {}, {}   # pinned staging of the status planes, by size
+
+
+def allreduce_partials_packed(ll_t, status: Optional[np.ndarray], group=None, packed=None):
+    """The path's only collective: ONE all-reduce(sum) over the ranks of a packed float64 buffer
+    [ W partial log-likelihoods | N_STATUS_BITS x W status bit planes ].  A walker's partial sum enters as 0 where this
+    rank flagged it; a bit plane sums to the number of ranks that set the bit (exact in float64), so the OR of the status
+    words falls out of the same reduction.  `ll_t` is a float64 tensor on the collective's device (CUDA for NCCL: the
+    reduction is enqueued behind the evaluation on the current stream, no host round trip before it).  Returns host arrays
+    (ll with NaN where any rank flagged the walker, OR-ed status)."""
     import torch
     import torch.distributed as dist
+    W = ll_t.shape[0]
+    n = W * (1 + N_STATUS_BITS)
+    if packed is None or packed.shape[0] < n or packed.device != ll_t.device:
+        packed = torch.empty(n, dtype=torch.float64, device=ll_t.device)
+    buf = packed[:n]
+    st = np.zeros(W, dtype=np.int32) if status is None else np.ascontiguousarray(status, dtype=np.int32)
+    planes = ((st[None, :] >> np.arange(N_STATUS_BITS, dtype=np.int32)[:, None]) & 1).astype(np.float64)   # [bits, W]
+    if ll_t.is_cuda:
+        pin = _PINNED.get(n - W)
+        if pin is None:
+            pin = _PINNED[n - W] = torch.empty(n - W, dtype=torch.float64, pin_memory=True)
+        else:
+            torch.cuda.current_stream().synchronize() if _PINNED_BUSY.get(n - W) else None
+        pin.numpy()[:] = planes.reshape(-1)
+        _PINNED_BUSY[n - W] = True
+        buf[W:].copy_(pin, non_blocking=True)
+    else:
+        buf[W:].copy_(torch.from_numpy(planes.reshape(-1)))
+    flagged = buf[W:].view(N_STATUS_BITS, W).sum(0) != 0
+    buf[:W].copy_(torch.where(flagged, torch.zeros_like(ll_t), ll_t))
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    host = buf.cpu().numpy()      # synchronises: the pinned staging buffer is free again
+    _PINNED_BUSY[n - W] = False
+    counts = host[W:].reshape(N_STATUS_BITS, W)
+    st_or = ((counts != 0).astype(np.int32) << np.arange(N_STATUS_BITS, dtype=np.int32)[:, None]).sum(0).astype(np.int32)
+    out = np.where(st_or != 0, np.nan, host[:W])
+    return out, st_or
+
+
+def allreduce_partials(ll_partial: np.ndarray, status: Optional[np.ndarray] = None, group=None):
+    """Host-array front end of allreduce_partials_packed (one collective)."""
+    import torch
     dev = _dist_device(group)
     t = torch.as_tensor(np.ascontiguousarray(ll_partial, dtype=np.float64)).to(dev)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    out = t.cpu().numpy()
-    if status is None:
-        return out
-    s = torch.as_tensor(np.ascontiguousarray(status, dtype=np.int32)).to(dev)
-    # bitwise OR over ranks, bit by bit (MAX on each bit plane keeps it exact on every backend)
-    acc = torch.zeros_like(s)
-    for bit in range(8):
-        plane = (s >> bit) & 1
-        dist.all_reduce(plane, op=dist.ReduceOp.MAX, group=group)
-        acc |= plane << bit
-    st = acc.cpu().numpy()
-    out = np.where(st != 0, np.nan, out)
-    return out, st
+    out, st = allreduce_partials_packed(t, status, group)
+    return out if status is None else (out, st)
 
 
 def allgather_walkers(ll_local: np.ndarray, n_walkers: int, group=None) -> np.ndarray:
@@ -152,8 +187,18 @@ def loglike_walker_sharded(inf, X: np.ndarray, group=None) -> np.ndarray:
 
 
 def loglike_locus_sharded(inf_local, X: np.ndarray, group=None):
-    """`inf_local` holds this rank's families (build_locus_sharded); returns the full-data log-likelihood of every
-    walker on all ranks."""
+    """`inf_local` holds this rank's families (build_locus_sharded); returns (log-likelihood of every walker on the full
+    data, OR-ed status) on all ranks.  Device path: the partial sums stay in HBM between the evaluation and the all-reduce;
+    the only host<->device traffic is the parameter vectors / root prior in and one read of the reduced buffer."""
+    eng = getattr(inf_local, "engine", None)
+    if eng is not None and hasattr(eng, "loglike_enqueue"):
+        X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
+        ll_t, status = eng.loglike_enqueue(X, inf_local.stationary_distributions)
+        packed = getattr(eng, "_packed_reduce_buf", None)
+        n = X.shape[0] * (1 + N_STATUS_BITS)
+        if packed is None or packed.shape[0] < n:
+            packed = eng._packed_reduce_buf = eng.torch.empty(n, dtype=eng.torch.float64, device=ll_t.device)
+        return allreduce_partials_packed(ll_t, status, group, packed)
     ll, status = inf_local.loglike_batch(X, raise_on_error=False, return_status=True)
     ll = np.where(status != 0, 0.0, ll)
     return allreduce_partials(ll, status, group)

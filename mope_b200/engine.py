@@ -166,6 +166,18 @@ class Engine:
         cut into `n_chunks`; while the device evaluates chunk i (enqueued, not awaited) the host computes stat_fn for
         chunk i+1.  One device->host read of the log-likelihoods at the end.  Returns (ll, status)."""
         torch = self.torch
+        out_dev, status = self.loglike_enqueue(params, stat_fn, n_chunks)
+        W = out_dev.shape[0]
+        with torch.cuda.device(self.device):
+            self._out_pin[:W].copy_(out_dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return self._out_pin[:W].numpy().copy(), status
+
+    def loglike_enqueue(self, params: np.ndarray, stat_fn, n_chunks: int = 4):
+        """As loglike_pipelined, but the log-likelihoods stay on the device: returns (CUDA float64 tensor [W] that the
+        current stream will have written, host status [W]) without synchronising.  The tensor is engine-owned scratch,
+        valid until the next evaluation."""
+        torch = self.torch
         params = np.ascontiguousarray(params, dtype=np.float64)
         W = params.shape[0]
         dev = "cuda:%d" % self.device
@@ -189,9 +201,7 @@ class Engine:
                 stat_pin_np[lo:hi] = stat_fn(params[lo:hi])
                 self._stat_dev[lo:hi].copy_(self._stat_pin[lo:hi], non_blocking=True)
                 status[lo:hi] = self.loglike_device(params[lo:hi], self._stat_dev[lo:hi], self._out_dev[lo:hi])
-            self._out_pin[:W].copy_(self._out_dev[:W], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return self._out_pin[:W].numpy().copy(), status
+        return self._out_dev[:W], status
 
     def loglike_device(self, params_host: np.ndarray, stat_dev, out_dev):
         """Device-resident variant: stat_dev [W, F] and out_dev [W] are CUDA float64 tensors.  Enqueue only."""
@@ -216,6 +226,13 @@ class Engine:
         g, i = C.c_int64(0), C.c_int64(0)
         _lib.check(self.lib.mope_b200_last_eval_stats(self.ctx, C.byref(g), C.byref(i)), "mope_b200_last_eval_stats")
         return g.value, i.value
+
+    def last_eval_unit_rows(self) -> int:
+        """Sum over the GEMM units the pruning kernel executed in the last evaluation of the unit's real rows
+        (2 * F^2 * this = executed flops); synchronises."""
+        v = C.c_int64(0)
+        _lib.check(self.lib.mope_b200_last_eval_unit_rows(self.ctx, C.byref(v)), "mope_b200_last_eval_unit_rows")
+        return int(v.value)
 
     def kernel_times(self):
         """(tree_ms, tree_launches, interp_ms, interp_launches) accumulated since the last call; synchronises."""

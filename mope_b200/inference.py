@@ -284,12 +284,21 @@ class Inference(object):
     def translate_positions(self, pos):
         """mope/_util.pyx:29-53: log10 -> natural scale for the chain file; drift within one decade of its lower bound is
         reported as 0 (point mass) with a NaN mutation rate; root parameters stay in log10."""
+        import math
         pos = np.asarray(pos, dtype=np.float64)
         ret = pos.copy()
         nv = self.num_varnames
         zero = pos[:, :nv] <= self.lower[:nv] + 1
-        ret[:, :nv] = np.where(zero, 0.0, 10 ** pos[:, :nv])
-        ret[:, nv:2 * nv] = np.where(zero, np.nan, 10 ** pos[:, nv:2 * nv])
+        # the reference's 10**x is C pow() on scalars; NumPy's vectorised power can differ from it in the last bit, which
+        # would show in the printed chain -- so: libm pow per element
+        for i in range(pos.shape[0]):
+            for j in range(nv):
+                if zero[i, j]:
+                    ret[i, j] = 0.0
+                    ret[i, j + nv] = np.nan
+                else:
+                    ret[i, j] = math.pow(10.0, pos[i, j])
+                    ret[i, j + nv] = math.pow(10.0, pos[i, j + nv])
         return ret
 
     @staticmethod

@@ -19,6 +19,8 @@ from . import newick
 
 def read_table(path_or_text, is_text: bool = False) -> pd.DataFrame:
     """TSV reader with the reference's options (inference.py:332-333, :510)."""
+    if isinstance(path_or_text, pd.DataFrame):   # already parsed (synthetic data sets are built as tables)
+        return path_or_text
     src = io.StringIO(path_or_text) if is_text else path_or_text
     return pd.read_csv(src, sep="\t", comment="#", na_values=["NA"], header=0)
 

@@ -9,20 +9,66 @@ implementations.
 from __future__ import annotations
 
 import io
-from dataclasses import dataclass
 from typing import List
 
 import numpy as np
 
 
-@dataclass
 class SyntheticPedigree:
-    data_tsv: str
-    tree: str
-    ages_tsv: str
-    leaf_names: List[str]
-    n_loci: int
-    n_fam: int
+    """One synthetic pedigree type: the data and ages tables (as the DataFrames the reference's pd.read_csv would give)
+    and the tree.  `data_tsv` / `ages_tsv` render the reference's TSV text on first use (the CPU reference arm and the
+    parity tests read files; a million-locus table is never rendered)."""
+
+    def __init__(self, data, tree: str, ages, leaf_names: List[str], n_loci: int = None, n_fam: int = None):
+        import pandas as pd
+        from . import model
+        self._data_tsv = data if isinstance(data, str) else None
+        self._ages_tsv = ages if isinstance(ages, str) else None
+        self.data = model.read_table(data, True) if isinstance(data, str) else data
+        self.ages = model.read_table(ages, True) if isinstance(ages, str) else ages
+        assert isinstance(self.data, pd.DataFrame) and isinstance(self.ages, pd.DataFrame)
+        self.tree = tree
+        self.leaf_names = list(leaf_names)
+        self.n_loci = int(self.data.shape[0] if n_loci is None else n_loci)
+        self.n_fam = int(self.ages.shape[0] if n_fam is None else n_fam)
+
+    @property
+    def data_tsv(self) -> str:
+        if self._data_tsv is None:
+            leaves = self.leaf_names
+            buf = io.StringIO()
+            cols = list(self.data.columns)
+            buf.write("\t".join(cols) + "\n")
+            x = self.data[leaves].values
+            cov = self.data[[l + "_n" for l in leaves]].values
+            fam = self.data["family"].values
+            for i in range(x.shape[0]):
+                row = [("NA" if np.isnan(x[i, j]) else "%d" % x[i, j]) for j in range(len(leaves))]
+                row += ["%d" % cov[i, j] for j in range(len(leaves))]
+                row.append("%d" % fam[i])
+                buf.write("\t".join(row) + "\n")
+            self._data_tsv = buf.getvalue()
+        return self._data_tsv
+
+    @property
+    def ages_tsv(self) -> str:
+        if self._ages_tsv is None:
+            a = self.ages
+            buf = io.StringIO()
+            buf.write("family\tmother_birth_age\tchild_age\tmother_age\n")
+            fam, mba, ca, ma = a["family"].values, a["mother_birth_age"].values, a["child_age"].values, a["mother_age"].values
+            for k in range(a.shape[0]):
+                buf.write("%d\t%.4f\t%.4f\t%.4f\n" % (fam[k], mba[k], ca[k], ma[k]))
+            self._ages_tsv = buf.getvalue()
+        return self._ages_tsv
+
+    def subset(self, n_loci: int) -> "SyntheticPedigree":
+        """The first n_loci loci and the families they belong to, same tree."""
+        n_loci = min(int(n_loci), self.data.shape[0])
+        d = self.data.iloc[:n_loci].reset_index(drop=True)
+        fams = set(d["family"].values.tolist())
+        a = self.ages[self.ages["family"].isin(fams)].reset_index(drop=True)
+        return SyntheticPedigree(d, self.tree, a, self.leaf_names)
 
 
 def balanced_tree(n_leaves: int = 16, rate_leaves: bool = False, rate_internal: bool = False, bottleneck: bool = False) -> str:
@@ -78,19 +124,16 @@ def make_dataset(n_loci: int, n_leaves: int = 16, tree: str = None, loci_per_fam
     x[dead, 0] = np.floor(cov[dead, 0] / 2)
     miss = rng.rand(n_loci, n_leaves) < missing_frac
     miss[:, 0] = False
-    buf = io.StringIO()
-    cols = leaves + [l + "_n" for l in leaves] + ["family"]
-    buf.write("\t".join(cols) + "\n")
-    for i in range(n_loci):
-        row = [("NA" if miss[i, j] else "%d" % x[i, j]) for j in range(n_leaves)]
-        row += ["%d" % cov[i, j] for j in range(n_leaves)]
-        row.append("%d" % fam_of_locus[i])
-        buf.write("\t".join(row) + "\n")
-    abuf = io.StringIO()
-    abuf.write("family\tmother_birth_age\tchild_age\tmother_age\n")
-    for k in range(n_fam):
-        abuf.write("%d\t%.4f\t%.4f\t%.4f\n" % (k, mba[k], ca[k], ma[k]))
-    return SyntheticPedigree(buf.getvalue(), tree, abuf.getvalue(), leaves, n_loci, n_fam)
+    import pandas as pd
+    xs = np.where(miss, np.nan, x)
+    data = pd.DataFrame(np.concatenate((xs, cov.astype(np.float64)), axis=1), columns=leaves + [l + "_n" for l in leaves])
+    data["family"] = fam_of_locus.astype(np.int64)
+
+    def as_written(v):   # the value a reader of the TSV gets back ("%.4f")
+        return np.char.mod("%.4f", v).astype(np.float64)
+    ages = pd.DataFrame({"family": np.arange(n_fam, dtype=np.int64), "mother_birth_age": as_written(mba),
+                         "child_age": as_written(ca), "mother_age": as_written(ma)})
+    return SyntheticPedigree(data, tree, ages, leaves, n_loci, n_fam)
 
 
 def walkers_in_prior_box(lower: np.ndarray, upper: np.ndarray, n_walkers: int, seed: int = 1, shrink: float = 0.0) -> np.ndarray:

@@ -43,7 +43,12 @@ PATCHES = [
     ("simulate.py", r"^from scipy\.misc import comb", "from scipy.special import comb"),
     # pandas >= 3 hands out read-only buffers; the typed memoryview in _likes needs a writable one
     ("ascertainment.py", r"counts = asc_ages\['count'\]\.values", "counts = np.array(asc_ages['count'].values)"),
+    # inspect.getargspec left the standard library in Python 3.11 (used by run_mcmc to pick emcee's store keyword)
+    ("inference.py", r"inspect\.getargspec\(", "inspect.getfullargspec("),
 ]
+
+# bump when the patch list or the shims change: an existing install with another version is rebuilt
+INSTALL_VERSION = "2"
 
 INIT_PY = "inf_data = None\n__version__ = '0.5.1'\n"
 
@@ -88,7 +93,7 @@ def install(reference: str = "/root/reference", force: bool = False) -> str:
     if not os.path.isdir(src_pkg):
         raise FileNotFoundError(src_pkg)
     stamp = os.path.join(DEST, ".installed")
-    if os.path.exists(stamp) and not force:
+    if os.path.exists(stamp) and not force and open(stamp).read().strip() == INSTALL_VERSION:
         return DEST
     if os.path.isdir(DEST):
         shutil.rmtree(DEST)
@@ -108,7 +113,7 @@ def install(reference: str = "/root/reference", force: bool = False) -> str:
     _patch(os.path.join(DEST, "mope"))
     _build(DEST)
     with open(stamp, "w") as fout:
-        fout.write("ok\n")
+        fout.write(INSTALL_VERSION + "\n")
     return DEST
 
 

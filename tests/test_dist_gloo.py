@@ -50,7 +50,14 @@ def _worker(rank, world, port, case_name, nvec, q):
             d, a = mdist.shard_pedigree_text(ped["data"], ped["ages"], world, rank)
             local_case["peds"].append(dict(data=d, tree=ped["tree"], ages=a))
         inf_local = _OracleAsInference(H.oracle_inference(local_case, tb))
-        total, st = mdist.loglike_locus_sharded(inf_local, X)
+        calls = []
+        real_all_reduce = tdist.all_reduce
+        tdist.all_reduce = lambda *a, **k: (calls.append(1), real_all_reduce(*a, **k))[1]
+        try:
+            total, st = mdist.loglike_locus_sharded(inf_local, X)
+        finally:
+            tdist.all_reduce = real_all_reduce
+        assert len(calls) == 1, "the locus-sharded evaluation must issue exactly one collective, saw %d" % len(calls)
         ref = out[case_name + "/loglike"][:nvec]
         rel = np.abs(total - ref) / np.abs(ref)
         assert rel.max() < 1e-11, rel
@@ -64,6 +71,11 @@ def _worker(rank, world, port, case_name, nvec, q):
         st = np.array([0, 1 if rank == 0 else 0, 4 if rank == 1 else 0, 0], dtype=np.int32)
         tot, sst = mdist.allreduce_partials(ll, st)
         assert list(sst) == [0, 1, 4, 0] and np.isnan(tot[1]) and np.isnan(tot[2]) and tot[0] == 1.0 and tot[3] == 7.0
+        # a NaN partial of a flagged walker must not poison the sum of the others; every status bit survives the packing
+        ll2 = np.array([np.nan if rank == 0 else 5.0, 2.0])
+        st2 = np.array([(64 | 32 | 2) if rank == 0 else 16, 0], dtype=np.int32)
+        tot2, sst2 = mdist.allreduce_partials(ll2, st2)
+        assert list(sst2) == [64 | 32 | 16 | 2, 0] and np.isnan(tot2[0]) and tot2[1] == 4.0
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback

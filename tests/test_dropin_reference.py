@@ -1,0 +1,155 @@
+"""The drop-in, driven by the reference itself: the UNMODIFIED reference (baseline/_ref, installed by
+oracle/install_ref.py) runs its own Inference.run_mcmc (mope/inference.py:1322-1363) once on its CPU path (pool=None) and
+once with `pool=GpuPool(gpu_inference)` -- the plug-in point INTEGRATION.md documents -- and the two chain files must agree.
+Plus: the chain-file helpers against the reference's Cython originals, and tables.load on a master file in the
+reference's HDF5 layout (read through the oracle's h5py stand-in)."""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+TB = H.load_tables()
+CASES = H.load_cases()
+OUT = H.load_outputs()
+
+
+def _activate_ref():
+    from oracle import install_ref
+    if not install_ref.activate():
+        pytest.skip("baseline/_ref is not installed (python oracle/install_ref.py)")
+
+
+def _write_master(path, mats, axis, axis_name, us, extra):
+    """A master table file in the reference's layout (generate_transitions.py:242-295): one dataset per grid point with
+    attrs N, gen|Nb, u (+ s, v for drift), file attrs frequencies / breaks -- written through the h5py stand-in."""
+    import h5py
+    with h5py.File(path, "w") as f:
+        f.attrs["frequencies"] = TB["freqs"]
+        f.attrs["breaks"] = TB["breaks"]
+        f.attrs["N"] = int(TB["N"])
+        k = 0
+        for i, a in enumerate(axis):
+            for j, u in enumerate(us):
+                ds = f.create_dataset("P%d" % k, data=mats[i, j])
+                ds.attrs["N"] = int(TB["N"])
+                ds.attrs[axis_name] = int(a)
+                ds.attrs["u"] = float(u)
+                for kk, vv in extra.items():
+                    ds.attrs[kk] = vv if kk != "v" else float(u)
+                k += 1
+
+
+@pytest.fixture(scope="module")
+def master_files(tmp_path_factory):
+    _activate_ref()
+    d = tmp_path_factory.mktemp("tables")
+    drift, bot = str(d / "drift_master.h5"), str(d / "bot_master.h5")
+    _write_master(drift, TB["drift"], TB["gens"], "gen", TB["us"], {"s": 0.0, "v": None})
+    _write_master(bot, TB["bot"], TB["nbs"], "Nb", TB["bot_us"], {})
+    return drift, bot
+
+
+def test_tables_load_reads_master_files(master_files):
+    """mope_b200.tables.load on the files `mope run` is given (HDF5 master files of the drift and bottleneck grids)."""
+    from mope_b200 import tables
+    tb = tables.load(*master_files)
+    np.testing.assert_array_equal(tb.drift, TB["drift"])
+    np.testing.assert_array_equal(tb.bot, TB["bot"])
+    np.testing.assert_array_equal(tb.gens, TB["gens"])
+    np.testing.assert_array_equal(tb.us, TB["us"])
+    np.testing.assert_array_equal(tb.nbs, TB["nbs"])
+    np.testing.assert_array_equal(tb.bot_us, TB["bot_us"])
+    np.testing.assert_array_equal(tb.freqs, TB["freqs"])
+    assert tb.N == float(TB["N"]) and tables.load(master_files[0]).bot is None
+
+
+def test_chain_file_helpers_byte_identical_to_reference():
+    """Inference.print_csv_lines / translate_positions against mope/_util.pyx:17-53 on the same arrays: the chain file a
+    run writes is byte-compatible with what `mope make-figures` / `mope acceptance` parse."""
+    _activate_ref()
+    from mope import _util
+    from mope_b200.inference import Inference
+    rng = np.random.RandomState(3)
+    nv = 7
+    lower = np.concatenate((rng.uniform(-5, -3, nv), np.full(nv, -8.0), (-9, -9)))
+    pos = np.concatenate((lower[None, :nv] + rng.uniform(0, 3, (40, nv)), rng.uniform(-8, -1, (40, nv)), rng.uniform(-9, 0, (40, 2))), axis=1)
+    pos[5, 2] = lower[2] + 1.0            # exactly on the point-mass boundary
+    pos[6, 0] = lower[0] + 0.999999
+    lnp = rng.uniform(-1e5, -1, 40)
+    lnp[3] = -np.inf
+    fake = type("F", (), {"num_varnames": nv, "lower": lower})()
+    ours = Inference.translate_positions(fake, pos)
+    ref = np.asarray(_util.translate_positions(pos.copy(), lower, nv))
+    np.testing.assert_array_equal(ours, ref)
+    a, b = io.StringIO(), io.StringIO()
+    Inference.print_csv_lines(ours, lnp, file=a)
+    with contextlib.redirect_stdout(b):
+        _util.print_csv_lines(ref, lnp)
+    assert a.getvalue() == b.getvalue() and a.getvalue().count("\n") == 40
+
+
+def _chain(text):
+    body = [l for l in text.splitlines() if l and not l.startswith("#")]
+    header, rows = body[0], body[1:]
+    return header, np.array([[float(t) for t in r.split("\t")] for r in rows])
+
+
+@pytest.mark.gpu
+def test_reference_run_mcmc_with_gpu_pool(master_files, tmp_path):
+    """mcmc.run_mcmc's call (mope/mcmc.py:65-108 -> Inference.run_mcmc) with the GPU pool plugged in."""
+    _activate_ref()
+    import emcee                                   # the stand-in under baseline/_ref/shims (emcee-style wrapper objects)
+    from mope import inference as refinf
+    from mope_b200 import GpuPool, Inference
+    case = CASES["example_both"]
+    ped = case["peds"][0]
+    paths = {}
+    for key in ("data", "tree", "ages"):
+        paths[key] = str(tmp_path / (key + ".txt"))
+        with open(paths[key], "w") as f:
+            f.write(ped[key])
+    kw = dict(true_parameters=None, start_from="prior", data_are_freqs=False, genome_size=16569, min_freq=0.001,
+              poisson_like_penalty=1.0, log_unif_drift=True, lower_drift_limit=1e-3, upper_drift_limit=3, min_phred_score=None)
+    ref = refinf.Inference(data_files=[paths["data"]], tree_files=[paths["tree"]], age_files=[paths["ages"]],
+                           transitions_file=master_files[0], bottleneck_file=master_files[1], **kw)
+    # the GPU Inference reads the very same files
+    gpu = Inference([paths["data"]], [paths["tree"]], [paths["ages"]], master_files[0], bottleneck_file=master_files[1],
+                    log_unif_drift=True)
+    try:
+        assert gpu.header == ref.header and gpu.ndim == ref.ndim
+        np.testing.assert_allclose(gpu.lower, ref.lower, rtol=1e-15)
+        nw, nit = 2 * ref.ndim, 3
+        p0 = np.random.RandomState(5).uniform(0.6 * ref.lower + 0.4 * ref.upper, 0.4 * ref.lower + 0.6 * ref.upper, (nw, ref.ndim))
+
+        def run(pool):
+            emcee.EnsembleSampler.default_seed = 1234
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                ref.run_mcmc(nit, nw, chain_alpha=1.4, init_pos=p0.copy(), pool=pool)
+            return buf.getvalue()
+
+        cpu_text = run(None)
+        launches0 = gpu.engine.launch_count()
+        pool = GpuPool(gpu)
+        calls = []
+        real = gpu.log_posterior_batch
+        gpu.log_posterior_batch = lambda X: (calls.append(np.shape(X)), real(X))[1]
+        gpu_text = run(pool)
+        # one batched device call per emcee pool.map: the initial ensemble, then two half-steps per iteration
+        assert calls == [(nw, ref.ndim)] + [(nw // 2, ref.ndim)] * (2 * nit)
+        assert gpu.engine.launch_count() > launches0
+        h1, c1 = _chain(cpu_text)
+        h2, c2 = _chain(gpu_text)
+        assert h1 == h2 == ref.header and c1.shape == c2.shape == (nw * nit, ref.ndim + 1)
+        # same accept/reject decisions -> identical positions; log-posteriors within the parity bar
+        np.testing.assert_array_equal(np.nan_to_num(c1[:, 1:], nan=-1.0), np.nan_to_num(c2[:, 1:], nan=-1.0))
+        rel = np.abs(c1[:, 0] - c2[:, 0]) / np.abs(c1[:, 0])
+        assert rel.max() <= 1e-10, rel.max()
+        assert len({tuple(r) for r in c1[:, 1:3]}) > nw       # the chain moved
+    finally:
+        gpu.close()
