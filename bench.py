@@ -294,13 +294,13 @@ def cpu_throughput(X, n_loci, cores, steps, warmup):
     return X.shape[0] * n_loci / dt, dt, np.array(vals)
 
 
-def reference_parity(ds, tb, ref_tables, X, n_loci_sample, workdir, device, label):
+def reference_parity(ds, tb, ref_tables, X, n_loci_sample, workdir, device, label, max_walkers=16):
     """Parity of the GPU path against the reference's own code on a sample: the first `n_loci_sample` loci (whole
     families) of the configuration's dataset, the configuration's tables, the first walkers of its ensemble.  Both
     implementations evaluate the same sample; returns the dict that goes into the bench line."""
     from mope_b200 import Inference
     cores = os.cpu_count() or 1
-    nw = int(min(X.shape[0], max(8, min(cores, 16))))
+    nw = int(min(X.shape[0], max(8, min(cores, max_walkers))))
     sub = ds.subset(n_loci_sample)
     t0 = time.perf_counter()
     kind = build_cpu_inference(sub, ref_tables, workdir)
@@ -562,7 +562,7 @@ def run_extra_config(D, name, base_tb, workdir, peak, do_cpu, steps_cap):
     elif name == "cfg5":
         loci, W, tree = 1000, 512, synth.balanced_tree(16)
         tb = generate.generate_tables(N=1000, breaks=(0.5, 1e-9), gens=CFG5_GENS, us=CFG5_US, device=D.device)
-        tag, n_sample = "cfg5", 30
+        tag, n_sample = "cfg5", 6      # the reference needs ~1 s per (row, walker) at F = 1001: keep the sample to seconds
         desc = "cfg5: F=1001 (WF N=1000, every count its own bin), L=1000 loci x 16 tissues, B=30 fixed-length branches, W=512 walkers/GPU, walker-sharded, 16x8 drift grid"
     else:
         raise ValueError(name)
@@ -621,7 +621,7 @@ def run_extra_config(D, name, base_tb, workdir, peak, do_cpu, steps_cap):
     torch.cuda.empty_cache()
     if do_cpu and D.world == 1 and D.rank == 0:
         parity = reference_parity(ds, tb, RefTables(tb, workdir, tag) if tag != "main" else run_extra_config.main_ref_tables,
-                                  X, n_sample, workdir, D.local_rank, name)
+                                  X, n_sample, workdir, D.local_rank, name, max_walkers=8 if name == "cfg5" else 16)
     if D.rank != 0:
         return None
     out = {"name": name, "workload": desc, "n_gpus": D.world, "scaling": "strong" if name == "cfg4" else "weak",

@@ -55,6 +55,7 @@ extern "C" {
 #define MOPE_ST_NB_TOO_LARGE 16     /* transition_data_bottleneck.py:121-123 */
 #define MOPE_ST_NOT_FINITE 32       /* transition_data_2d.py:135-136,158-161 */
 #define MOPE_ST_NO_BOTTLENECK_TABLE 64 /* likelihoods.py:381-382 */
+#define MOPE_ST_SKIPPED 128         /* device-resident evaluation only: prior = -inf, likelihood not evaluated (inference.py:1148-1149) */
 
 typedef struct mope_ctx mope_ctx;
 
@@ -73,6 +74,8 @@ typedef struct {
     const double* bot_us;  /* [n_bot_us] ascending */
     double N;              /* Wright-Fisher population size of the tables */
     const double* freqs;   /* [F] bin frequencies */
+    const int32_t* breaks; /* [F] first Wright-Fisher state (0..N) of every frequency bin, ascending from 0 (the file attribute
+                            * `breaks`, generate_transitions.py:133-192); NULL = no device root prior (mope_b200_root_prior) */
 } mope_tables_desc;
 
 /* One pedigree type (data file + tree + ages file) after the reference's init-time processing
@@ -141,6 +144,61 @@ int mope_b200_eval(mope_ctx* ctx, const double* params, const double* stat, int 
 int mope_b200_eval_device(mope_ctx* ctx, const double* params_host, const double* stat_dev, int n_walkers,
                           void* workspace, size_t workspace_bytes, void* stream,
                           double* out_ll_dev, int32_t* out_status_host);
+
+/* Root (stationary) distribution of every walker on the device: likelihoods.get_stationary_distribution_double_beta
+ * (mope/likelihoods.py:27-60) for alphabeta, polyprob = 10**x[-2:] (mope/inference.py:824-827).
+ *   params_dev    device [n_walkers][ndim], the vectors mope_b200_eval receives (only the last two columns are read)
+ *   out_stat_dev  device [n_walkers][F], usable as the `stat_dev` argument of mope_b200_eval_device
+ * Every cell mass is integrated directly instead of being taken as a difference of two incomplete-beta values, so it
+ * carries ~2e-15 relative error for any ab; the reference's own cell masses lose digits as ab -> 0 (relative error
+ * ~1e-16 / (ab * cell width): 3e-8 at ab = 1e-5, 3e-4 at ab = 1e-9), which is why the host wrapper keeps SciPy's betainc
+ * for walkers with ab < 1e-6 when bit-level agreement with the reference is wanted.  Enqueues only.  Needs
+ * mope_tables_desc.breaks. */
+int mope_b200_root_prior(mope_ctx* ctx, const double* params_dev, int n_walkers, void* stream, double* out_stat_dev);
+
+/* Device-resident evaluation: the same computation as mope_b200_eval with NOTHING on the host -- the parameter vectors stay
+ * in HBM and the per-walker interpolation plans (range checks, searchsorted, bilinear weights) are derived by a kernel.
+ *   params_dev      device [n_walkers][ndim] (sign-folded log10 parameters, as for mope_b200_eval)
+ *   stat_dev        device [n_walkers][F] root distributions, or NULL: computed here by the kernel of mope_b200_root_prior
+ *   lnprior_dev     device [n_walkers] or NULL; walkers whose entry is -inf (or NaN) are skipped (status MOPE_ST_SKIPPED)
+ *   out_ll_dev      device [n_walkers]; NaN for walkers with a non-zero status
+ *   out_status_dev  device [n_walkers] MOPE_ST_* bits
+ * The matrix pool is laid out statically (every walker owns the worst-case number of blocks), so the workspace must hold
+ * at least one walker at that size: mope_b200_workspace_bytes gives it.  Enqueues only; no host synchronisation, no
+ * host<->device copy. */
+int mope_b200_eval_resident(mope_ctx* ctx, const double* params_dev, const double* stat_dev, const double* lnprior_dev,
+                            int n_walkers, void* workspace, size_t workspace_bytes, void* stream,
+                            double* out_ll_dev, int32_t* out_status_dev);
+
+/* Ensemble sampler on the device: one half-step of emcee's stretch move (what mope's Inference.run_mcmc iterates,
+ * mope/inference.py:1353-1356, with `a` = --chain-alpha), including Inference.log_posterior's sign folding and box prior
+ * (mope/inference.py:1132-1149, 1055-1110) and the likelihood of the proposals (mope_b200_eval_resident).  All pointers
+ * are device pointers owned by the caller; nothing is copied to or from the host and the call only enqueues.
+ * The ensemble is split into walkers [0, n/2) and [n/2, n); which_half = 0 moves the first half against the second. */
+typedef struct {
+    double* pos;             /* [n_walkers][ndim] positions (log10 parameters as emcee holds them, not sign-folded) */
+    double* lnprob;          /* [n_walkers] log posterior of pos */
+    int64_t* naccept;        /* [n_walkers] accepted proposals so far */
+    double* q;               /* scratch [n_walkers/2][ndim] proposals */
+    double* folded;          /* scratch [n_walkers/2][ndim] sign-folded proposals */
+    double* factor;          /* scratch [n_walkers/2] */
+    double* lnprior;         /* scratch [n_walkers/2] */
+    double* ll;              /* scratch [n_walkers/2] */
+    int32_t* status;         /* scratch [n_walkers/2] MOPE_ST_* bits of the proposals' evaluation */
+    const double* lower;     /* [ndim] prior box (Inference.lower / upper) */
+    const double* upper;
+    const double* prior_slope; /* [ndim] log prior inside the box = prior_const + sum_d prior_slope[d] * x[d] */
+    double prior_const;
+    const double* zu;        /* [n_walkers/2] uniforms for z, or NULL: counter-based Philox4x32-10 keyed by seed, step */
+    const int32_t* partner;  /* [n_walkers/2] partner index within the other half (required when zu is given) */
+    const double* au;        /* [n_walkers/2] uniforms for the accept test, or NULL: Philox */
+    uint64_t seed, step;     /* Philox key / counter; step must differ for every half-step of a chain */
+    double a;                /* stretch scale */
+    int32_t n_walkers;
+} mope_sampler_state;
+
+int mope_b200_mcmc_halfstep(mope_ctx* ctx, const mope_sampler_state* state, int which_half,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of kernels this library launched since the context was created. */
 int64_t mope_b200_launch_count(const mope_ctx* ctx);

@@ -34,7 +34,7 @@ class TablesDesc(C.Structure):
                 ("drift", C.POINTER(C.c_double)), ("gens", C.POINTER(C.c_double)), ("us", C.POINTER(C.c_double)),
                 ("n_nbs", C.c_int32), ("n_bot_us", C.c_int32),
                 ("bot", C.POINTER(C.c_double)), ("nbs", C.POINTER(C.c_double)), ("bot_us", C.POINTER(C.c_double)),
-                ("N", C.c_double), ("freqs", C.POINTER(C.c_double))]
+                ("N", C.c_double), ("freqs", C.POINTER(C.c_double)), ("breaks", C.POINTER(C.c_int32))]
 
 
 class PedigreeDesc(C.Structure):
@@ -54,9 +54,17 @@ class ModelDesc(C.Structure):
                 ("poisson_like_penalty", C.c_double)]
 
 
+class SamplerState(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("lnprob", C.c_void_p), ("naccept", C.c_void_p), ("q", C.c_void_p), ("folded", C.c_void_p),
+                ("factor", C.c_void_p), ("lnprior", C.c_void_p), ("ll", C.c_void_p), ("status", C.c_void_p),
+                ("lower", C.c_void_p), ("upper", C.c_void_p), ("prior_slope", C.c_void_p), ("prior_const", C.c_double),
+                ("zu", C.c_void_p), ("partner", C.c_void_p), ("au", C.c_void_p),
+                ("seed", C.c_uint64), ("step", C.c_uint64), ("a", C.c_double), ("n_walkers", C.c_int32)]
+
+
 # every symbol include/mope_b200.h declares
 SYMBOLS = ["mope_b200_arena_bytes", "mope_b200_create", "mope_b200_destroy", "mope_b200_workspace_bytes",
-           "mope_b200_eval", "mope_b200_eval_device", "mope_b200_launch_count", "mope_b200_schedule_stats", "mope_b200_last_eval_stats", "mope_b200_last_eval_unit_rows", "mope_b200_set_profiling",
+           "mope_b200_eval", "mope_b200_eval_device", "mope_b200_eval_resident", "mope_b200_mcmc_halfstep", "mope_b200_root_prior", "mope_b200_launch_count", "mope_b200_schedule_stats", "mope_b200_last_eval_stats", "mope_b200_last_eval_unit_rows", "mope_b200_set_profiling",
            "mope_b200_kernel_times", "mope_b200_fp64_peak", "mope_b200_transition_matrix",
            "mope_b200_leaf_likelihoods", "mope_b200_branch_update", "mope_b200_non_asc_probs", "mope_b200_beta_cdf_table",
            "mope_b200_last_error", "mope_b200_version"]
@@ -69,6 +77,7 @@ ST_MESSAGES = {
     16: "bottleneck size too large",
     32: "scaled_time is not finite",
     64: "pre-computed bottleneck data needed",
+    128: "prior is -inf (likelihood not evaluated)",
 }
 
 _lib = None
@@ -91,6 +100,9 @@ def lib():
     L.mope_b200_workspace_bytes.argtypes = [vp, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.mope_b200_eval.argtypes = [vp, dp, dp, C.c_int, vp, C.c_size_t, vp, dp, ip, dp, dp]
     L.mope_b200_eval_device.argtypes = [vp, dp, vp, C.c_int, vp, C.c_size_t, vp, vp, ip]
+    L.mope_b200_root_prior.argtypes = [vp, vp, C.c_int, vp, vp]
+    L.mope_b200_eval_resident.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_size_t, vp, vp, vp]
+    L.mope_b200_mcmc_halfstep.argtypes = [vp, C.POINTER(SamplerState), C.c_int, vp, C.c_size_t, vp]
     L.mope_b200_launch_count.argtypes = [vp]
     L.mope_b200_launch_count.restype = C.c_int64
     L.mope_b200_schedule_stats.argtypes = [C.POINTER(ModelDesc), C.c_int, C.c_int, ip]

@@ -94,6 +94,7 @@ struct TreeParams {
     int32_t debug;           // measurement only: 1 = skip the MMAs (data movement only), 2 = skip the copies (MMAs only)
     int32_t* work_ctr;       // zeroed before the launch: next item to hand out
     unsigned long long* unit_rows;   // statistics: += real rows x GEMM units (branch x generation segment) executed (may be null)
+    const int32_t* wstatus;  // device-planned evaluations: per-walker MOPE_ST_* bits, non-zero = skip the walker (may be null)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -171,164 +172,6 @@ __global__ void emission_kernel(EmissionParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// interpolation of transition matrices (transition_data_2d.py:195-238, _interp.pyx:30-35, _util.pyx:129-148).
-// HBM-bound: per matrix 4 (or 2) F x F source matrices are read once and one Fp x Fp block is written once.
-// Output block: Fp x Fp matrix (zero padded) followed by the BLK_EXTRA vectors described at the top of this file.
-//
-// One CTA per (matrix, tile of `rows` consecutive matrix rows).  The rows of a tile are one contiguous run of
-// rows * F doubles in every source matrix, so
-//   phase 1  all threads stream the run of each source with fully coalesced loads (16 independent loads per thread in
-//            flight), blend in the reference's evaluation order, clamp, and park the tile in shared memory;
-//   phase 2  thread r walks row r of the parked tile: the reference's left-to-right row sum (_util.pyx:144-145) is a
-//            dependent chain of F additions that cannot be re-associated, so the tile runs `rows` independent chains side by
-//            side (row stride odd in doubles: no bank conflicts) while the other CTAs of the SM are in their memory phases;
-//   phase 3  one warp per row divides (when the sum exceeds 1), writes the row coalesced in the (optionally k-permuted)
-//            layout, and forms the low / high column sums of the stored row.
-// ------------------------------------------------------------------------------------------------
-constexpr int INTERP_THREADS = 256;
-__host__ __device__ __forceinline__ int interp_row_stride(int F) { return F | 1; }   // doubles, odd
-// rows per tile: as many as fit ~51 KB of shared memory (4 CTAs per SM), at most 32
-__host__ __device__ __forceinline__ int interp_rows_per_tile(int F) {
-    int rows = 32;
-    while (rows > 1 && (size_t)rows * interp_row_stride(F) * sizeof(double) > 52 * 1024) rows >>= 1;
-    return rows;
-}
-
-__global__ void __launch_bounds__(INTERP_THREADS, 4)
-interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __restrict__ tables, double* __restrict__ pool, int F, int Fp,
-              int perm, const int8_t* __restrict__ asc_mask /* [2][F]: e0 then eN, may be null */, int rows, int tiles_per_job,
-              unsigned div_magic /* ceil(2^32 / F) */) {
-    extern __shared__ double tile[];          // [rows][FS]
-    __shared__ double s_sum[32];
-    const int FS = interp_row_stride(F);
-    const int j = blockIdx.x / tiles_per_job;
-    const int i0 = (blockIdx.x - j * tiles_per_job) * rows;   // first matrix row of the tile
-    const InterpJob jb = jobs[j];
-    double* dst0 = pool + jb.dst;
-    double* dsum = dst0 + (size_t)Fp * Fp;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nreal = min(rows, F - i0);      // real (non-padding) rows of the tile, may be <= 0
-    const bool ident = (jb.flags & 2) != 0;   // identity short-cut (transition_data_2d.py:184-187)
-    const bool two = (jb.flags & 4) != 0;
-    const bool check = (jb.flags & 1) != 0;
-
-    if (nreal > 0 && !ident) {
-        // ---- phase 1: stream, blend, clamp ----
-        const int n = nreal * F;
-        const size_t off = (size_t)i0 * F;
-        const double* __restrict__ q11 = tables + jb.src[0] + off;
-        const double* __restrict__ q12 = tables + jb.src[1] + off;
-        const double* __restrict__ q21 = tables + jb.src[2] + off;
-        const double* __restrict__ q22 = tables + jb.src[3] + off;
-        const double w11 = jb.w[0], w12 = jb.w[1], w21 = jb.w[2], w22 = jb.w[3];
-        constexpr int U = 4;
-        for (int base = threadIdx.x; base < n; base += U * INTERP_THREADS) {
-            double a[U], b[U], c[U], d[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = base + u * INTERP_THREADS;
-                if (e < n) {
-                    a[u] = __ldg(q11 + e);
-                    b[u] = __ldg(q12 + e);
-                    if (!two) { c[u] = __ldg(q21 + e); d[u] = __ldg(q22 + e); }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = base + u * INTERP_THREADS;
-                if (e < n) {
-                    double v;
-                    if (two) {
-                        v = __dadd_rn(__dmul_rn(a[u], w11), __dmul_rn(b[u], w12));
-                    } else {
-                        // ((q11*w11 + q21*w21) + q12*w12) + q22*w22
-                        v = __dadd_rn(__dmul_rn(a[u], w11), __dmul_rn(c[u], w21));
-                        v = __dadd_rn(v, __dmul_rn(b[u], w12));
-                        v = __dadd_rn(v, __dmul_rn(d[u], w22));
-                    }
-                    if (check) {
-                        if (v > 1.0) v = 1.0;
-                        else if (v < 0.0) v = 0.0;
-                    }
-                    const int r = (int)__umulhi((unsigned)e, div_magic);   // e / F (exact for e < 2^16)
-                    tile[r * FS + (e - r * F)] = v;
-                }
-            }
-        }
-        __syncthreads();
-        // ---- phase 2: the reference's sequential row sums, one chain per thread ----
-        if (threadIdx.x < nreal) {
-            const double* row = tile + threadIdx.x * FS;
-            double s = 0.0;
-#pragma unroll 8
-            for (int f = 0; f < F; ++f) s = __dadd_rn(s, row[f]);
-            s_sum[threadIdx.x] = s;
-        }
-        __syncthreads();
-    }
-
-    // ---- phase 3: one warp per row ----
-    // column masks of the low / high sums for this lane's columns f = lane + 32 k (bit k), the same for every row
-    unsigned m_lo = 0, m_hi = 0;
-    if (asc_mask)
-        for (int f = lane, k = 0; f < F; f += 32, ++k) {
-            m_lo |= (asc_mask[f] ? 1u : 0u) << (k & 31);
-            m_hi |= (asc_mask[F + f] ? 1u : 0u) << (k & 31);
-        }
-    const bool masks_in_regs = F <= 1024;   // 32 columns per lane
-    for (int r = warp; r < rows; r += INTERP_THREADS / 32) {
-        const int i = i0 + r;
-        if (i >= Fp) break;
-        double* dst = dst0 + (size_t)i * Fp;
-        if (i >= F) {  // zero padding rows
-            for (int f = lane; f < Fp; f += 32) dst[f] = 0.0;
-            if (lane == 0) { dsum[i] = 0.0; dsum[Fp + i] = 0.0; dsum[2 * Fp + i] = 0.0; }
-            continue;
-        }
-        if (ident) {
-            for (int f = lane; f < Fp; f += 32) dst[perm ? kperm(f) : f] = (f == i) ? 1.0 : 0.0;
-            if (lane == 0) {
-                dsum[i] = 1.0;
-                dsum[Fp + i] = (asc_mask && asc_mask[i]) ? 1.0 : 0.0;
-                dsum[2 * Fp + i] = (asc_mask && asc_mask[F + i]) ? 1.0 : 0.0;
-            }
-            continue;
-        }
-        const double* row = tile + r * FS;
-        const double s = s_sum[r];
-        const bool div = check && (s > 1.0);
-        // low / high sums of the stored (normalised) row: lane-strided partial sums, then a fixed-order warp reduction
-        double lo = 0.0, hi = 0.0;
-        for (int f = lane, k = 0; f < Fp; f += 32, ++k) {
-            double v = 0.0;
-            if (f < F) {
-                v = row[f];
-                if (div) v = __ddiv_rn(v, s);
-                if (asc_mask) {
-                    const bool is_lo = masks_in_regs ? ((m_lo >> k) & 1u) : (asc_mask[f] != 0);
-                    const bool is_hi = masks_in_regs ? ((m_hi >> k) & 1u) : (asc_mask[F + f] != 0);
-                    if (is_lo) lo = __dadd_rn(lo, v);
-                    if (is_hi) hi = __dadd_rn(hi, v);
-                }
-            }
-            dst[perm ? kperm(f) : f] = v;
-        }
-        if (asc_mask) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lo = __dadd_rn(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                hi = __dadd_rn(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-            }
-        }
-        if (lane == 0) {
-            dsum[i] = s;
-            dsum[Fp + i] = lo;
-            dsum[2 * Fp + i] = hi;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // fused pruning pass
 //
 // One CTA owns a 64-row tile of one walker and walks the whole branch schedule for it.  Every branch is a
@@ -393,6 +236,201 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
                  ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// interpolation of transition matrices (transition_data_2d.py:195-238, _interp.pyx:30-35, _util.pyx:129-148).
+// HBM-bound: per matrix 4 (or 2) F x F source matrices are read once and one Fp x Fp block is written once.
+// Output block: Fp x Fp matrix (zero padded) followed by the BLK_EXTRA vectors described at the top of this file.
+//
+// One CTA per (matrix, tile of `rows` consecutive matrix rows).  The rows of a tile are one contiguous run of
+// rows * F doubles in every source matrix, so
+//   stage    one lane issues ONE bulk copy (cp.async.bulk, the TMA engine) per source run into shared memory, completing
+//            on an mbarrier: the bytes in flight do not occupy registers, and four CTAs per SM keep ~200 KB outstanding
+//            (a run starts on an 8-byte boundary; the copy starts one element early when that is not a 16-byte one);
+//   phase 1  all threads blend the staged runs in the reference's evaluation order, clamp, and leave the tile in place;
+//   phase 2  thread r walks row r of the tile: the reference's left-to-right row sum (_util.pyx:144-145) is a dependent
+//            chain of F additions that cannot be re-associated, so the tile runs `rows` independent chains side by side
+//            while the other CTAs of the SM are in their memory phases;
+//   phase 3  one warp per row divides (when the sum exceeds 1), writes the row coalesced in the (optionally k-permuted)
+//            layout, and forms the low / high column sums of the stored row.
+// ------------------------------------------------------------------------------------------------
+constexpr int INTERP_THREADS = 256;
+// doubles per staged source run: rows * F elements, one leading element of alignment slack, rounded up to a 16-byte multiple
+__host__ __device__ __forceinline__ int interp_buf_doubles(int rows, int F) { return (rows * F + 3) & ~1; }
+// rows per tile: the four staged runs of a tile take ~51 KB of shared memory (4 CTAs per SM), at most 32 rows
+__host__ __device__ __forceinline__ int interp_rows_per_tile(int F) {
+    int rows = 32;
+    while (rows > 1 && (size_t)4 * interp_buf_doubles(rows, F) * sizeof(double) > 52 * 1024) rows >>= 1;
+    return rows;
+}
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// blend of the staged runs, in place over run 0 (one instance per job flavour: straight-line loops)
+template <bool TWO, bool CHECK>
+__device__ __forceinline__ void interp_blend(double* __restrict__ tile, const double* __restrict__ q12, const double* __restrict__ q21,
+                                             const double* __restrict__ q22, double w11, double w12, double w21, double w22, int n) {
+    for (int e = threadIdx.x; e < n; e += INTERP_THREADS) {
+        double v;
+        if (TWO) {
+            v = __dadd_rn(__dmul_rn(tile[e], w11), __dmul_rn(q12[e], w12));
+        } else {
+            // ((q11*w11 + q21*w21) + q12*w12) + q22*w22
+            v = __dadd_rn(__dmul_rn(tile[e], w11), __dmul_rn(q21[e], w21));
+            v = __dadd_rn(v, __dmul_rn(q12[e], w12));
+            v = __dadd_rn(v, __dmul_rn(q22[e], w22));
+        }
+        if (CHECK) v = fmin(fmax(v, 0.0), 1.0);   // entries > 1 -> 1, < 0 -> 0 (_util.pyx:140-143); blends are never NaN
+        tile[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(INTERP_THREADS, 4)
+interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __restrict__ tables, double* __restrict__ pool, int F, int Fp,
+              int perm, const int8_t* __restrict__ asc_mask /* [2][F]: e0 then eN, may be null */,
+              const unsigned* __restrict__ lane_masks /* [2][32] bit k of word l: column l + 32 k is in e0 / eN (F <= 1024), may be null */,
+              int rows, int tiles_per_job) {
+    extern __shared__ __align__(16) double stage[];   // [4][interp_buf_doubles(rows, F)]
+    __shared__ double s_sum[32];
+    __shared__ unsigned long long bar;
+    const int BUF = interp_buf_doubles(rows, F);
+    const int j = blockIdx.x / tiles_per_job;
+    const int i0 = (blockIdx.x - j * tiles_per_job) * rows;   // first matrix row of the tile
+    const InterpJob jb = jobs[j];
+    if (jb.flags & 8) return;                 // unused slot of a statically laid out job list (device-side planning)
+    double* dst0 = pool + jb.dst;
+    double* dsum = dst0 + (size_t)Fp * Fp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nreal = min(rows, F - i0);      // real (non-padding) rows of the tile, may be <= 0
+    const bool ident = (jb.flags & 2) != 0;   // identity short-cut (transition_data_2d.py:184-187)
+    const bool two = (jb.flags & 4) != 0;
+    const bool check = (jb.flags & 1) != 0;
+    double* tile = stage;                     // the blended tile replaces the first staged run (plus its alignment offset)
+
+    if (nreal > 0 && !ident) {
+        const int n = nreal * F;
+        const size_t off = (size_t)i0 * F;
+        const int nsrc = two ? 2 : 4;
+        int mis[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mis[k] = (int)((jb.src[k] + (int64_t)off) & 1);   // run starts on an odd element: 8 mod 16 bytes
+        // ---- stage: one bulk copy per source run ----
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+            unsigned total = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k < nsrc) total += (unsigned)(((n + mis[k] + 1) & ~1) * 8);
+            mbar_expect_tx(&bar, total);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < nsrc) bulk_load_1d(stage + (size_t)k * BUF, tables + jb.src[k] + off - mis[k], (unsigned)(((n + mis[k] + 1) & ~1) * 8), &bar);
+        }
+        __syncthreads();          // the barrier is initialised before anybody waits on it
+        mbar_wait(&bar, 0);
+        // ---- phase 1: blend, clamp (in place over run 0) ----
+        const double* q11 = stage + mis[0];
+        const double* q12 = stage + (size_t)BUF + mis[1];
+        const double* q21 = stage + (size_t)2 * BUF + mis[2];
+        const double* q22 = stage + (size_t)3 * BUF + mis[3];
+        const double w11 = jb.w[0], w12 = jb.w[1], w21 = jb.w[2], w22 = jb.w[3];
+        tile = stage + mis[0];
+        (void)q11;
+        if (two) interp_blend<true, false>(tile, q12, q21, q22, w11, w12, w21, w22, n);
+        else if (check) interp_blend<false, true>(tile, q12, q21, q22, w11, w12, w21, w22, n);
+        else interp_blend<false, false>(tile, q12, q21, q22, w11, w12, w21, w22, n);
+        __syncthreads();
+        // ---- phase 2: the reference's sequential row sums, one chain per thread ----
+        if (threadIdx.x < nreal) {
+            const double* row = tile + threadIdx.x * F;
+            double s = 0.0;
+#pragma unroll 8
+            for (int f = 0; f < F; ++f) s = __dadd_rn(s, row[f]);
+            s_sum[threadIdx.x] = s;
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3: one warp per row ----
+    // column masks of the low / high sums for this lane's columns f = lane + 32 k (bit k), the same for every row
+    unsigned m_lo = 0, m_hi = 0;
+    const bool masks_in_regs = F <= 1024;   // 32 columns per lane
+    if (asc_mask && masks_in_regs) {
+        if (lane_masks) { m_lo = lane_masks[lane]; m_hi = lane_masks[32 + lane]; }
+        else
+            for (int f = lane, k = 0; f < F; f += 32, ++k) {
+                m_lo |= (asc_mask[f] ? 1u : 0u) << (k & 31);
+                m_hi |= (asc_mask[F + f] ? 1u : 0u) << (k & 31);
+            }
+    }
+    const int pl = perm ? kperm(lane) : lane;   // storage position of column lane + 32 k is pl + 32 k (chunks are 16 wide)
+    for (int r = warp; r < rows; r += INTERP_THREADS / 32) {
+        const int i = i0 + r;
+        if (i >= Fp) break;
+        double* dst = dst0 + (size_t)i * Fp;
+        if (i >= F) {  // zero padding rows
+            for (int f = lane; f < Fp; f += 32) dst[f] = 0.0;
+            if (lane == 0) { dsum[i] = 0.0; dsum[Fp + i] = 0.0; dsum[2 * Fp + i] = 0.0; }
+            continue;
+        }
+        if (ident) {
+            for (int f = lane; f < Fp; f += 32) dst[perm ? kperm(f) : f] = (f == i) ? 1.0 : 0.0;
+            if (lane == 0) {
+                dsum[i] = 1.0;
+                dsum[Fp + i] = (asc_mask && asc_mask[i]) ? 1.0 : 0.0;
+                dsum[2 * Fp + i] = (asc_mask && asc_mask[F + i]) ? 1.0 : 0.0;
+            }
+            continue;
+        }
+        const double* row = tile + r * F;
+        const double s = s_sum[r];
+        const bool div = check && (s > 1.0);
+        // v / s for a whole row: one correctly rounded reciprocal, then per element q0 = v * rcp, rem = v - s * q0 (exact in
+        // an FMA), q = q0 + rem * rcp.  With rcp = RN(1 / s) this is the correctly rounded quotient RN(v / s) (Markstein),
+        // i.e. bit-identical to the reference's division, as long as the remainder does not underflow (v >= 2^-970);
+        // smaller entries take the plain division.
+        const double rcp = div ? __drcp_rn(s) : 1.0;
+        // low / high sums of the stored (normalised) row: lane-strided partial sums, then a fixed-order warp reduction
+        double lo = 0.0, hi = 0.0;
+        for (int f = lane, k = 0; f < Fp; f += 32, ++k) {
+            double v = 0.0;
+            if (f < F) {
+                v = row[f];
+                if (div && v != 0.0) {
+                    if (v >= 1e-290) {
+                        const double q0 = __dmul_rn(v, rcp);
+                        const double rem = __fma_rn(-q0, s, v);
+                        v = __fma_rn(rem, rcp, q0);
+                    } else {
+                        v = __ddiv_rn(v, s);
+                    }
+                }
+                if (asc_mask) {
+                    const bool is_lo = masks_in_regs ? ((m_lo >> k) & 1u) : (asc_mask[f] != 0);
+                    const bool is_hi = masks_in_regs ? ((m_hi >> k) & 1u) : (asc_mask[F + f] != 0);
+                    if (is_lo) lo = __dadd_rn(lo, v);
+                    if (is_hi) hi = __dadd_rn(hi, v);
+                }
+            }
+            dst[pl + 32 * k] = v;
+        }
+        if (asc_mask) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = __dadd_rn(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = __dadd_rn(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+        }
+        if (lane == 0) {
+            dsum[i] = s;
+            dsum[Fp + i] = lo;
+            dsum[2 * Fp + i] = hi;
+        }
+    }
+}
 
 // what the copy-issuing lane needs to know about one GEMM unit (branch x pass x segment)
 struct UnitDesc {
@@ -530,6 +568,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
             w = (int)(rem / t_count);
             tile = t_first + (int)(rem % t_count);
         }
+        if (p.wstatus != nullptr && p.wstatus[w] != 0) { __syncthreads(); continue; }   // walker outside the tables / prior
         const int row0 = tile * TM;
         bool prologue_issued = false;   // chunks 0..PF-1 of the coming unit are already in flight
         // one round trip for all matrix offsets of this walker instead of a dependent global load per branch
@@ -854,7 +893,9 @@ struct FinalizeParams {
     const int32_t* fam_asc;  // [n_fam]
     const double* fam_count; // [n_fam]
     const double* fam_lgamma;// [n_fam]
-    const int32_t* widx;     // [W] global walker index of each walker of the chunk (outputs are indexed by it)
+    const int32_t* widx;     // [W] global walker index of each walker of the chunk (outputs are indexed by it); null: w_base + w
+    int32_t w_base;
+    const int32_t* wstatus;  // [W] chunk-local, non-zero = the walker was skipped: its outputs are NaN (may be null)
     double* out_ll;          // [*] accumulated (+=) across pedigrees
     double* out_root_ll;     // [W][ped_stride] or null
     double* out_log_asc;     // [W][asc_stride] or null
@@ -879,7 +920,17 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
 __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p) {
     __shared__ double sh[256];
     const int w = blockIdx.x;
-    const int wg = p.widx[w];
+    const int wg = p.widx ? p.widx[w] : p.w_base + w;
+    if (p.wstatus != nullptr && p.wstatus[w] != 0) {
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        if (threadIdx.x == 0) {
+            p.out_ll[wg] = qnan;
+            if (p.out_root_ll != nullptr) p.out_root_ll[(size_t)wg * p.ped_stride + p.ped_index] = qnan;
+        }
+        if (p.out_log_asc != nullptr)
+            for (int u = threadIdx.x; u < p.n_asc; u += 256) p.out_log_asc[(size_t)wg * p.asc_stride + p.asc_offset + u] = qnan;
+        return;
+    }
     double a = 0.0;
     for (int t = threadIdx.x; t < p.n_tiles; t += 256) a += p.tile_ll[(size_t)w * p.n_tiles + t];
     const double root_ll = block_sum_256(a, sh);
@@ -917,50 +968,411 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Poisson-binomial non-ascertainment probabilities (_poisson_binom.pyx:18-90), DP truncated to the K
-// columns that are read back.  One CTA per read set, one thread per frequency; qualities are staged
-// through shared memory in coalesced chunks.
+// Poisson-binomial non-ascertainment probabilities (_poisson_binom.pyx:18-90).  Only the columns k < K =
+// ceil(min_freq * nreads) of the reference's DP table are ever read back, so the DP is carried on those columns only.
+// One CTA per read set, one thread per frequency; qualities are staged through shared memory in coalesced chunks.
+// The K columns are processed in blocks of PB_BLK held in registers: block b needs, for every read j, the value
+// P_{j-1}(32 b - 1) of the previous block's last column; a thread writes that sequence to its own column of a global
+// scratch ([read][frequency], coalesced) while it runs block b - 1 and reads it back in block b.  Every P_j(k) is formed by
+// the same expression from the same operands as in a single pass, and the final sum runs over k in ascending order, so
+// the result does not depend on the blocking.  K <= PB_BLK needs no scratch.
 // ------------------------------------------------------------------------------------------------
-constexpr int PB_MAXK = 32;
+constexpr int PB_BLK = 32;
 __global__ void pb_kernel(const double* __restrict__ qual, const int64_t* __restrict__ off, const double* __restrict__ freqs,
-                          int F, double min_freq, double* __restrict__ out, int* __restrict__ overflow) {
+                          int F, double min_freq, double* __restrict__ out,
+                          double* __restrict__ carry /* per set with K > PB_BLK: [2][nreads][F] at carry_off[set] (doubles), else unused */,
+                          const int64_t* __restrict__ carry_off) {
     __shared__ double sq[256];
     const int set = blockIdx.x;
     const int64_t q0 = off[set], q1 = off[set + 1];
     const int nq = (int)(q1 - q0);
     const int K = (int)ceil(min_freq * (double)nq);
-    if (K > PB_MAXK) { if (threadIdx.x == 0) atomicExch(overflow, K); return; }
+    const int nblk = (K + PB_BLK - 1) / PB_BLK;
+    double* cbase = (nblk > 1) ? carry + carry_off[set] : nullptr;
     for (int fbase = 0; fbase < F; fbase += blockDim.x) {
         const int fi = fbase + threadIdx.x;
-        const double f = fi < F ? freqs[fi] : 0.0;
-        double P[PB_MAXK + 1];
+        const int fc = fi < F ? fi : F - 1;      // idle threads of the last group shadow a valid column (no stores)
+        const double f = freqs[fc];
+        double acc = 0.0;
+        for (int b = 0; b < max(nblk, 1); ++b) {
+            const double* cin = (b > 0 && fi < F) ? cbase + (size_t)((b - 1) & 1) * nq * F + fc : nullptr;
+            double* cout = (b + 1 < nblk && fi < F) ? cbase + (size_t)(b & 1) * nq * F + fc : nullptr;
+            double P[PB_BLK];
 #pragma unroll
-        for (int k = 0; k <= PB_MAXK; ++k) P[k] = 0.0;
-        for (int base = 0; base < nq; base += 256) {
-            __syncthreads();
-            for (int t = threadIdx.x; t < 256; t += blockDim.x)
-                sq[t] = (base + t < nq) ? pow(10.0, -qual[q0 + base + t] / 10.0) : 0.0;
-            __syncthreads();
-            const int lim = min(256, nq - base);
-            for (int jj = 0; jj < lim; ++jj) {
-                const double e = sq[jj];
-                const double ap = f * (1.0 - e) + (1 - f) * e;
-                if (base + jj == 0) {
-                    P[0] = 1 - ap;
-                    P[1] = ap;
-                } else {
+            for (int k = 0; k < PB_BLK; ++k) P[k] = 0.0;
+            for (int base = 0; base < nq; base += 256) {
+                __syncthreads();
+                for (int t = threadIdx.x; t < 256; t += blockDim.x)
+                    sq[t] = (base + t < nq) ? pow(10.0, -qual[q0 + base + t] / 10.0) : 0.0;
+                __syncthreads();
+                const int lim = min(256, nq - base);
+                for (int jj = 0; jj < lim; ++jj) {
+                    const int j = base + jj;
+                    const double e = sq[jj];
+                    const double ap = f * (1.0 - e) + (1 - f) * e;
+                    if (j == 0) {
+                        if (b == 0) { P[0] = 1 - ap; P[1] = ap; }
+                    } else {
+                        const double left = cin ? cin[(size_t)j * F] : 0.0;   // P_{j-1}(32 b - 1); column -1 is identically 0
+                        if (cout) cout[(size_t)j * F] = P[PB_BLK - 1];         // P_{j-1}(32 b + 31) for the next block
 #pragma unroll
-                    for (int k = PB_MAXK; k >= 1; --k) P[k] = ap * P[k - 1] + (1 - ap) * P[k];
-                    P[0] = (1 - ap) * P[0];
+                        for (int k = PB_BLK - 1; k >= 1; --k) P[k] = ap * P[k - 1] + (1 - ap) * P[k];
+                        P[0] = ap * left + (1 - ap) * P[0];
+                    }
                 }
             }
-        }
-        if (fi < F) {
-            double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < PB_MAXK; ++k) if (k < K) acc += P[k];
-            out[(size_t)set * F + fi] = (nq > 0) ? acc : 0.0;
+            for (int k = 0; k < PB_BLK; ++k) if (b * PB_BLK + k < K) acc += P[k];
         }
+        if (fi < F) out[(size_t)set * F + fi] = (nq > 0) ? acc : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// root (stationary) distribution on the device (likelihoods.py:27-60): point masses (1 - ppoly) / 2 at the two fixed
+// states and ppoly * Beta(ab, ab) on the N - 1 interior Wright-Fisher cells, summed into the frequency bins.
+// The reference takes every cell as a DIFFERENCE of two regularised incomplete beta values; for the small ab of the
+// prior box (1e-9 .. 1) both are ~1/2 and the difference keeps only ~16 + log10(ab) digits.  Here every cell mass is
+// integrated directly, to ~2e-15 relative for any ab:
+//   interior cell [lo, hi]   16-point Gauss-Legendre of t^(a-1) (1-t)^(a-1): the nearest singularity (t = 0 or 1) is at
+//                            least one cell width away, Bernstein-ellipse parameter >= 2 + sqrt(3), error < 1e-17;
+//                            nodes are placed as lo + (hi - lo)/2 * (1 + xi) so that the interval ends are the exact edges;
+//   the cells at 0 and 1     series of the incomplete beta integral, x^a / (a B) * (1 + a sum_n c_n x^n / (a + n)),
+//                            c_n = prod (k - a) / k, x = the (exactly representable) cell width;
+//   1 / B(a, a)              a Gamma(2a + 1) / (2 Gamma(a + 1)^2): no cancellation for tiny a.
+// One CTA per walker.  Edges are the reference's (2 j - 1) / (2 (N - 2)) evaluated in the same floating-point expression.
+// ------------------------------------------------------------------------------------------------
+__constant__ double GL16_1PX[16] = {   // 1 + xi_i
+    0x1.5b4f66ca1e080p-7, 0x1.c60a99e906500p-5, 0x1.132ff2bac6df4p-3, 0x1.f4ee8896e3654p-3, 0x1.874b732542e90p-2,
+    0x1.157ed32de2c47p-1, 0x1.6fd1a8cdee642p-1, 0x1.cf5a853312ac1p-1, 0x1.1852bd6676aa0p+0, 0x1.48172b9908cdfp+0,
+    0x1.754096690e9dcp+0, 0x1.9e2d2336af45cp+0, 0x1.c1622eed23936p+0, 0x1.dd9a01a8a7242p+0, 0x1.f1cfab30b7cd8p+0,
+    0x1.fd4961326bc3fp+0};
+__constant__ double GL16_W[16] = {
+    0x1.bcddab4b7c228p-6, 0x1.fdfb1a2c1261ep-5, 0x1.85c4ee79cc24bp-4, 0x1.fe7af2bad3878p-4, 0x1.325f61bca3cbep-3,
+    0x1.5a6ebbb5a7600p-3, 0x1.75f8c77e0c011p-3, 0x1.83feae80e4e01p-3, 0x1.83feae80e4e01p-3, 0x1.75f8c77e0c011p-3,
+    0x1.5a6ebbb5a7600p-3, 0x1.325f61bca3cbep-3, 0x1.fe7af2bad3878p-4, 0x1.85c4ee79cc24bp-4, 0x1.fdfb1a2c1261ep-5,
+    0x1.bcddab4b7c228p-6};
+
+__device__ __forceinline__ double beta_edge_cell(double a, double x, double halfish) {
+    // I_x(a, a) for a small x: x^a / (a B(a,a)) * (1 + a * sum_{n>=1} c_n x^n / (a + n)), halfish = 1 / (a B(a,a))
+    double c = 1.0, sum = 0.0, xn = 1.0;
+#pragma unroll
+    for (int n = 1; n <= 9; ++n) {
+        c *= ((double)n - a) / (double)n;
+        xn *= x;
+        sum += c * xn / (a + (double)n);
+    }
+    return halfish * exp(a * log(x)) * (1.0 + a * sum);
+}
+
+__global__ void __launch_bounds__(256) root_prior_kernel(const double* __restrict__ params, int ndim, int W, const int32_t* __restrict__ breaks,
+                                                         int F, int Nwf, double* __restrict__ out, int ld /* row pitch of out, >= F; the tail is zeroed */) {
+    extern __shared__ double distn[];   // [Nwf + 1]
+    const int w = blockIdx.x;
+    if (w >= W) return;
+    // alphabeta, polyprob = 10**x[-2:]  (inference.py:824)
+    const double a = pow(10.0, params[(size_t)w * ndim + ndim - 2]);
+    const double pp = pow(10.0, params[(size_t)w * ndim + ndim - 1]);
+    const int Ni = Nwf - 2;
+    const double den = 2.0 * (double)Ni;
+    const double g1 = tgamma(a + 1.0);
+    const double halfish = tgamma(2.0 * a + 1.0) / (2.0 * g1 * g1);   // 1 / (a B(a, a))
+    const double invB = a * halfish;
+    const double am1 = a - 1.0;
+    for (int c = threadIdx.x; c <= Ni; c += blockDim.x) {
+        double m;
+        if (c == 0) {
+            m = beta_edge_cell(a, 1.0 / den, halfish);
+        } else if (c == Ni) {
+            m = beta_edge_cell(a, 1.0 - (double)(2 * Ni - 1) / den, halfish);
+        } else {
+            const double lo = (double)(2 * c - 1) / den, hi = (double)(2 * c + 1) / den;
+            const double hw = 0.5 * (hi - lo);
+            double acc = 0.0;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const double t = lo + hw * GL16_1PX[i];
+                acc += GL16_W[i] * exp(am1 * (log(t) + log1p(-t)));
+            }
+            m = invB * hw * acc;
+        }
+        distn[1 + c] = m * pp;
+    }
+    if (threadIdx.x == 0) { distn[0] = (1.0 - pp) / 2; distn[Nwf] = (1.0 - pp) / 2; }
+    __syncthreads();
+    // np.add.reduceat(distn, breaks): bin f holds the states breaks[f] .. breaks[f+1]-1, summed left to right
+    for (int f = threadIdx.x; f < ld; f += blockDim.x) {
+        double s = 0.0;
+        if (f < F) {
+            const int b0 = breaks[f], b1 = (f + 1 < F) ? breaks[f + 1] : Nwf + 1;
+            for (int k = b0; k < b1; ++k) s += distn[k];
+        }
+        out[(size_t)w * ld + f] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-walker interpolation plans on the device (device-resident evaluation: the parameter vectors never visit the host).
+// The scalar part of TransitionData.get_transition_probabilities_2d -- range checks, searchsorted, bilinear weights
+// (transition_data_2d.py:148-238, transition_data_bottleneck.py:96-183) -- for every (walker, matrix key), the same
+// arithmetic the host planner of mope_b200.cu performs.  The matrix pool has a STATIC layout here: every walker owns
+// max_blocks blocks (one per shared-matrix key, n_gens per age-scaled key); unused slots carry flag 8 and interp_kernel
+// leaves them alone.  One thread per (walker, key).
+// ------------------------------------------------------------------------------------------------
+struct FixedKeyDev { int32_t var, bott; };
+struct RateKeyDev { int32_t var, pad; double min_mult, max_mult; };
+constexpr int MOPE_ST_SKIPPED_DEV = 128;   // prior = -inf: the likelihood of the walker is not evaluated (inference.py:1148-1149)
+
+struct PlanParams {
+    const double* params;    // [W][ndim] log10 parameters (sign-folded)
+    const double* lnprior;   // [W] or null: -inf / NaN marks walkers to skip
+    int32_t ndim, n_var, W;
+    const double *gens, *us, *nbs, *bot_us;
+    int32_t n_gens, n_us, n_nbs, n_bot_us, has_bot;
+    double N, max_coal, min_mut, max_mut, min_bmut, max_bmut, min_nb, max_nb;
+    const FixedKeyDev* fkeys; int32_t n_fixed;
+    const RateKeyDev* rkeys; int32_t n_rate;
+    int64_t bot_base;
+    int32_t F, Fp, max_blocks;
+    InterpJob* jobs;         // [W][max_blocks]
+    int64_t* mat_off;        // [W][n_fixed]
+    RateInfo* rate;          // [W][n_rate]
+    int32_t* status;         // [W], zeroed before the launch
+};
+
+__device__ __forceinline__ int lower_bound_dev(const double* v, int n, double x) {   // searchsorted(side='left')
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (v[mid] < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void plan_kernel(PlanParams p) {
+    const int nk = p.n_fixed + p.n_rate;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)p.W * nk) return;
+    const int w = (int)(gid / nk), k = (int)(gid % nk);
+    const double* x = p.params + (size_t)w * p.ndim;
+    const size_t FF = (size_t)p.F * p.F;
+    const size_t blk = blk_doubles(p.Fp);
+    InterpJob* jobs = p.jobs + (size_t)w * p.max_blocks;
+    int32_t st = 0;
+    if (k == 0 && p.lnprior != nullptr && !(p.lnprior[w] > -INFINITY)) st |= MOPE_ST_SKIPPED_DEV;
+    if (k < p.n_fixed) {
+        const FixedKeyDev key = p.fkeys[k];
+        const double len = pow(10.0, x[key.var]), mut = pow(10.0, x[p.n_var + key.var]);
+        InterpJob jb;
+        jb.flags = 8;
+        jb.pad = 0;
+        jb.dst = (int64_t)(((size_t)w * p.max_blocks + k) * blk);
+        int64_t moff = -1;
+        if (key.bott) {
+            // transition_data_bottleneck.py:118-129, 138-171
+            if (!p.has_bot) st |= 64;
+            else {
+                if (isnan(len) || isnan(mut)) st |= 32;
+                if (len < p.min_nb) st |= 8;
+                if (len > p.max_nb) st |= 16;
+                if (mut < p.min_bmut) st |= 2;
+                if (mut > p.max_bmut) st |= 4;
+                const int nbn = p.n_nbs, nun = p.n_bot_us;
+                const int bi = min(lower_bound_dev(p.nbs, nbn, len), nbn - 1);
+                const double u = mut / (2.0 * p.N);
+                const int ui = min(lower_bound_dev(p.bot_us, nun, u), nun - 1);
+                const int b1 = bi > 0 ? bi - 1 : nbn - 1, u1i = ui > 0 ? ui - 1 : nun - 1;  // python's index -1 wraps
+                const double t = len, t1 = p.nbs[b1], t2 = p.nbs[bi], u1 = p.bot_us[u1i], u2 = p.bot_us[ui];
+                const double denom = __dmul_rn(__dsub_rn(t2, t1), __dsub_rn(u2, u1));
+                jb.w[0] = __ddiv_rn(__dmul_rn(__dsub_rn(t2, t), __dsub_rn(u2, u)), denom);
+                jb.w[2] = __ddiv_rn(__dmul_rn(__dsub_rn(t, t1), __dsub_rn(u2, u)), denom);
+                jb.w[1] = __ddiv_rn(__dmul_rn(__dsub_rn(t2, t), __dsub_rn(u, u1)), denom);
+                jb.w[3] = __ddiv_rn(__dmul_rn(__dsub_rn(t, t1), __dsub_rn(u, u1)), denom);
+                jb.src[0] = p.bot_base + (int64_t)(((size_t)b1 * nun + u1i) * FF);
+                jb.src[1] = p.bot_base + (int64_t)(((size_t)b1 * nun + ui) * FF);
+                jb.src[2] = p.bot_base + (int64_t)(((size_t)bi * nun + u1i) * FF);
+                jb.src[3] = p.bot_base + (int64_t)(((size_t)bi * nun + ui) * FF);
+                jb.flags = 0;
+                moff = jb.dst;
+            }
+        } else {
+            // transition_data_2d.py:158-173, 183-224
+            if (!isfinite(len) || !isfinite(mut)) st |= 32;
+            if (len > p.max_coal) st |= 1;
+            if (mut < p.min_mut) st |= 2;
+            if (mut > p.max_mut) st |= 4;
+            const double t = __dmul_rn(p.N, len);
+            if (!(t < p.gens[0])) {
+                const int G = p.n_gens, U = p.n_us;
+                const int gi = min(lower_bound_dev(p.gens, G, t), G - 1);
+                const double xd = mut / (2.0 * p.N);
+                const int xi = min(lower_bound_dev(p.us, U, xd), U - 1);
+                const int g1 = gi > 0 ? gi - 1 : G - 1, x1i = xi > 0 ? xi - 1 : U - 1;
+                const double t1 = p.gens[g1], t2 = p.gens[gi], x1 = p.us[x1i], x2 = p.us[xi];
+                const double denom = __dmul_rn(__dsub_rn(t2, t1), __dsub_rn(x2, x1));
+                jb.w[0] = __ddiv_rn(__dmul_rn(__dsub_rn(t2, t), __dsub_rn(x2, xd)), denom);
+                jb.w[2] = __ddiv_rn(__dmul_rn(__dsub_rn(t, t1), __dsub_rn(x2, xd)), denom);
+                jb.w[1] = __ddiv_rn(__dmul_rn(__dsub_rn(t2, t), __dsub_rn(xd, x1)), denom);
+                jb.w[3] = __ddiv_rn(__dmul_rn(__dsub_rn(t, t1), __dsub_rn(xd, x1)), denom);
+                jb.src[0] = (int64_t)(((size_t)g1 * U + x1i) * FF);
+                jb.src[1] = (int64_t)(((size_t)g1 * U + xi) * FF);
+                jb.src[2] = (int64_t)(((size_t)gi * U + x1i) * FF);
+                jb.src[3] = (int64_t)(((size_t)gi * U + xi) * FF);
+                jb.flags = 1;
+                moff = jb.dst;
+            }   // else: identity short-cut (transition_data_2d.py:184-187): no matrix, the tree kernel forwards the message
+        }
+        if (st & ~MOPE_ST_SKIPPED_DEV) { jb.flags = 8; }
+        if (jb.flags & 8) { jb.src[0] = jb.src[1] = jb.src[2] = jb.src[3] = 0; jb.w[0] = jb.w[1] = jb.w[2] = jb.w[3] = 0.0; }
+        jobs[k] = jb;
+        p.mat_off[(size_t)w * p.n_fixed + k] = moff;
+    } else {
+        const int r = k - p.n_fixed;
+        const RateKeyDev key = p.rkeys[r];
+        const double len = pow(10.0, x[key.var]), mut = pow(10.0, x[p.n_var + key.var]);
+        const double tmax = key.max_mult * len, tmin = key.min_mult * len;
+        if (!isfinite(tmax) || !isfinite(tmin) || !isfinite(mut)) st |= 32;
+        if (tmax > p.max_coal) st |= 1;
+        if (mut < p.min_mut) st |= 2;
+        if (mut > p.max_mut) st |= 4;
+        const int G = p.n_gens, U = p.n_us;
+        const int base = p.n_fixed + r * G;
+        RateInfo ri;
+        ri.len = len;
+        ri.gbase = 0;
+        ri.gcount = 0;
+        ri.off = (int64_t)(((size_t)w * p.max_blocks + base) * blk);
+        int glo = 1, ghi = 0;
+        const double gmax = p.N * tmax, gmin = p.N * tmin;
+        if (!(st & ~MOPE_ST_SKIPPED_DEV) && !(gmax < p.gens[0])) {
+            ghi = min(lower_bound_dev(p.gens, G, gmax), G - 1);
+            glo = (gmin < p.gens[0]) ? 0 : max(min(lower_bound_dev(p.gens, G, gmin), G - 1) - 1, 0);
+            ri.gbase = glo;
+            ri.gcount = ghi - glo + 1;
+            ri.off = (int64_t)(((size_t)w * p.max_blocks + base + glo) * blk);
+        }
+        const double xd = mut / (2.0 * p.N);
+        const int xi = min(lower_bound_dev(p.us, U, xd), U - 1);
+        const int x1i = xi > 0 ? xi - 1 : U - 1;
+        const double x1 = p.us[x1i], x2 = p.us[xi];
+        const double bx = __ddiv_rn(__dsub_rn(x2, xd), __dsub_rn(x2, x1)), cx = __ddiv_rn(__dsub_rn(xd, x1), __dsub_rn(x2, x1));
+        for (int g = 0; g < G; ++g) {
+            InterpJob jb;
+            jb.pad = 0;
+            jb.dst = (int64_t)(((size_t)w * p.max_blocks + base + g) * blk);
+            if (g >= glo && g <= ghi) {
+                jb.src[0] = (int64_t)(((size_t)g * U + x1i) * FF);
+                jb.src[1] = (int64_t)(((size_t)g * U + xi) * FF);
+                jb.src[2] = jb.src[0];
+                jb.src[3] = jb.src[1];
+                jb.w[0] = bx; jb.w[1] = cx; jb.w[2] = 0.0; jb.w[3] = 0.0;
+                jb.flags = 4;   // two-term blend; the clamp/renormalisation is applied per row in the tree kernel
+            } else {
+                jb.src[0] = jb.src[1] = jb.src[2] = jb.src[3] = 0;
+                jb.w[0] = jb.w[1] = jb.w[2] = jb.w[3] = 0.0;
+                jb.flags = 8;
+            }
+            jobs[base + g] = jb;
+        }
+        p.rate[(size_t)w * p.n_rate + r] = ri;
+    }
+    if (st) atomicOr(&p.status[w], st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ensemble sampler on the device: the affine-invariant stretch move of emcee, which mope's run_mcmc drives
+// (inference.py:1353-1356; `a` = --chain-alpha).  One half of the ensemble moves against the other half:
+//   propose   y = c + z (x - c),  z = ((a-1) u + 1)^2 / a,  partner c drawn from the other half; then the sign folding and
+//             the box prior of Inference.log_posterior / logprior (inference.py:1132-1149, 1055-1110)
+//   (the likelihood of the proposals: mope_b200_eval_resident)
+//   accept    with probability min(1, z^(ndim-1) p(y) / p(x))
+// Random numbers: either streams supplied by the caller (tests: the same draws as the host sampler) or Philox4x32-10
+// keyed by (seed) and counted by (step, walker) -- no state to carry, any number of walkers in parallel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+        const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n2 = hi0 ^ ctr[3] ^ k1;
+        ctr[0] = n0; ctr[1] = lo1; ctr[2] = n2; ctr[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// uniform in (0, 1) with 53 random bits
+__device__ __forceinline__ double u01_53(uint32_t a, uint32_t b) {
+    return ((double)(((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6)) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+struct SamplerParams {
+    double* pos;              // [W][ndim] current positions (emcee's walker coordinates, not folded)
+    double* lnprob;           // [W]
+    long long* naccept;       // [W]
+    double* q;                // [half][ndim] proposals
+    double* folded;           // [half][ndim] sign-folded proposals (what the likelihood sees)
+    double* factor;           // [half] (ndim - 1) log z
+    double* lnprior;          // [half]
+    const double* ll;         // [half] log-likelihood of the proposals (accept)
+    const double *lower, *upper, *prior_slope;   // [ndim]; log prior inside the box = prior_const + sum_d prior_slope[d] x[d]
+    double prior_const;
+    const double *zu, *au;    // [half] uniform streams, or null -> Philox
+    const int32_t* partner;   // [half] partner index inside the other half, or null -> Philox
+    unsigned long long seed, step;
+    double a;
+    int32_t ndim, n_var, first, other_first, half;
+};
+
+__global__ void stretch_propose_kernel(SamplerParams p) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.half) return;
+    double u;
+    int j;
+    if (p.zu != nullptr) { u = p.zu[k]; j = p.partner[k]; }
+    else {
+        uint32_t c[4] = {(uint32_t)k, (uint32_t)(p.step & 0xffffffffu), (uint32_t)(p.step >> 32), 0u};
+        philox4x32_10(c, (uint32_t)(p.seed & 0xffffffffu), (uint32_t)(p.seed >> 32));
+        u = u01_53(c[0], c[1]);
+        j = (int)(((unsigned long long)c[2] * (unsigned long long)p.half) >> 32);
+    }
+    const double t = __dadd_rn(__dmul_rn(p.a - 1.0, u), 1.0);
+    const double z = __ddiv_rn(__dmul_rn(t, t), p.a);
+    p.factor[k] = ((double)p.ndim - 1.0) * log(z);
+    const double* s = p.pos + (size_t)(p.first + k) * p.ndim;
+    const double* c = p.pos + (size_t)(p.other_first + j) * p.ndim;
+    double* q = p.q + (size_t)k * p.ndim;
+    double* x = p.folded + (size_t)k * p.ndim;
+    bool inside = true;
+    double lp = p.prior_const;
+    for (int d = 0; d < p.ndim; ++d) {
+        const double v = __dsub_rn(c[d], __dmul_rn(__dsub_rn(c[d], s[d]), z));   // q = c - (c - s) z
+        q[d] = v;
+        // x[nv:2nv] = -|x|, x[-2:] = -|x|  (inference.py:1140-1145)
+        const double f = ((d >= p.n_var && d < 2 * p.n_var) || d >= p.ndim - 2) ? -fabs(v) : v;
+        x[d] = f;
+        if (f < p.lower[d] || f > p.upper[d] || f != f) inside = false;
+        lp += p.prior_slope[d] * f;
+    }
+    p.lnprior[k] = inside ? lp : -INFINITY;
+}
+
+__global__ void stretch_accept_kernel(SamplerParams p) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.half) return;
+    double u;
+    if (p.au != nullptr) u = p.au[k];
+    else {
+        uint32_t c[4] = {(uint32_t)k, (uint32_t)(p.step & 0xffffffffu), (uint32_t)(p.step >> 32), 1u};
+        philox4x32_10(c, (uint32_t)(p.seed & 0xffffffffu), (uint32_t)(p.seed >> 32));
+        u = u01_53(c[0], c[1]);
+    }
+    const int w = p.first + k;
+    double newlp = p.lnprior[k];
+    if (newlp > -INFINITY) newlp += p.ll[k];      // the likelihood of a walker outside the prior is never evaluated
+    if (newlp != newlp) newlp = -INFINITY;         // NaN -> -inf (inference.py:1155-1156)
+    const double lnpdiff = p.factor[k] + newlp - p.lnprob[w];
+    if (log(u) < lnpdiff) {
+        const double* q = p.q + (size_t)k * p.ndim;
+        double* x = p.pos + (size_t)w * p.ndim;
+        for (int d = 0; d < p.ndim; ++d) x[d] = q[d];
+        p.lnprob[w] = newlp;
+        p.naccept[w] += 1;
     }
 }
 
@@ -986,11 +1398,11 @@ __global__ void fill_nan_kernel(double* __restrict__ dst, int n) {
 }
 // stat[widx[i]][0..F) -> dst[i][0..Fp) zero padded
 __global__ void gather_pad_kernel(const double* __restrict__ src, const int32_t* __restrict__ widx, double* __restrict__ dst,
-                                  int n, int F, int Fp) {
+                                  int n, int F, int Fp, int w_base = 0) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)n * Fp) return;
     const int i = (int)(idx / Fp), f = (int)(idx % Fp);
-    dst[idx] = (f < F) ? src[(size_t)widx[i] * F + f] : 0.0;
+    dst[idx] = (f < F) ? src[(size_t)(widx ? widx[i] : w_base + i) * F + f] : 0.0;
 }
 // E[s][r][f] (padded) -> out[l][s][f]
 __global__ void emission_to_lsf_kernel(const double* __restrict__ E, double* __restrict__ out, int L, int S, int F, int Fp, int R_pad) {

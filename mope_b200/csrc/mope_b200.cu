@@ -102,6 +102,14 @@ struct mope_ctx {
     double* gens_dev = nullptr;
     int32_t* work_ctr = nullptr;   // item counter of tree_kernel4 (zeroed before every launch)
     int8_t* asc_mask = nullptr;    // [2][F] e0 (freq < min_freq) then eN (freq > 1 - min_freq)
+    unsigned* lane_masks = nullptr; // [2][32] asc_mask as per-lane column bit masks (interp_kernel), null when F > 1024
+    int32_t* breaks_dev = nullptr; // [F] first Wright-Fisher state of every bin (null: no device root prior)
+    bool has_breaks = false;
+    // constants of the device-side planner (library-owned, a few KB): grids and matrix keys
+    char* plan_consts = nullptr;
+    double *us_dev = nullptr, *nbs_dev = nullptr, *bot_us_dev = nullptr;
+    FixedKeyDev* fkeys_dev = nullptr;
+    RateKeyDev* rkeys_dev = nullptr;
     // model
     int n_var = 0, ndim = 0, n_ped = 0, asc_total = 0;
     double min_phred = -1, min_freq = 0, genome = 0, penalty = 0;
@@ -543,7 +551,10 @@ int layout_arena(mope_ctx* c, const mope_tables_desc* t, const mope_model_desc* 
     double* gd = bump.take<double>(t->n_gens);
     int32_t* wc = bump.take<int32_t>(64);
     int8_t* am = bump.take<int8_t>(2 * (size_t)t->F);
-    if (!dry) { c->tables = tab; c->gens_dev = gd; c->work_ctr = wc; c->asc_mask = am; c->bot_base = (int64_t)t->n_gens * t->n_us * FF; }
+    int32_t* brk = bump.take<int32_t>(t->F);
+    unsigned* lm = bump.take<unsigned>(64);
+    if (!dry && t->F <= 1024) c->lane_masks = lm;
+    if (!dry) { c->tables = tab; c->gens_dev = gd; c->work_ctr = wc; c->asc_mask = am; c->breaks_dev = brk; c->bot_base = (int64_t)t->n_gens * t->n_us * FF; }
     const int Fp = round_up_i(t->F, 16);
     for (int k = 0; k < m->n_ped; ++k) {
         const mope_pedigree_desc& pd = m->peds[k];
@@ -620,19 +631,17 @@ int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d
     const int F = c->F, Fp = c->Fp;
     const int rows = interp_rows_per_tile(F);
     const int tiles = (Fp + rows - 1) / rows;
-    const size_t smem = (size_t)rows * interp_row_stride(F) * sizeof(double);
+    const size_t smem = (size_t)4 * interp_buf_doubles(rows, F) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CUDA_TRY(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    if ((size_t)rows * F >= 65536) return fail(MOPE_E_INVALID, "interp: tile of %d x %d elements exceeds the index range of the fast division", rows, F);
-    const unsigned magic = (unsigned)((0x100000000ull + (unsigned long long)F - 1) / (unsigned long long)F);
     const unsigned long long grid = (unsigned long long)n_jobs * tiles;
     if (grid > 0x7fffffffull) return fail(MOPE_E_INVALID, "interp: too many matrices in one launch (%zu)", n_jobs);
     interp_kernel<<<(unsigned)grid, INTERP_THREADS, smem, st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, F, Fp, perm ? 1 : 0, c->asc_mask,
-                                                                rows, tiles, magic);
+                                                                c->lane_masks, rows, tiles);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return 0;
@@ -1163,6 +1172,149 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
     return 0;
 }
 
+// Device-resident evaluation (mope_b200_eval_resident): nothing on the host but launch parameters.
+int eval_resident_impl(mope_ctx* c, const double* params_dev, const double* stat_dev, const double* lnprior_dev, int W,
+                       void* workspace, size_t ws_bytes, cudaStream_t st, double* out_ll_dev, int32_t* out_status_dev) {
+    if (!c || !params_dev || !out_ll_dev || !out_status_dev || W < 0) return fail(MOPE_E_INVALID, "eval_resident: null argument");
+    if (W == 0) return 0;
+    if (!workspace) return fail(MOPE_E_INVALID, "eval_resident: null workspace");
+    if (!stat_dev && !c->has_breaks) return fail(MOPE_E_INVALID, "eval_resident: no root distributions given and the context has no `breaks` to compute them");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int Fp = c->Fp, F = c->F;
+    const int n_mat = (int)c->fixed_keys.size(), n_rate = (int)c->rate_keys.size();
+    const size_t max_blocks = std::max<size_t>(max_blocks_per_walker(c), 1);
+    const size_t blk = blk_doubles(Fp);
+
+    Bump ws;
+    ws.base = (char*)workspace;
+    ws.cap = ws_bytes;
+    double* scratch = ws.take<double>(scratch_doubles(c));
+    if (!ws.ok()) return fail(MOPE_E_NOMEM, "workspace too small: %zu bytes, need more than %zu", ws_bytes, ws.used);
+    const size_t fixed_used = ws.used;
+    CUtensorMap tmapS;
+    if (!c->use_v4)
+        if (int rc = make_tmap(&tmapS, scratch, (uint64_t)c->num_sms * c->max_slots * TM, Fp, TM)) return rc;
+    const size_t pw = per_walker_bytes(c, max_blocks);
+    const size_t avail = ws_bytes - align_up(fixed_used, 256);
+    const size_t slack = 16 * 256;
+    if (avail < slack + pw) return fail(MOPE_E_NOMEM, "workspace too small for a single walker: %zu bytes available, %zu needed", avail, slack + pw);
+    const int Wchunk = (int)std::min<size_t>((size_t)W, (avail - slack) / pw);
+
+    CUDA_TRY(cudaMemsetAsync(out_status_dev, 0, (size_t)W * sizeof(int32_t), st));
+    CUDA_TRY(cudaMemsetAsync(c->work_ctr + 8, 0, sizeof(unsigned long long), st));
+    c->last_stream = st;
+    c->last_gemm_ops = -1;
+    c->last_identity_ops = -1;
+
+    for (int w0 = 0; w0 < W; w0 += Wchunk) {
+        const int Wc = std::min(Wchunk, W - w0);
+        const size_t n_blocks = (size_t)Wc * max_blocks;
+        Bump cw = ws;
+        cw.used = fixed_used;
+        InterpJob* d_jobs = cw.take<InterpJob>(n_blocks);
+        int64_t* d_mat_off = cw.take<int64_t>(std::max<size_t>((size_t)Wc * n_mat, 1));
+        RateInfo* d_rate = cw.take<RateInfo>(std::max<size_t>((size_t)Wc * n_rate, 1));
+        cw.take<int32_t>(Wc);   // (widx of the host-planned path; keeps the carve identical)
+        double* d_stat = cw.take<double>((size_t)Wc * Fp);
+        double* d_pool = cw.take<double>(n_blocks * blk);
+        double* d_tile_ll = cw.take<double>((size_t)Wc * c->max_tiles);
+        double* d_asc_dot = cw.take<double>((size_t)Wc * std::max(c->max_asc2, 2));
+        double* d_uni = cw.take<double>(std::max<size_t>((size_t)Wc * c->max_uroot * 2 * Fp, 1));
+        if (!cw.ok()) return fail(MOPE_E_NOMEM, "internal: chunk carve exceeded the workspace (%zu > %zu)", cw.used, cw.cap);
+        int32_t* d_status = out_status_dev + w0;
+
+        // plans
+        PlanParams pp{};
+        pp.params = params_dev + (size_t)w0 * c->ndim;
+        pp.lnprior = lnprior_dev ? lnprior_dev + w0 : nullptr;
+        pp.ndim = c->ndim; pp.n_var = c->n_var; pp.W = Wc;
+        pp.gens = c->gens_dev; pp.us = c->us_dev; pp.nbs = c->nbs_dev; pp.bot_us = c->bot_us_dev;
+        pp.n_gens = c->n_gens; pp.n_us = c->n_us; pp.n_nbs = c->n_nbs; pp.n_bot_us = c->n_bot_us; pp.has_bot = c->has_bot ? 1 : 0;
+        pp.N = c->N; pp.max_coal = c->max_coal; pp.min_mut = c->min_mut; pp.max_mut = c->max_mut;
+        pp.min_bmut = c->min_bmut; pp.max_bmut = c->max_bmut; pp.min_nb = c->min_nb; pp.max_nb = c->max_nb;
+        pp.fkeys = c->fkeys_dev; pp.n_fixed = n_mat; pp.rkeys = c->rkeys_dev; pp.n_rate = n_rate;
+        pp.bot_base = c->bot_base; pp.F = F; pp.Fp = Fp; pp.max_blocks = (int)max_blocks;
+        pp.jobs = d_jobs; pp.mat_off = d_mat_off; pp.rate = d_rate; pp.status = d_status;
+        const long long nthreads = (long long)Wc * std::max(n_mat + n_rate, 1);
+        plan_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(pp);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+
+        // root distributions
+        if (stat_dev) {
+            const long long total = (long long)Wc * Fp;
+            gather_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(stat_dev, nullptr, d_stat, Wc, F, Fp, w0);
+        } else {
+            const int Nwf = (int)c->N;
+            root_prior_kernel<<<Wc, 256, (size_t)(Nwf + 1) * sizeof(double), st>>>(params_dev + (size_t)w0 * c->ndim, c->ndim, Wc, c->breaks_dev,
+                                                                                   F, Nwf, d_stat, Fp);
+        }
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+
+        {
+            ScopedTimer timer(c, st, &c->ev_interp);
+            if (int rc = launch_interp(c, d_jobs, n_blocks, d_pool, st, c->use_v4)) return rc;
+        }
+        CUtensorMap tmapP;
+        if (int rc = make_tmap(&tmapP, d_pool, (uint64_t)n_blocks * (Fp + BLK_EXTRA), Fp, tree_prows(c))) return rc;
+
+        for (int k = 0; k < c->n_ped; ++k) {
+            const Pedigree& P = c->peds[k];
+            const int tile_block_default = std::max(1, std::min(P.n_tiles, c->num_sms / 4));
+            const long long items = (long long)Wc * P.n_tiles;
+            const int grid = (int)std::min<long long>(items, c->num_sms);
+            if (c->use_v4) {
+                Tree4Params t4{};
+                t4.tmapE = P.tmapE; t4.tmapP = tmapP;
+                t4.E = P.E; t4.E_leaf_stride = (int64_t)P.R_pad * Fp;
+                t4.scratch = scratch;
+                t4.ops = P.ops4; t4.n_ops = (int)P.ops4_h.size(); t4.n_slots = c->max_slots4;
+                t4.R = P.R; t4.L = P.L; t4.R_pad = P.R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = P.n_tiles; t4.W = Wc;
+                t4.tile_block = tile_block_default;
+                t4.pool = d_pool; t4.mat_off = d_mat_off; t4.n_mat = n_mat; t4.n_rate = n_rate; t4.rate = d_rate;
+                t4.mult = P.mult; t4.gens = c->gens_dev; t4.n_gens = c->n_gens; t4.Npop = c->N; t4.stat = d_stat;
+                t4.tile_ll = d_tile_ll; t4.asc_dot = d_asc_dot; t4.Yout = nullptr;
+                t4.wstatus = d_status;
+                const int pure_asc_tiles = (P.R_pad - (P.L + TM - 1) / TM * TM) / TM;
+                if (P.n_uroot4 > 0 && pure_asc_tiles >= 8 && !getenv("MOPE_NO_ASC_FAST") && !getenv("MOPE_NO_ASC_CSE")) {
+                    t4.uni_msg = d_uni; t4.n_uroot = P.n_uroot4;
+                    Tree4Params tc = t4;
+                    tc.canonical = 1;
+                    if (launch_tree4(c, tc, std::min(Wc, c->num_sms), st)) return MOPE_E_CUDA;
+                }
+                if (launch_tree4(c, t4, grid, st)) return MOPE_E_CUDA;
+            } else {
+                TreeParams tp{};
+                tp.tmapE = P.tmapE; tp.tmapS = tmapS; tp.tmapP = tmapP;
+                tp.E = P.E; tp.E_leaf_stride = (int64_t)P.R_pad * Fp; tp.scratch = scratch;
+                tp.ops = P.ops; tp.n_ops = P.n_ops; tp.n_slots = c->max_slots;
+                tp.R = P.R; tp.L = P.L; tp.R_pad = P.R_pad; tp.Fp = Fp; tp.F = F; tp.NT = c->NT; tp.n_tiles = P.n_tiles; tp.W = Wc;
+                tp.tile_block = tile_block_default;
+                tp.pool = d_pool; tp.mat_off = d_mat_off; tp.n_mat = n_mat; tp.n_rate = n_rate; tp.rate = d_rate;
+                tp.mult = P.mult; tp.gens = c->gens_dev; tp.n_gens = c->n_gens; tp.Npop = c->N; tp.stat = d_stat;
+                tp.tile_ll = d_tile_ll; tp.asc_dot = d_asc_dot; tp.Yout = nullptr;
+                tp.wstatus = d_status;
+                if (launch_tree(c, tp, grid, st)) return MOPE_E_CUDA;
+            }
+            FinalizeParams fp{};
+            fp.tile_ll = d_tile_ll; fp.asc_dot = d_asc_dot;
+            fp.fam_asc = P.fam_asc; fp.fam_count = P.fam_count; fp.fam_lgamma = P.fam_lgamma;
+            fp.out_ll = out_ll_dev; fp.out_root_ll = nullptr; fp.out_log_asc = nullptr;
+            fp.widx = nullptr; fp.w_base = w0; fp.wstatus = d_status;
+            fp.n_tiles = P.n_tiles; fp.n_asc = P.n_asc; fp.n_fam = P.n_fam; fp.W = Wc;
+            fp.ped_index = k; fp.ped_stride = c->n_ped; fp.asc_offset = P.asc_offset; fp.asc_stride = c->asc_total;
+            fp.accumulate = (k > 0);
+            fp.log_genome = std::log(c->genome);
+            fp.penalty = c->penalty;
+            finalize_kernel<<<Wc, 256, 0, st>>>(fp);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+        }
+    }
+    return 0;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1276,6 +1428,14 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
     if (c->has_bot)
         CUDA_TRY_C(cudaMemcpyAsync(c->tables + c->bot_base, t->bot, (size_t)t->n_nbs * t->n_bot_us * FF * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY_C(cudaMemcpyAsync(c->gens_dev, t->gens, (size_t)t->n_gens * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (t->breaks) {
+        if (t->breaks[0] != 0) return cleanup_fail(fail(MOPE_E_INVALID, "breaks must start at state 0"));
+        for (int f = 1; f < t->F; ++f)
+            if (t->breaks[f] <= t->breaks[f - 1] || t->breaks[f] > (int)t->N)
+                return cleanup_fail(fail(MOPE_E_INVALID, "breaks must be strictly ascending states in 0..N"));
+        CUDA_TRY_C(cudaMemcpyAsync(c->breaks_dev, t->breaks, (size_t)t->F * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        c->has_breaks = true;
+    }
 
     // per-frequency emission constants on the host with libm (mope/_binom.pyx:76-91)
     const int F = t->F, Fp = c->Fp;
@@ -1293,6 +1453,14 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
     }
     CUDA_TRY_C(cudaMemcpyAsync(c->asc_mask, e0.data(), F, cudaMemcpyHostToDevice, st));
     CUDA_TRY_C(cudaMemcpyAsync(c->asc_mask + F, eN.data(), F, cudaMemcpyHostToDevice, st));
+    std::vector<unsigned> lane_masks_h(64, 0u);
+    if (c->lane_masks) {
+        for (int f = 0; f < F; ++f) {
+            if (e0[f]) lane_masks_h[f & 31] |= 1u << (f >> 5);
+            if (eN[f]) lane_masks_h[32 + (f & 31)] |= 1u << (f >> 5);
+        }
+        CUDA_TRY_C(cudaMemcpyAsync(c->lane_masks, lane_masks_h.data(), 64 * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    }
 
     int asc_off = 0;
     for (int k = 0; k < m->n_ped; ++k) {
@@ -1369,6 +1537,34 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         if (int rc = make_tmap(&P.tmapE, P.E, (uint64_t)P.n_leaves * P.R_pad, Fp, TM)) return cleanup_fail(rc);
     }
     c->asc_total = asc_off;
+    {   // constants of the device-side planner
+        std::vector<FixedKeyDev> fk_h;
+        for (const FixedKey& k : c->fixed_keys) fk_h.push_back({k.var, k.bott});
+        std::vector<RateKeyDev> rk_h;
+        for (const RateKey& k : c->rate_keys) rk_h.push_back({k.var, 0, k.min_mult, k.max_mult});
+        Bump pb;
+        pb.dry = true;
+        auto carve = [&](Bump& b) {
+            c->us_dev = b.take<double>(c->n_us);
+            c->nbs_dev = b.take<double>(std::max(c->n_nbs, 1));
+            c->bot_us_dev = b.take<double>(std::max(c->n_bot_us, 1));
+            c->fkeys_dev = b.take<FixedKeyDev>(std::max<size_t>(fk_h.size(), 1));
+            c->rkeys_dev = b.take<RateKeyDev>(std::max<size_t>(rk_h.size(), 1));
+        };
+        carve(pb);
+        CUDA_TRY_C(cudaMalloc(&c->plan_consts, pb.used + 256));
+        Bump rb;
+        rb.base = c->plan_consts; rb.cap = pb.used + 256;
+        carve(rb);
+        CUDA_TRY_C(cudaMemcpyAsync(c->us_dev, c->us.data(), c->us.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (c->has_bot) {
+            CUDA_TRY_C(cudaMemcpyAsync(c->nbs_dev, c->nbs.data(), c->nbs.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            CUDA_TRY_C(cudaMemcpyAsync(c->bot_us_dev, c->bot_us.data(), c->bot_us.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        if (!fk_h.empty()) CUDA_TRY_C(cudaMemcpyAsync(c->fkeys_dev, fk_h.data(), fk_h.size() * sizeof(FixedKeyDev), cudaMemcpyHostToDevice, st));
+        if (!rk_h.empty()) CUDA_TRY_C(cudaMemcpyAsync(c->rkeys_dev, rk_h.data(), rk_h.size() * sizeof(RateKeyDev), cudaMemcpyHostToDevice, st));
+        CUDA_TRY_C(cudaStreamSynchronize(st));
+    }
     CUDA_TRY_C(cudaStreamSynchronize(st));
 #undef CUDA_TRY_C
     *out = c;
@@ -1381,6 +1577,7 @@ int mope_b200_destroy(mope_ctx* c) {
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < 2; ++i) if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
     if (c->opbuf) cudaFree(c->opbuf);
+    if (c->plan_consts) cudaFree(c->plan_consts);
     for (auto& pr : c->ev_tree) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pr : c->ev_interp) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -1405,6 +1602,53 @@ int mope_b200_eval(mope_ctx* c, const double* params, const double* stat, int W,
 int mope_b200_eval_device(mope_ctx* c, const double* params_host, const double* stat_dev, int W, void* workspace,
                           size_t ws_bytes, void* stream, double* out_ll_dev, int32_t* out_status_host) {
     return eval_impl(c, params_host, stat_dev, true, W, workspace, ws_bytes, (cudaStream_t)stream, out_ll_dev, true, out_status_host, nullptr, nullptr);
+}
+
+int mope_b200_root_prior(mope_ctx* c, const double* params_dev, int W, void* stream, double* out_stat_dev) {
+    if (!c || !params_dev || !out_stat_dev || W < 0) return fail(MOPE_E_INVALID, "root_prior: bad argument");
+    if (!c->has_breaks) return fail(MOPE_E_INVALID, "root_prior: the context was created without mope_tables_desc.breaks");
+    if (W == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int Nwf = (int)c->N;
+    root_prior_kernel<<<W, 256, (size_t)(Nwf + 1) * sizeof(double), (cudaStream_t)stream>>>(params_dev, c->ndim, W, c->breaks_dev, c->F, Nwf,
+                                                                                             out_stat_dev, c->F);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int mope_b200_eval_resident(mope_ctx* c, const double* params_dev, const double* stat_dev, const double* lnprior_dev, int W,
+                            void* workspace, size_t ws_bytes, void* stream, double* out_ll_dev, int32_t* out_status_dev) {
+    return eval_resident_impl(c, params_dev, stat_dev, lnprior_dev, W, workspace, ws_bytes, (cudaStream_t)stream, out_ll_dev, out_status_dev);
+}
+
+int mope_b200_mcmc_halfstep(mope_ctx* c, const mope_sampler_state* s, int which_half, void* workspace, size_t ws_bytes, void* stream) {
+    if (!c || !s || !s->pos || !s->lnprob || !s->naccept || !s->q || !s->folded || !s->factor || !s->lnprior || !s->ll || !s->status ||
+        !s->lower || !s->upper || !s->prior_slope)
+        return fail(MOPE_E_INVALID, "mcmc_halfstep: null argument");
+    if (s->n_walkers < 2 || (s->n_walkers & 1)) return fail(MOPE_E_INVALID, "mcmc_halfstep: the stretch move needs an even number of walkers");
+    if (s->zu && !s->partner) return fail(MOPE_E_INVALID, "mcmc_halfstep: partner indices are required with a supplied z stream");
+    if (!(s->a > 1.0)) return fail(MOPE_E_INVALID, "mcmc_halfstep: stretch scale a must exceed 1");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int half = s->n_walkers / 2;
+    SamplerParams p{};
+    p.pos = s->pos; p.lnprob = s->lnprob; p.naccept = reinterpret_cast<long long*>(s->naccept);
+    p.q = s->q; p.folded = s->folded; p.factor = s->factor; p.lnprior = s->lnprior; p.ll = s->ll;
+    p.lower = s->lower; p.upper = s->upper; p.prior_slope = s->prior_slope; p.prior_const = s->prior_const;
+    p.zu = s->zu; p.au = s->au; p.partner = s->partner;
+    p.seed = s->seed; p.step = s->step; p.a = s->a;
+    p.ndim = c->ndim; p.n_var = c->n_var; p.half = half;
+    p.first = which_half ? half : 0;
+    p.other_first = which_half ? 0 : half;
+    stretch_propose_kernel<<<(half + 127) / 128, 128, 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    if (int rc = eval_resident_impl(c, s->folded, nullptr, s->lnprior, half, workspace, ws_bytes, st, s->ll, s->status)) return rc;
+    stretch_accept_kernel<<<(half + 127) / 128, 128, 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    return 0;
 }
 
 int64_t mope_b200_launch_count(const mope_ctx* c) { return c ? c->launches : 0; }
@@ -1712,17 +1956,23 @@ int mope_b200_non_asc_probs(mope_ctx* c, const double* qualities, const int64_t*
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nq = qual_off[n_sets];
+    // sets whose K = ceil(min_freq * nreads) exceeds one register block need a carry scratch of 2 x nreads x F doubles
+    std::vector<int64_t> coff(n_sets, 0);
+    size_t carry_doubles = 0;
     for (int s = 0; s < n_sets; ++s) {
         if (qual_off[s + 1] < qual_off[s]) return fail(MOPE_E_INVALID, "non_asc_probs: offsets not ascending");
-        const int K = (int)std::ceil(min_freq * (double)(qual_off[s + 1] - qual_off[s]));
-        if (K > PB_MAXK) return fail(MOPE_E_INVALID, "non_asc_probs: ceil(min_freq*nreads) = %d exceeds the supported %d", K, PB_MAXK);
+        const int64_t n = qual_off[s + 1] - qual_off[s];
+        const int K = (int)std::ceil(min_freq * (double)n);
+        if (K > PB_BLK) { coff[s] = (int64_t)carry_doubles; carry_doubles += (size_t)2 * n * F; }
     }
+    if (carry_doubles * sizeof(double) > ((size_t)8 << 30))
+        return fail(MOPE_E_NOMEM, "non_asc_probs: the read sets of this call need %zu bytes of carry scratch; pass fewer sets per call", carry_doubles * sizeof(double));
     Bump b;
     b.dry = true;
-    double *dq, *df, *dout; int64_t* doff; int* dflag;
+    double *dq, *df, *dout, *dcarry; int64_t *doff, *dcoff;
     auto carve = [&](Bump& bb) {
-        dq = bb.take<double>(std::max<int64_t>(nq, 1)); doff = bb.take<int64_t>(n_sets + 1); df = bb.take<double>(F);
-        dout = bb.take<double>((size_t)n_sets * F); dflag = bb.take<int>(1);
+        dq = bb.take<double>(std::max<int64_t>(nq, 1)); doff = bb.take<int64_t>(n_sets + 1); dcoff = bb.take<int64_t>(n_sets);
+        df = bb.take<double>(F); dout = bb.take<double>((size_t)n_sets * F); dcarry = bb.take<double>(std::max<size_t>(carry_doubles, 1));
     };
     carve(b);
     if (ensure_opbuf(c, b.used + 256)) return MOPE_E_CUDA;
@@ -1731,9 +1981,9 @@ int mope_b200_non_asc_probs(mope_ctx* c, const double* qualities, const int64_t*
     carve(r);
     if (nq) CUDA_TRY(cudaMemcpyAsync(dq, qualities, (size_t)nq * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(doff, qual_off, (size_t)(n_sets + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dcoff, coff.data(), (size_t)n_sets * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(df, freqs, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(dflag, 0, sizeof(int), st));
-    pb_kernel<<<n_sets, 128, 0, st>>>(dq, doff, df, F, min_freq, dout, dflag);
+    pb_kernel<<<n_sets, 128, 0, st>>>(dq, doff, df, F, min_freq, dout, dcarry, dcoff);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     CUDA_TRY(cudaMemcpyAsync(out, dout, (size_t)n_sets * F * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -88,6 +88,7 @@ struct Tree4Params {
     int32_t n_uroot, canonical;
     int32_t* work_ctr;       // zeroed before the launch: next item to hand out (items differ in cost: identity branches)
     unsigned long long* unit_rows;   // statistics: += real rows x GEMM units actually run through the tensor pipe (may be null)
+    const int32_t* wstatus;  // device-planned evaluations: per-walker MOPE_ST_* bits, non-zero = skip the walker (may be null)
 };
 
 struct Tree4Smem {
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             tile = t_first + (int)(rem % t_count);
         }
         if (p.canonical) { w = (int)item; tile = 0; }
+        if (p.wstatus != nullptr && p.wstatus[w] != 0) { __syncthreads(); continue; }   // walker outside the tables / prior: NaN from finalize
         // the canonical item of a walker: the first pseudo-row pair (rows L, L + 1 = parities 0, 1) leads the tile
         const int row0 = p.canonical ? p.L : tile * TM;
         const int my_row = row0 + warp * 8 + x;     // the row this thread's fragments belong to

@@ -193,7 +193,10 @@ def loglike_locus_sharded(inf_local, X: np.ndarray, group=None):
     eng = getattr(inf_local, "engine", None)
     if eng is not None and hasattr(eng, "loglike_enqueue"):
         X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
-        ll_t, status = eng.loglike_enqueue(X, inf_local.stationary_distributions)
+        if hasattr(inf_local, "root_prior_host_mask"):
+            ll_t, status = eng.loglike_hybrid(X, inf_local.root_prior_host_mask(X), inf_local.stationary_distributions, keep_on_device=True)
+        else:
+            ll_t, status = eng.loglike_enqueue(X, inf_local.stationary_distributions)
         packed = getattr(eng, "_packed_reduce_buf", None)
         n = X.shape[0] * (1 + N_STATUS_BITS)
         if packed is None or packed.shape[0] < n:

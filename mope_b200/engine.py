@@ -55,6 +55,8 @@ class Engine:
             td.bot = td.nbs = td.bot_us = None
         td.N = float(tables.N)
         td.freqs = _lib.dptr(tables.freqs)
+        self._breaks32 = np.ascontiguousarray(tables.breaks, dtype=np.int32)
+        td.breaks = _lib.iptr(self._breaks32)
 
         pds = (_lib.PedigreeDesc * self.n_ped)()
         for k, (p, vidx) in enumerate(zip(peds, var_index)):
@@ -202,6 +204,100 @@ class Engine:
                 self._stat_dev[lo:hi].copy_(self._stat_pin[lo:hi], non_blocking=True)
                 status[lo:hi] = self.loglike_device(params[lo:hi], self._stat_dev[lo:hi], self._out_dev[lo:hi])
         return self._out_dev[:W], status
+
+    def root_prior_device(self, params: np.ndarray, out_dev=None):
+        """Root distributions of the walkers on the device (mope_b200_root_prior): params [W, ndim] host array ->
+        CUDA float64 tensor [W, F] (engine-owned scratch unless out_dev is given).  Enqueue only."""
+        torch = self.torch
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        W = params.shape[0]
+        dev = "cuda:%d" % self.device
+        if getattr(self, "_rp_W", 0) < W:
+            self._rp_pin = torch.empty((W, self.ndim), dtype=torch.float64, pin_memory=True)
+            self._rp_par = torch.empty((W, self.ndim), dtype=torch.float64, device=dev)
+            self._rp_out = torch.empty((W, self.F), dtype=torch.float64, device=dev)
+            self._rp_W = W
+        out = self._rp_out[:W] if out_dev is None else out_dev
+        with torch.cuda.device(self.device):
+            # the pinned staging row block is reused: the previous copy out of it must have completed
+            if getattr(self, "_rp_busy", None) is not None:
+                self._rp_busy.synchronize()
+            self._rp_pin.numpy()[:W] = params
+            self._rp_par[:W].copy_(self._rp_pin[:W], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._rp_busy = ev
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(self.lib.mope_b200_root_prior(self.ctx, self._rp_par.data_ptr(), W, stream, out.data_ptr()),
+                       "mope_b200_root_prior")
+        return out
+
+    def loglike_hybrid(self, params: np.ndarray, host_mask: np.ndarray, stat_fn, keep_on_device: bool = False):
+        """End-to-end evaluation with the root prior on the device for the walkers where host_mask is False and from
+        stat_fn (host, SciPy) where it is True.  The device-prior walkers are enqueued first, so the host work of the others
+        runs while the device is busy.  Returns (ll, status)."""
+        torch = self.torch
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        W = params.shape[0]
+        dev = "cuda:%d" % self.device
+        if getattr(self, "_pipe_W", 0) < W:
+            self._stat_pin = torch.empty((W, self.F), dtype=torch.float64, pin_memory=True)
+            self._stat_dev = torch.empty((W, self.F), dtype=torch.float64, device=dev)
+            self._out_dev = torch.empty(W, dtype=torch.float64, device=dev)
+            self._out_pin = torch.empty(W, dtype=torch.float64, pin_memory=True)
+            self._pipe_W = W
+        status = np.zeros(W, dtype=np.int32)
+        idx_d = np.nonzero(~host_mask)[0]
+        idx_h = np.nonzero(host_mask)[0]
+        nd, nh = idx_d.shape[0], idx_h.shape[0]
+        with torch.cuda.device(self.device):
+            if nd:
+                Xd = params[idx_d]
+                self.root_prior_device(Xd, out_dev=self._stat_dev[:nd])
+                status[idx_d] = self.loglike_device(Xd, self._stat_dev[:nd], self._out_dev[:nd])
+            if nh:
+                Xh = params[idx_h]
+                self._stat_pin.numpy()[nd:nd + nh] = stat_fn(Xh)
+                self._stat_dev[nd:nd + nh].copy_(self._stat_pin[nd:nd + nh], non_blocking=True)
+                status[idx_h] = self.loglike_device(Xh, self._stat_dev[nd:nd + nh], self._out_dev[nd:nd + nh])
+            if keep_on_device:
+                # walker order on the device, no synchronisation: (CUDA tensor [W], host status)
+                if nh == 0:
+                    return self._out_dev[:W], status
+                order = torch.as_tensor(np.concatenate((idx_d, idx_h)), device=dev)
+                sorted_out = torch.empty(W, dtype=torch.float64, device=dev)
+                sorted_out[order] = self._out_dev[:W]
+                return sorted_out, status
+            self._out_pin[:W].copy_(self._out_dev[:W], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        ll = np.empty(W)
+        got = self._out_pin[:W].numpy()
+        ll[idx_d] = got[:nd]
+        ll[idx_h] = got[nd:nd + nh]
+        return ll, status
+
+    def loglike_resident(self, params_dev, stat_dev=None, lnprior_dev=None, out_dev=None, status_dev=None):
+        """Device-resident evaluation (mope_b200_eval_resident): params_dev [W, ndim] CUDA float64 tensor of sign-folded
+        parameters; the interpolation plans and (when stat_dev is None) the root distributions are derived on the device.
+        Walkers whose lnprior_dev entry is -inf are skipped.  Returns (ll CUDA tensor [W], status CUDA int32 tensor [W]);
+        enqueue only, nothing touches the host."""
+        torch = self.torch
+        assert params_dev.is_cuda and params_dev.dtype == torch.float64 and params_dev.is_contiguous()
+        W = params_dev.shape[0]
+        dev = params_dev.device
+        out_dev = torch.empty(W, dtype=torch.float64, device=dev) if out_dev is None else out_dev
+        status_dev = torch.empty(W, dtype=torch.int32, device=dev) if status_dev is None else status_dev
+        if W == 0:
+            return out_dev, status_dev
+        ws = self._workspace(W)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = self.lib.mope_b200_eval_resident(self.ctx, params_dev.data_ptr(),
+                                                  None if stat_dev is None else stat_dev.data_ptr(),
+                                                  None if lnprior_dev is None else lnprior_dev.data_ptr(),
+                                                  W, ws.data_ptr(), ws.numel(), stream, out_dev.data_ptr(), status_dev.data_ptr())
+        _lib.check(rc, "mope_b200_eval_resident")
+        return out_dev, status_dev
 
     def loglike_device(self, params_host: np.ndarray, stat_dev, out_dev):
         """Device-resident variant: stat_dev [W, F] and out_dev [W] are CUDA float64 tensors.  Enqueue only."""

@@ -52,7 +52,7 @@ class Inference(object):
                  transition_copy=None, transition_buf=None, transition_shape=None, print_debug=False,
                  log_unif_drift=False, inverse_bot_priors=False, post_is_prior=False, lower_drift_limit=1e-3,
                  upper_drift_limit=3, min_phred_score=None, selection_model=False, device=0, workspace_bytes=None,
-                 _inputs_are_text=False, mult_bounds=None):
+                 _inputs_are_text=False, mult_bounds=None, root_prior=None):
         if selection_model:
             raise NotImplementedError("the selection model is outside the GPU log-likelihood path")
         if data_are_freqs:
@@ -78,6 +78,15 @@ class Inference(object):
         self.upper_drift_limit = upper_drift_limit
         self.min_phred_score = min_phred_score
         self.selection_model = False
+        # where the root (stationary) distribution is computed: "auto" (default) = on the device for walkers with
+        # ab >= ROOT_PRIOR_HOST_BELOW, SciPy's betainc on the host below it (there the reference's CDF differences are
+        # dominated by rounding noise that only the same betainc reproduces); "device" = always the device kernel (the more
+        # accurate values; differs from the reference by up to ~3e-10 relative in the log-likelihood at ab ~ 1e-9);
+        # "scipy" = always the host
+        import os as _os
+        self.root_prior = root_prior or _os.environ.get("MOPE_B200_ROOT_PRIOR", "auto")
+        if self.root_prior not in ("auto", "device", "scipy"):
+            raise ValueError("root_prior must be 'auto', 'device' or 'scipy'")
         self.true_params = None
         self.true_loglike = None
 
@@ -180,6 +189,16 @@ class Inference(object):
     # ------------------------------------------------------------------------------------------
     # likelihood
     # ------------------------------------------------------------------------------------------
+    ROOT_PRIOR_HOST_BELOW = 1e-6   # alphabeta below which "auto" keeps the reference's own betainc (see __init__)
+
+    def root_prior_host_mask(self, X: np.ndarray) -> np.ndarray:
+        """Walkers whose root distribution comes from SciPy's betainc on the host (see `root_prior` in __init__)."""
+        if self.root_prior == "scipy":
+            return np.ones(X.shape[0], dtype=bool)
+        if self.root_prior == "device":
+            return np.zeros(X.shape[0], dtype=bool)
+        return X[:, -2] < np.log10(self.ROOT_PRIOR_HOST_BELOW)
+
     def stationary_distributions(self, X: np.ndarray) -> np.ndarray:
         ab = 10 ** X[:, -2]
         pp = 10 ** X[:, -1]
@@ -190,7 +209,9 @@ class Inference(object):
         X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
         if X.shape[1] != self.ndim:
             raise ValueError("expected parameter vectors of length {}".format(self.ndim))
-        if X.shape[0] >= 32:
+        if self.root_prior != "scipy":
+            ll, status = self.engine.loglike_hybrid(X, self.root_prior_host_mask(X), self.stationary_distributions)
+        elif X.shape[0] >= 32:
             # large batches: root distributions (host, SciPy) for the next chunk overlap the device work of the current one
             ll, status = self.engine.loglike_pipelined(X, self.stationary_distributions)
         else:
@@ -353,11 +374,13 @@ class Inference(object):
                 print("# warning: attempted start at initial position where prior is not finite", file=file or sys.stdout)
 
     def run_mcmc(self, num_iter, num_walkers, num_processes=1, mpi=False, prev_chain=None, start_from="prior", init_norm_sd=0.2,
-                 chain_alpha=2.0, init_pos=None, pool=None, seed=None, file=None):
+                 chain_alpha=2.0, init_pos=None, pool=None, seed=None, file=None, device_sampler=False):
         """inference.py:1322-1363 with the built-in stretch-move sampler; every half-step is one device call.  `pool`,
-        `num_processes` and `mpi` are accepted for signature compatibility and ignored (the GPU is the pool)."""
+        `num_processes` and `mpi` are accepted for signature compatibility and ignored (the GPU is the pool).
+        device_sampler=True keeps the whole step on the GPU (ensemble.DeviceEnsembleSampler): only the printed ensembles
+        come back."""
         import sys
-        from .ensemble import EnsembleSampler
+        from .ensemble import DeviceEnsembleSampler, EnsembleSampler
         global inf_data
         inf_data = self
         file = file or sys.stdout
@@ -366,8 +389,11 @@ class Inference(object):
         if init_pos is None:
             init_pos = self._get_initial_mcmc_position(num_walkers, prev_chain, rng, file=file)
         print(self.header, file=file)
-        sampler = EnsembleSampler(num_walkers, self.ndim, self.log_posterior_batch, a=chain_alpha,
-                                  seed=None if seed is None else seed + 1)
+        if device_sampler:
+            sampler = DeviceEnsembleSampler(self, num_walkers, a=chain_alpha, seed=None if seed is None else seed + 1)
+        else:
+            sampler = EnsembleSampler(num_walkers, self.ndim, self.log_posterior_batch, a=chain_alpha,
+                                      seed=None if seed is None else seed + 1)
         for ps, lnprobs, _state in sampler.sample(init_pos, iterations=num_iter):
             self.print_csv_lines(self.translate_positions(ps), lnprobs, file=file)
         print("# mean acceptance across chains:", np.mean(sampler.acceptance_fraction), file=file)

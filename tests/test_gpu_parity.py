@@ -124,6 +124,24 @@ def test_poisson_binomial_matches_reference(inf_both):
     assert np.all(got[1] == 0)
 
 
+def test_poisson_binomial_any_depth(inf_both):
+    """K = ceil(min_freq * nreads) beyond one register block of the DP (the reference handles any depth,
+    _poisson_binom.pyx:18-90): block boundaries, deep read sets and a mixed ragged batch, against the oracle."""
+    from oracle import mope_oracle as orc
+    E = inf_both.engine
+    rng = np.random.RandomState(17)
+    freqs = TB["freqs"]
+    for nr, mf in ((640, 0.05), (660, 0.05), (1280, 0.05), (1300, 0.05), (2000, 0.1), (3300, 0.01)):   # K = 32, 33, 64, 65, 200, 33
+        q = rng.choice([20.0, 30.0, 40.0], size=nr, p=[0.1, 0.6, 0.3])
+        got = E.non_asc_probs([q], freqs, mf)[0]
+        np.testing.assert_allclose(got, orc.get_non_asc_probs(q, freqs, mf), rtol=1e-12, atol=1e-300)
+    sets = [rng.choice([20.0, 30.0, 40.0], size=n) for n in (50, 1500, 0, 700, 3)]                    # K = 3, 75, 0, 35, 1
+    got = E.non_asc_probs(sets, freqs, 0.05)
+    for k, q in enumerate(sets):
+        ref = orc.get_non_asc_probs(q, freqs, 0.05) if len(q) else np.zeros(freqs.shape[0])
+        np.testing.assert_allclose(got[k], ref, rtol=1e-12, atol=1e-300)
+
+
 @pytest.mark.parametrize("name", sorted(CASES.keys()))
 def test_full_likelihood_matches_reference(name):
     I = _inference(CASES[name])
@@ -234,5 +252,125 @@ def test_run_mcmc_chain_file_and_resume(tmp_path):
         buf2 = io.StringIO()
         I.run_mcmc(2, nw, prev_chain=str(fn), chain_alpha=1.4, seed=5, file=buf2)
         assert len([l for l in buf2.getvalue().splitlines() if not l.startswith("#")]) == 1 + 2 * nw
+    finally:
+        I.close()
+
+
+def test_device_root_prior(inf_both):
+    """mope_b200_root_prior against the reference's stationary distributions (golden, absolute 1e-13: the reference's own
+    cell masses carry that much rounding noise at small ab) and against an exact evaluation (mpmath, relative 1e-13)."""
+    I = inf_both
+    abpp = OUT["unit/stat_abpp"]
+    X = np.zeros((abpp.shape[0], I.ndim))
+    X[:, -2:] = np.log10(abpp)
+    got = I.engine.root_prior_device(X).cpu().numpy()
+    ref = OUT["unit/stat_dist"]
+    assert np.abs(got - ref).max() <= 1e-13
+    assert np.abs(got.sum(1) - 1).max() <= 1e-14
+    # large ab: the reference's differences are accurate there, so the relative agreement is tight as well
+    big = abpp[:, 0] >= 1e-2
+    np.testing.assert_allclose(got[big], ref[big], rtol=1e-11)
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    N = int(TB["N"])
+    Ni = N - 2
+    edges = np.arange(1, 2 * Ni, 2) / (2 * Ni)
+    for row, (a, pp) in zip(got, abpp):
+        cdf = [mp.betainc(float(a), float(a), 0, mp.mpf(float(x)), regularized=True) for x in edges]
+        cells = np.array([float(h - l) for h, l in zip(cdf + [mp.mpf(1)], [mp.mpf(0)] + cdf)])
+        d = np.zeros(N + 1)
+        d[0] = d[-1] = (1 - pp) / 2
+        d[1:-1] = cells * pp
+        exact = np.add.reduceat(d, TB["breaks"])
+        np.testing.assert_allclose(row, exact, rtol=1e-13, atol=0)
+
+
+def test_root_prior_modes_agree_within_parity(inf_both):
+    """auto (device kernel above ab = 1e-6, SciPy below) is the default; 'scipy' reproduces round 1; 'device' is the
+    all-device mode of the resident sampler.  All three within the parity bar of the reference on the golden vectors,
+    which span log10 ab from -8.5 to -0.5."""
+    I = inf_both
+    X = OUT["example_both/X"]
+    ref = OUT["example_both/loglike"]
+    assert I.root_prior == "auto"
+    mask = I.root_prior_host_mask(X)
+    assert mask.any() and (~mask).any()            # both branches exercised
+    try:
+        for mode, tol in (("auto", 1e-10), ("scipy", 1e-10), ("device", 1e-9)):
+            I.root_prior = mode
+            ll = I.loglike_batch(X)
+            assert H.relerr(ll, ref).max() <= tol, (mode, H.relerr(ll, ref).max())
+    finally:
+        I.root_prior = "auto"
+
+
+def test_device_sampler_matches_host_sampler():
+    """The device-resident stretch move (mope_b200_mcmc_halfstep) against the host EnsembleSampler fed the same uniform
+    stream: same proposals, same accept/reject decisions, hence identical positions; log-posteriors within the parity bar.
+    Then the counter-based generator: reproducible under a seed, sensible acceptance, no host evaluation calls."""
+    import time
+    from mope_b200.ensemble import DeviceEnsembleSampler, EnsembleSampler
+    I = _inference(CASES["example_both"])
+    try:
+        I.root_prior = "device"                    # the host sampler evaluates with the same root prior as the resident step
+        nw, nit = 2 * I.ndim + 4, 6
+        p0 = np.random.RandomState(9).uniform(0.7 * I.lower + 0.3 * I.upper, 0.3 * I.lower + 0.7 * I.upper, (nw, I.ndim))
+        # flip signs on the folded coordinates of a few walkers: positions are stored unfolded
+        p0[::3, I.num_varnames:2 * I.num_varnames] *= -1.0
+        host = EnsembleSampler(nw, I.ndim, I.log_posterior_batch, a=1.4, seed=77, randomize_split=False)
+        hchain = [(p, lp) for p, lp, _ in host.sample(p0, iterations=nit)]
+        dev = DeviceEnsembleSampler(I, nw, a=1.4, streams=np.random.RandomState(77))
+        calls = []
+        real = I.log_posterior_batch
+        I.log_posterior_batch = lambda X: (calls.append(np.shape(X)), real(X))[1]
+        dchain = [(p, lp) for p, lp, _ in dev.sample(p0, iterations=nit)]
+        I.log_posterior_batch = real
+        assert calls == [(nw, I.ndim)]             # only the initial ensemble goes through the host API
+        moved = 0
+        for (ph, lph), (pd_, lpd) in zip(hchain, dchain):
+            np.testing.assert_array_equal(ph, pd_)
+            assert H.relerr(lpd, lph).max() <= 1e-10
+            moved += int((ph != p0).any(axis=1).sum())
+        assert moved > 0
+        np.testing.assert_array_equal(dev.acceptance_fraction, host.acceptance_fraction)
+        assert int(dev.status_or.max().item()) in (0, 128)          # proposals are either evaluated or outside the prior
+        # Philox streams: deterministic under a seed, different under another
+        a = [p for p, _, _ in DeviceEnsembleSampler(I, nw, a=1.4, seed=5).sample(p0, iterations=4)][-1]
+        b = [p for p, _, _ in DeviceEnsembleSampler(I, nw, a=1.4, seed=5).sample(p0, iterations=4)][-1]
+        c = [p for p, _, _ in DeviceEnsembleSampler(I, nw, a=1.4, seed=6).sample(p0, iterations=4)][-1]
+        np.testing.assert_array_equal(a, b)
+        assert (a != c).any()
+        s = DeviceEnsembleSampler(I, nw, a=1.4, seed=11)
+        last = None
+        for p, lp, _ in s.sample(p0, iterations=40):
+            last = (p, lp)
+        acc = s.acceptance_fraction.mean()
+        assert 0.05 < acc < 0.95, acc
+        # the stored log-posteriors belong to the stored positions
+        chk = I.log_posterior_batch(last[0])
+        assert H.relerr(last[1], chk).max() <= 1e-10
+        # host time per half-step of the resident sampler (enqueue only)
+        s2 = DeviceEnsembleSampler(I, nw, a=1.4, seed=12)
+        list(s2.sample(p0, iterations=3))
+        ws = I.engine._workspace(nw // 2)
+        st = s2._state(1000)
+        import ctypes as C
+        import torch
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 50
+        for k in range(n):
+            st.step = 1000 + k
+            assert I.engine.lib.mope_b200_mcmc_halfstep(I.engine.ctx, C.byref(st), k & 1, ws.data_ptr(), ws.numel(),
+                                                        torch.cuda.current_stream().cuda_stream) == 0
+        host_us = (time.perf_counter() - t0) / n * 1e6
+        torch.cuda.synchronize()
+        print("host time per resident half-step: %.1f us" % host_us)
+        # full chain through Inference.run_mcmc(device_sampler=True): reference chain-file format
+        import io
+        buf = io.StringIO()
+        I.run_mcmc(3, nw, chain_alpha=1.4, seed=3, file=buf, device_sampler=True, init_pos=p0)
+        body = [l for l in buf.getvalue().splitlines() if not l.startswith("#")]
+        assert body[0] == I.header and len(body) == 1 + 3 * nw
     finally:
         I.close()

@@ -1,6 +1,8 @@
 """GPU tests on the BASELINE.json workload shapes: oracle comparisons at sizes the oracle finishes in seconds, and
 size-independent properties (row-permutation invariance, additivity over a family partition, determinism) at the full
 cfg2 row count.  All through the C ABI."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -183,3 +185,67 @@ def test_locus_shards_with_rate_branches_sum_to_full():
         tot += Il.loglike_batch(X)
         Il.close()
     assert (np.abs(tot - ll) / np.abs(ll)).max() < 1e-12
+
+
+def test_resident_evaluation_matches_host_planned():
+    """mope_b200_eval_resident (plans and root prior derived by kernels from device-resident parameters) against the
+    host-planned path on every kind of branch: fixed, age-scaled, bottleneck, identity short-cuts, walkers outside the
+    tables, and walkers skipped through lnprior = -inf.  Same arithmetic up to the device's pow(): rtol 1e-12."""
+    import torch
+    from tests import helpers as H
+    CASES = H.load_cases()
+    OUT = H.load_outputs()
+    TBL = H.load_tables()
+    from mope_b200 import Inference, TransitionTables
+    tb = TransitionTables(drift=TBL["drift"], gens=TBL["gens"], us=TBL["us"], N=float(TBL["N"]), freqs=TBL["freqs"],
+                          breaks=TBL["breaks"], bot=TBL["bot"], nbs=TBL["nbs"], bot_us=TBL["bot_us"])
+    for name in ("example_both", "two_pedigrees", "example_fixed"):
+        case = CASES[name]
+        peds = case["peds"]
+        opts = dict(log_unif_drift=True)
+        opts.update(case.get("opts", {}))
+        I = Inference([p["data"] for p in peds], [p["tree"] for p in peds], [p["ages"] for p in peds], tb, _inputs_are_text=True, **opts)
+        try:
+            X = OUT[name + "/X"].copy()
+            nv = I.num_varnames
+            bad_mut = X[1].copy()
+            bad_mut[nv] = 3.0                                   # mutation rate beyond the table
+            bad_time = X[2].copy()
+            bad_time[:nv] = 1.5                                 # drift beyond the table
+            X = np.vstack([X, bad_mut, bad_time])
+            W = X.shape[0]
+            lnprior = np.zeros(W)
+            lnprior[3] = -np.inf
+            # reference: the host-planned path with the same (device) root prior, so that the comparison isolates the planner
+            stat = I.engine.root_prior_device(X).clone()
+            out = torch.empty(W, dtype=torch.float64, device=stat.device)
+            st_host = I.engine.loglike_device(X, stat, out)
+            ll_host = out.cpu().numpy()
+            Xd = torch.as_tensor(X, device=stat.device)
+            ll_res, st_res = I.engine.loglike_resident(Xd, lnprior_dev=torch.as_tensor(lnprior, device=stat.device))
+            ll_res, st_res = ll_res.cpu().numpy(), st_res.cpu().numpy()
+            assert st_res[3] == 128 and np.isnan(ll_res[3])
+            st_res[3] = st_host[3]
+            np.testing.assert_array_equal(st_res, st_host)
+            assert st_host[-1] != 0 and st_host[-2] != 0
+            ok = st_host == 0
+            ok[3] = False
+            assert np.all(np.isnan(ll_res[~ok]))
+            np.testing.assert_allclose(ll_res[ok], ll_host[ok], rtol=1e-12)
+            # a workspace that holds two walkers at a time gives the same numbers (chunked, static pool layout)
+            mn, full = C.c_size_t(0), C.c_size_t(0)
+            I.engine.lib.mope_b200_workspace_bytes(I.engine.ctx, 2, C.byref(mn), C.byref(full))
+            small = torch.empty(int(full.value), dtype=torch.uint8, device=stat.device)
+            out2 = torch.empty(W, dtype=torch.float64, device=stat.device)
+            st2 = torch.empty(W, dtype=torch.int32, device=stat.device)
+            rc = I.engine.lib.mope_b200_eval_resident(I.engine.ctx, Xd.data_ptr(), None, None, W, small.data_ptr(), small.numel(),
+                                                      torch.cuda.current_stream().cuda_stream, out2.data_ptr(), st2.data_ptr())
+            assert rc == 0
+            got2 = out2.cpu().numpy()
+            np.testing.assert_array_equal(got2[ok], ll_res[ok])
+            assert np.isfinite(got2[3]) and abs(got2[3] - ll_host[3]) <= 1e-12 * abs(ll_host[3])   # not skipped without lnprior
+            # and against the reference's golden values (auto root prior rules apply: the device prior is within 1e-9 everywhere)
+            ref = OUT[name + "/loglike"]
+            assert H.relerr(ll_res[:ref.shape[0]][ok[:ref.shape[0]]], ref[ok[:ref.shape[0]]]).max() <= 1e-9
+        finally:
+            I.close()
