@@ -263,6 +263,16 @@ __host__ __device__ __forceinline__ int interp_rows_per_tile(int F) {
     while (rows > 1 && (size_t)4 * interp_buf_doubles(rows, F) * sizeof(double) > 52 * 1024) rows >>= 1;
     return rows;
 }
+// Wide grids (F = 1001: one staged row is 8 KB per source) leave too few rows per tile for the row-sum chains to hide
+// behind the memory phases; they stage through registers instead (coalesced loads, only the blended tile in shared
+// memory, odd row stride) and fit four times as many rows.
+__host__ __device__ __forceinline__ int interp_row_stride_ldg(int F) { return F | 1; }
+__host__ __device__ __forceinline__ int interp_rows_per_tile_ldg(int F) {
+    int rows = 32;
+    while (rows > 1 && (size_t)rows * interp_row_stride_ldg(F) * sizeof(double) > 52 * 1024) rows >>= 1;
+    return rows;
+}
+__host__ __device__ __forceinline__ bool interp_use_bulk(int F) { return interp_rows_per_tile(F) >= 8; }
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
@@ -288,15 +298,54 @@ __device__ __forceinline__ void interp_blend(double* __restrict__ tile, const do
     }
 }
 
+// blend straight from global memory into the shared tile (wide grids), 16 independent loads per thread in flight
+template <bool TWO, bool CHECK>
+__device__ __forceinline__ void interp_blend_ldg(double* __restrict__ tile, int FS, const double* __restrict__ q11, const double* __restrict__ q12,
+                                                 const double* __restrict__ q21, const double* __restrict__ q22, double w11, double w12,
+                                                 double w21, double w22, int n, int F, unsigned div_magic) {
+    constexpr int U = 4;
+    for (int base = threadIdx.x; base < n; base += U * INTERP_THREADS) {
+        double a[U], b[U], c[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = base + u * INTERP_THREADS;
+            if (e < n) {
+                a[u] = __ldg(q11 + e);
+                b[u] = __ldg(q12 + e);
+                if (!TWO) { c[u] = __ldg(q21 + e); d[u] = __ldg(q22 + e); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = base + u * INTERP_THREADS;
+            if (e < n) {
+                double v;
+                if (TWO) {
+                    v = __dadd_rn(__dmul_rn(a[u], w11), __dmul_rn(b[u], w12));
+                } else {
+                    v = __dadd_rn(__dmul_rn(a[u], w11), __dmul_rn(c[u], w21));
+                    v = __dadd_rn(v, __dmul_rn(b[u], w12));
+                    v = __dadd_rn(v, __dmul_rn(d[u], w22));
+                }
+                if (CHECK) v = fmin(fmax(v, 0.0), 1.0);
+                const int r = (int)__umulhi((unsigned)e, div_magic);   // e / F (exact for e < 2^16)
+                tile[r * FS + (e - r * F)] = v;
+            }
+        }
+    }
+}
+
+template <bool BULK>
 __global__ void __launch_bounds__(INTERP_THREADS, 4)
 interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __restrict__ tables, double* __restrict__ pool, int F, int Fp,
               int perm, const int8_t* __restrict__ asc_mask /* [2][F]: e0 then eN, may be null */,
               const unsigned* __restrict__ lane_masks /* [2][32] bit k of word l: column l + 32 k is in e0 / eN (F <= 1024), may be null */,
-              int rows, int tiles_per_job) {
-    extern __shared__ __align__(16) double stage[];   // [4][interp_buf_doubles(rows, F)]
+              int rows, int tiles_per_job, unsigned div_magic /* ceil(2^32 / F), register-staged variant */) {
+    extern __shared__ __align__(16) double stage[];   // BULK: [4][interp_buf_doubles(rows, F)]; else the tile [rows][F | 1]
     __shared__ double s_sum[32];
     __shared__ unsigned long long bar;
     const int BUF = interp_buf_doubles(rows, F);
+    const int TS = BULK ? F : interp_row_stride_ldg(F);   // row stride of the blended tile
     const int j = blockIdx.x / tiles_per_job;
     const int i0 = (blockIdx.x - j * tiles_per_job) * rows;   // first matrix row of the tile
     const InterpJob jb = jobs[j];
@@ -310,7 +359,20 @@ interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __re
     const bool check = (jb.flags & 1) != 0;
     double* tile = stage;                     // the blended tile replaces the first staged run (plus its alignment offset)
 
-    if (nreal > 0 && !ident) {
+    if (nreal > 0 && !ident && !BULK) {
+        const int n = nreal * F;
+        const size_t off = (size_t)i0 * F;
+        const double* q11 = tables + jb.src[0] + off;
+        const double* q12 = tables + jb.src[1] + off;
+        const double* q21 = tables + jb.src[2] + off;
+        const double* q22 = tables + jb.src[3] + off;
+        const double w11 = jb.w[0], w12 = jb.w[1], w21 = jb.w[2], w22 = jb.w[3];
+        if (two) interp_blend_ldg<true, false>(tile, TS, q11, q12, q21, q22, w11, w12, w21, w22, n, F, div_magic);
+        else if (check) interp_blend_ldg<false, true>(tile, TS, q11, q12, q21, q22, w11, w12, w21, w22, n, F, div_magic);
+        else interp_blend_ldg<false, false>(tile, TS, q11, q12, q21, q22, w11, w12, w21, w22, n, F, div_magic);
+        __syncthreads();
+    }
+    if (nreal > 0 && !ident && BULK) {
         const int n = nreal * F;
         const size_t off = (size_t)i0 * F;
         const int nsrc = two ? 2 : 4;
@@ -343,9 +405,11 @@ interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __re
         else if (check) interp_blend<false, true>(tile, q12, q21, q22, w11, w12, w21, w22, n);
         else interp_blend<false, false>(tile, q12, q21, q22, w11, w12, w21, w22, n);
         __syncthreads();
+    }
+    if (nreal > 0 && !ident) {
         // ---- phase 2: the reference's sequential row sums, one chain per thread ----
         if (threadIdx.x < nreal) {
-            const double* row = tile + threadIdx.x * F;
+            const double* row = tile + threadIdx.x * TS;
             double s = 0.0;
 #pragma unroll 8
             for (int f = 0; f < F; ++f) s = __dadd_rn(s, row[f]);
@@ -385,7 +449,7 @@ interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __re
             }
             continue;
         }
-        const double* row = tile + r * F;
+        const double* row = tile + r * TS;
         const double s = s_sum[r];
         const bool div = check && (s > 1.0);
         // v / s for a whole row: one correctly rounded reciprocal, then per element q0 = v * rcp, rem = v - s * q0 (exact in

@@ -629,19 +629,28 @@ int launch_tree_t(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) 
 // one CTA per (matrix, tile of rows): see interp_kernel
 int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d_pool, cudaStream_t st, bool perm) {
     const int F = c->F, Fp = c->Fp;
-    const int rows = interp_rows_per_tile(F);
+    const bool bulk = interp_use_bulk(F);
+    const int rows = bulk ? interp_rows_per_tile(F) : interp_rows_per_tile_ldg(F);
     const int tiles = (Fp + rows - 1) / rows;
-    const size_t smem = (size_t)4 * interp_buf_doubles(rows, F) * sizeof(double);
+    const size_t smem = bulk ? (size_t)4 * interp_buf_doubles(rows, F) * sizeof(double) : (size_t)rows * interp_row_stride_ldg(F) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(interp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
+    if (!bulk && (size_t)rows * F >= 65536) return fail(MOPE_E_INVALID, "interp: tile of %d x %d elements exceeds the index range of the fast division", rows, F);
+    const unsigned magic = (unsigned)((0x100000000ull + (unsigned long long)F - 1) / (unsigned long long)F);
     const unsigned long long grid = (unsigned long long)n_jobs * tiles;
     if (grid > 0x7fffffffull) return fail(MOPE_E_INVALID, "interp: too many matrices in one launch (%zu)", n_jobs);
-    interp_kernel<<<(unsigned)grid, INTERP_THREADS, smem, st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, F, Fp, perm ? 1 : 0, c->asc_mask,
-                                                                c->lane_masks, rows, tiles);
+    if (bulk)
+        interp_kernel<true><<<(unsigned)grid, INTERP_THREADS, smem, st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, F, Fp, perm ? 1 : 0, c->asc_mask,
+                                                                          c->lane_masks, rows, tiles, magic);
+    else
+        interp_kernel<false><<<(unsigned)grid, INTERP_THREADS, smem, st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, F, Fp, perm ? 1 : 0, c->asc_mask,
+                                                                           c->lane_masks, rows, tiles, magic);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return 0;

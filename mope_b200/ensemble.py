@@ -115,7 +115,7 @@ class DeviceEnsembleSampler(object):
         self._const = const
         self._ring_pos = torch.empty((self.depth, W, nd), dtype=f64, pin_memory=True)
         self._ring_lp = torch.empty((self.depth, W), dtype=f64, pin_memory=True)
-        self.status_or = torch.zeros(half, dtype=torch.int32, device=dev)   # OR of the proposals' MOPE_ST_* bits over the run
+        self.status_or = torch.zeros(half, dtype=torch.int32, device=dev)   # OR of the MOPE_ST_* bits of in-prior proposals over the run (0 = none left the tables)
 
     @property
     def acceptance_fraction(self) -> np.ndarray:
@@ -180,7 +180,8 @@ class DeviceEnsembleSampler(object):
                                      None if au is None else au[it, h])
                     self._lib.check(lib.mope_b200_mcmc_halfstep(ctx, C.byref(st), h, ws.data_ptr(), ws.numel(), stream.cuda_stream),
                                     "mope_b200_mcmc_halfstep")
-                    self.status_or |= self._scratch["status"]
+                    stt = self._scratch["status"]
+                    self.status_or |= torch.where((stt & 128) != 0, torch.zeros_like(stt), stt)   # proposals outside the prior do not count
                 slot = it % self.depth
                 self._ring_pos[slot].copy_(self.pos, non_blocking=True)
                 self._ring_lp[slot].copy_(self.lnprob, non_blocking=True)

@@ -333,7 +333,7 @@ def test_device_sampler_matches_host_sampler():
             moved += int((ph != p0).any(axis=1).sum())
         assert moved > 0
         np.testing.assert_array_equal(dev.acceptance_fraction, host.acceptance_fraction)
-        assert int(dev.status_or.max().item()) in (0, 128)          # proposals are either evaluated or outside the prior
+        assert int(dev.status_or.max().item()) == 0                 # no in-prior proposal left the tables
         # Philox streams: deterministic under a seed, different under another
         a = [p for p, _, _ in DeviceEnsembleSampler(I, nw, a=1.4, seed=5).sample(p0, iterations=4)][-1]
         b = [p for p, _, _ in DeviceEnsembleSampler(I, nw, a=1.4, seed=5).sample(p0, iterations=4)][-1]
