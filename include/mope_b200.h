@@ -217,7 +217,9 @@ int mope_b200_last_eval_stats(const mope_ctx* ctx, int64_t* gemm_ops, int64_t* i
 /* Executed work of the last eval, counted by the pruning kernel itself: the sum over all GEMM units it ran through the
  * tensor pipe (a unit = one branch, or one generation segment of an age-scaled branch, on one tile) of the unit's real
  * rows.  2 * F^2 * unit_rows = executed flops.  Branches forwarded by the identity short-cut, generation segments no
- * row of a warp blends, and the ascertainment short-cuts do not count.  Synchronises the stream of the last eval. */
+ * row of a warp blends, the ascertainment short-cuts and the K chunks of a leaf branch in which a warp's eight emission
+ * rows are exactly zero (skipped: they add nothing) do not count -- the kernels count rows x k columns and this returns
+ * that sum / F.  Synchronises the stream of the last eval. */
 int mope_b200_last_eval_unit_rows(mope_ctx* ctx, int64_t* unit_rows);
 
 /* Measurement support (bench.py).  With profiling on, every pruning-kernel launch is bracketed by CUDA events on
@@ -260,6 +262,28 @@ int mope_b200_non_asc_probs(mope_ctx* ctx, const double* qualities, const int64_
  * threads (no interpreter lock involved).  Pure host code: no context, no device. */
 int mope_b200_beta_cdf_table(void* betainc_fn, const double* ab, int n_ab, const double* edges, int n_edges,
                              double* out, int n_threads);
+
+/* ---- transition-table generator (replaces the NumPy/SciPy loops of mope/generate_transitions.py) ----
+ * Device pointers, fp64, row-major; no context (tables are generated before any model exists).  `stream` is a
+ * cudaStream_t (0 = default); the calls are asynchronous on it. */
+
+/* P[i][j] = Binomial(j; n_trials, p_host[i]) for i < rows_valid and j <= n_trials, 0 elsewhere in the rows x cols matrix
+ * (leading dimension ld): the Wright-Fisher matrix (generate_transitions.py:57-67: n_trials = N, p = pstar) and the
+ * bottleneck factors (_transition.pyx:6-33: rows_valid = N1 + 1, n_trials = N2). */
+int mope_b200_gen_binom_matrix(double* P_dev, int ld, int rows, int cols, int rows_valid, int n_trials,
+                               const double* p_host, void* stream);
+
+/* At[c][r] = A[r][c] (rows x cols -> cols x rows). */
+int mope_b200_gen_transpose(const double* A_dev, double* At_dev, int rows, int cols, int lda, int ldt, void* stream);
+
+/* C[M x N] = A[M x K] . Bt[N x K]^T on the fp64 tensor pipe (np.dot / np.linalg.matrix_power of
+ * generate_transitions.py:48-53,217-228,386-414).  16-byte aligned operands, even leading dimensions. */
+int mope_b200_gen_dgemm_tn(const double* A_dev, const double* Bt_dev, double* C_dev, int M, int N, int K,
+                           int lda, int ldbt, int ldc, void* stream);
+
+/* out[F][F] = bin_matrix(P, breaks) (generate_transitions.py:194-208); breaks_dev: int32 [F] first state of every bin. */
+int mope_b200_gen_bin_matrix(const double* P_dev, int ld, int n_states, const int32_t* breaks_dev, int F,
+                             double* out_dev, void* stream);
 
 const char* mope_b200_last_error(void);
 const char* mope_b200_version(void);

@@ -67,6 +67,7 @@ SYMBOLS = ["mope_b200_arena_bytes", "mope_b200_create", "mope_b200_destroy", "mo
            "mope_b200_eval", "mope_b200_eval_device", "mope_b200_eval_resident", "mope_b200_mcmc_halfstep", "mope_b200_root_prior", "mope_b200_launch_count", "mope_b200_schedule_stats", "mope_b200_last_eval_stats", "mope_b200_last_eval_unit_rows", "mope_b200_set_profiling",
            "mope_b200_kernel_times", "mope_b200_fp64_peak", "mope_b200_transition_matrix",
            "mope_b200_leaf_likelihoods", "mope_b200_branch_update", "mope_b200_non_asc_probs", "mope_b200_beta_cdf_table",
+           "mope_b200_gen_binom_matrix", "mope_b200_gen_transpose", "mope_b200_gen_dgemm_tn", "mope_b200_gen_bin_matrix",
            "mope_b200_last_error", "mope_b200_version"]
 
 ST_MESSAGES = {
@@ -116,6 +117,10 @@ def lib():
     L.mope_b200_branch_update.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, C.c_double, vp, ip]
     L.mope_b200_non_asc_probs.argtypes = [vp, dp, C.POINTER(C.c_int64), C.c_int, dp, C.c_int, C.c_double, vp, dp]
     L.mope_b200_beta_cdf_table.argtypes = [vp, dp, C.c_int, dp, C.c_int, dp, C.c_int]
+    L.mope_b200_gen_binom_matrix.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.mope_b200_gen_transpose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.mope_b200_gen_dgemm_tn.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.mope_b200_gen_bin_matrix.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]
     L.mope_b200_last_error.restype = C.c_char_p
     L.mope_b200_version.restype = C.c_char_p
     for name in SYMBOLS:

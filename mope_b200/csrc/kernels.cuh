@@ -93,8 +93,9 @@ struct TreeParams {
     double* Yout;            // operator-level mode (single op): Y rows go to Yout[w][row][Fp] instead of a slot
     int32_t debug;           // measurement only: 1 = skip the MMAs (data movement only), 2 = skip the copies (MMAs only)
     int32_t* work_ctr;       // zeroed before the launch: next item to hand out
-    unsigned long long* unit_rows;   // statistics: += real rows x GEMM units (branch x generation segment) executed (may be null)
+    unsigned long long* unit_rows;   // statistics: += real rows x k columns of the GEMM units (branch x generation segment) executed (may be null)
     const int32_t* wstatus;  // device-planned evaluations: per-walker MOPE_ST_* bits, non-zero = skip the walker (may be null)
+    const unsigned long long* emask;   // [n_leaves][R_pad / 8]: K chunks of an 8-row group of E that are not all zero (may be null)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -169,6 +170,31 @@ __global__ void emission_kernel(EmissionParams p) {
         }
         out[p.perm ? kperm(f) : f] = v;
     }
+}
+
+// Which 16-wide K chunks of an 8-row group of the emission tensor hold a non-zero at all: bit c of
+// emask[leaf][row / 8] is set iff some E[leaf][8g .. 8g+7][16c .. 16c+15] != 0.  A binomial emission underflows to an
+// exact 0.0 some 37 standard deviations away from the observed frequency (38 % of the cfg2 tensor), and a chunk of zeros
+// adds exactly nothing to a leaf-branch GEMM, so the pruning kernels skip those chunks (bit-identical results).  The
+// k permutation of tree_kernel4 stays inside a chunk, so one mask serves both layouts.  One warp per (leaf, group).
+__global__ void emission_mask_kernel(const double* __restrict__ E, unsigned long long* __restrict__ emask, int S, int R_pad, int Fp) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long total = (long long)S * (R_pad / 8);
+    if (warp >= total) return;
+    const double* e = E + (size_t)warp * 8 * Fp;   // rows of a leaf are contiguous and R_pad is a multiple of 8
+    const int nch = Fp / KC;
+    unsigned long long m = 0;
+    if (nch > 64) { m = ~0ull; }
+    else {
+        for (int i = lane; i < 8 * Fp; i += 32) {
+            const int col = i % Fp;
+            if (e[i] != 0.0) m |= 1ull << (col / KC);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+    }
+    if (lane == 0) emask[warp] = m;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -524,10 +550,13 @@ __device__ __forceinline__ void issue_V(const TreeParams& p, unsigned char* ring
 // acc += (V0 .* V1 .* w)[64 x K] * P[rows x K]^T for this warp's 16 rows x NTW n-tiles; chunks g0 .. g0+nchunks-1 of
 // the ring.  Lane 0 of warp 0 keeps the ring PF chunks ahead.
 // cross: 0 = nothing follows in the ring, 1 = the next unit's P tiles may be issued ahead, 2 = its P and V tiles.
+// cm: bit c clear = the warp's 16 operand rows are exactly zero in chunk c (leaf branches, emission_mask_kernel): the chunk
+// adds nothing and its MMAs are skipped.  Returns the k columns actually run through the tensor pipe.
 template <int NTW, int NSRC, bool SCALED>
-__device__ __forceinline__ void gemm_unit(double (&acc)[2][NTW][2], const TreeParams& p, unsigned char* ring, TreeSmem* ts,
-                                          const UnitDesc& u, int nchunks, unsigned g0, double w0, double w1,
-                                          const UnitDesc& un, int cross, unsigned epi_n) {
+__device__ __forceinline__ int gemm_unit(double (&acc)[2][NTW][2], const TreeParams& p, unsigned char* ring, TreeSmem* ts,
+                                         const UnitDesc& u, int nchunks, unsigned g0, double w0, double w1,
+                                         const UnitDesc& un, int cross, unsigned epi_n, unsigned long long cm) {
+    int kcols = 0;
     using Cfg = TileCfg<NTW>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp & 3, wn = warp >> 2;
@@ -557,7 +586,9 @@ __device__ __forceinline__ void gemm_unit(double (&acc)[2][NTW][2], const TreePa
         const unsigned s = g % NS;
         if (p.debug < 2) mbar_wait(&ts->full[s], (g / NS) & 1u);
         const unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
-        if (p.debug != 1)
+        const bool run = (cm >> c) & 1ull;
+        kcols += run ? min(KC, p.F - KC * c) : 0;
+        if (p.debug != 1 && run)
 #pragma unroll
         for (int q = 0; q < KC / 4; ++q) {
             const int oq = ((q ^ z) << 4);
@@ -580,6 +611,7 @@ __device__ __forceinline__ void gemm_unit(double (&acc)[2][NTW][2], const TreePa
         __syncwarp();
         if (p.debug < 2 && lane == 0) mbar_arrive(&ts->empty[s]);
     }
+    return kcols;
 }
 
 template <int NTW>
@@ -771,11 +803,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                     }
                 }
 
-                if (pass == 0 && threadIdx.x == 0 && p.unit_rows != nullptr) {
-                    const int nun = (op.kind == 0) ? (identity ? 0 : 1) : max(0, ts->seg_hi - ts->seg_lo + 1);
-                    const int real = max(0, min(TM, p.R - row0));
-                    if (nun > 0 && real > 0) atomicAdd(p.unit_rows, (unsigned long long)nun * (unsigned)real);
+                // leaf branches: K chunks in which the warp's 16 emission rows are exactly zero are skipped
+                unsigned long long cm = ~0ull;
+                if (u.v_is_E && op.nsrc == 1 && p.emask != nullptr) {
+                    const unsigned long long* em = p.emask + ((size_t)op.src[0] * p.R_pad + row0) / 8 + 2 * wm;
+                    cm = em[0] | em[1];
                 }
+                int kcols = 0;
                 if (op.kind == 0) {
                     if (!identity) {
                         u.p_row = ts->prow[oi] + t0 * 8;
@@ -784,8 +818,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                             for (int c = 0; c < PF && c < nchunks; ++c) { issue_P<NTW>(p, ring, ts, u, c, g + c); issue_V<NTW>(p, ring, ts, u, c, g + c); }
                         }
                         const int cross = have_next ? (next_v_early ? 2 : 1) : 0;
-                        if (op.nsrc == 2) gemm_unit<NTW, 2, false>(acc, p, ring, ts, u, nchunks, g, 1.0, 1.0, un, cross, epi_n);
-                        else gemm_unit<NTW, 1, false>(acc, p, ring, ts, u, nchunks, g, 1.0, 1.0, un, cross, epi_n);
+                        if (op.nsrc == 2) kcols += gemm_unit<NTW, 2, false>(acc, p, ring, ts, u, nchunks, g, 1.0, 1.0, un, cross, epi_n, cm);
+                        else kcols += gemm_unit<NTW, 1, false>(acc, p, ring, ts, u, nchunks, g, 1.0, 1.0, un, cross, epi_n, cm);
                         g += nchunks;
                         prologue_issued = false;
                     }
@@ -801,13 +835,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel(const __grid_constant
                             if (epi_n > 0) mbar_wait(&ts->epi, (epi_n - 1) & 1u);
                             for (int c = 0; c < PF && c < nchunks; ++c) { issue_P<NTW>(p, ring, ts, u, c, g + c); issue_V<NTW>(p, ring, ts, u, c, g + c); }
                         }
-                        if (op.nsrc == 2) gemm_unit<NTW, 2, true>(acc, p, ring, ts, u, nchunks, g, w0, w1, un, 0, epi_n);
-                        else gemm_unit<NTW, 1, true>(acc, p, ring, ts, u, nchunks, g, w0, w1, un, 0, epi_n);
+                        if (op.nsrc == 2) kcols += gemm_unit<NTW, 2, true>(acc, p, ring, ts, u, nchunks, g, w0, w1, un, 0, epi_n, cm);
+                        else kcols += gemm_unit<NTW, 1, true>(acc, p, ring, ts, u, nchunks, g, w0, w1, un, 0, epi_n, cm);
                         g += nchunks;
                     }
                     prologue_issued = false;
                 }
 
+                // executed work: every pass runs the same chunks, so pass 0 of the warps of one N half counts for the branch
+                if (pass == 0 && wn == 0 && lane == 0 && kcols > 0 && p.unit_rows != nullptr) {
+                    const int real = max(0, min(16, p.R - (row0 + wm * 16)));
+                    if (real > 0) atomicAdd(p.unit_rows, (unsigned long long)kcols * (unsigned)real);
+                }
                 // Units that could not run ahead inside the main loop (age-scaled branches, identity-skipped GEMMs): start the
                 // next unit's tiles here, under the epilogue.
                 const bool issued_in_loop = (op.kind == 0 && !identity);

@@ -21,6 +21,7 @@
 #include "../../include/mope_b200.h"
 #include "kernels.cuh"
 #include "tree4.cuh"
+#include "generate.cuh"
 
 using namespace mope;
 
@@ -66,6 +67,7 @@ struct Pedigree {
     int n_leaves = 0, n_branches = 0, L = 0, n_fam = 0, n_mult = 0, n_asc = 0;
     int R = 0, R_pad = 0, n_tiles = 0, n_slots = 0, n_ops = 0;
     double* E = nullptr;
+    unsigned long long* emask = nullptr;   // [n_leaves][R_pad / 8] non-zero K chunks of E per 8-row group (emission_mask_kernel)
     double* mult = nullptr;  // [n_mult][R_pad]
     int32_t* fam_asc = nullptr;
     double* fam_count = nullptr;
@@ -561,6 +563,7 @@ int layout_arena(mope_ctx* c, const mope_tables_desc* t, const mope_model_desc* 
         const int R = pd.n_loci + 2 * pd.n_asc;
         const int R_pad = round_up_i(std::max(R, 1), TM);
         double* E = bump.take<double>((size_t)pd.n_leaves * R_pad * Fp);
+        unsigned long long* em = bump.take<unsigned long long>((size_t)pd.n_leaves * (R_pad / 8));
         double* mu = bump.take<double>((size_t)std::max(pd.n_mult, 1) * R_pad);
         int32_t* fa = bump.take<int32_t>(pd.n_fam);
         double* fc = bump.take<double>(pd.n_fam);
@@ -569,7 +572,7 @@ int layout_arena(mope_ctx* c, const mope_tables_desc* t, const mope_model_desc* 
         Op4* ops4 = bump.take<Op4>(pd.n_branches);
         if (!dry) {
             Pedigree& P = c->peds[k];
-            P.E = E; P.mult = mu; P.fam_asc = fa; P.fam_count = fc; P.fam_lgamma = fl; P.ops = ops; P.ops4 = ops4;
+            P.E = E; P.emask = em; P.mult = mu; P.fam_asc = fa; P.fam_count = fc; P.fam_lgamma = fl; P.ops = ops; P.ops4 = ops4;
         }
     }
     // transient inputs of the emission kernel live at the arena tail; they are dead after create().
@@ -1082,7 +1085,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
             if (c->use_v4) {
                 Tree4Params t4{};
                 t4.tmapE = P.tmapE; t4.tmapP = tmapP;
-                t4.E = P.E; t4.E_leaf_stride = (int64_t)P.R_pad * Fp;
+                t4.E = P.E; t4.E_leaf_stride = (int64_t)P.R_pad * Fp; t4.emask = getenv("MOPE_NO_EMASK") ? nullptr : P.emask;
                 t4.scratch = scratch;
                 t4.ops = P.ops4; t4.n_ops = (int)P.ops4_h.size(); t4.n_slots = c->max_slots4;
                 t4.R = P.R; t4.L = P.L; t4.R_pad = P.R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = P.n_tiles; t4.W = Wc;
@@ -1107,7 +1110,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
             tp.tmapE = P.tmapE;
             tp.tmapS = tmapS;
             tp.tmapP = tmapP;
-            tp.E = P.E;
+            tp.E = P.E; tp.emask = (getenv("MOPE_NO_EMASK") || c->Fp / KC > 64) ? nullptr : P.emask;
             tp.E_leaf_stride = (int64_t)P.R_pad * Fp;
             tp.scratch = scratch;
             tp.ops = P.ops;
@@ -1276,7 +1279,7 @@ int eval_resident_impl(mope_ctx* c, const double* params_dev, const double* stat
             if (c->use_v4) {
                 Tree4Params t4{};
                 t4.tmapE = P.tmapE; t4.tmapP = tmapP;
-                t4.E = P.E; t4.E_leaf_stride = (int64_t)P.R_pad * Fp;
+                t4.E = P.E; t4.E_leaf_stride = (int64_t)P.R_pad * Fp; t4.emask = getenv("MOPE_NO_EMASK") ? nullptr : P.emask;
                 t4.scratch = scratch;
                 t4.ops = P.ops4; t4.n_ops = (int)P.ops4_h.size(); t4.n_slots = c->max_slots4;
                 t4.R = P.R; t4.L = P.L; t4.R_pad = P.R_pad; t4.Fp = Fp; t4.F = F; t4.NT = c->NT; t4.n_tiles = P.n_tiles; t4.W = Wc;
@@ -1297,6 +1300,7 @@ int eval_resident_impl(mope_ctx* c, const double* params_dev, const double* stat
                 TreeParams tp{};
                 tp.tmapE = P.tmapE; tp.tmapS = tmapS; tp.tmapP = tmapP;
                 tp.E = P.E; tp.E_leaf_stride = (int64_t)P.R_pad * Fp; tp.scratch = scratch;
+                tp.emask = (getenv("MOPE_NO_EMASK") || c->Fp / KC > 64) ? nullptr : P.emask;
                 tp.ops = P.ops; tp.n_ops = P.n_ops; tp.n_slots = c->max_slots;
                 tp.R = P.R; tp.L = P.L; tp.R_pad = P.R_pad; tp.Fp = Fp; tp.F = F; tp.NT = c->NT; tp.n_tiles = P.n_tiles; tp.W = Wc;
                 tp.tile_block = tile_block_default;
@@ -1542,6 +1546,12 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         emission_kernel<<<grid, 256, 0, st>>>(ep);
         CUDA_TRY_C(cudaGetLastError());
         c->launches++;
+        {
+            const long long mwarps = (long long)P.n_leaves * (P.R_pad / 8);
+            emission_mask_kernel<<<(unsigned)((mwarps * 32 + 255) / 256), 256, 0, st>>>(P.E, P.emask, P.n_leaves, P.R_pad, Fp);
+            CUDA_TRY_C(cudaGetLastError());
+            c->launches++;
+        }
         CUDA_TRY_C(cudaStreamSynchronize(st));  // host vectors above go out of scope per pedigree
         if (int rc = make_tmap(&P.tmapE, P.E, (uint64_t)P.n_leaves * P.R_pad, Fp, TM)) return cleanup_fail(rc);
     }
@@ -1689,7 +1699,7 @@ int mope_b200_last_eval_unit_rows(mope_ctx* c, int64_t* unit_rows) {
     CUDA_TRY(cudaStreamSynchronize(c->last_stream));
     unsigned long long v = 0;
     CUDA_TRY(cudaMemcpy(&v, c->work_ctr + 8, sizeof v, cudaMemcpyDeviceToHost));
-    *unit_rows = (int64_t)v;
+    *unit_rows = (int64_t)((double)v / (double)c->F + 0.5);   // the kernels count rows x k columns; a full unit has F of them
     return 0;
 }
 
@@ -2018,6 +2028,115 @@ int mope_b200_beta_cdf_table(void* betainc_fn, const double* ab, int n_ab, const
     for (int t = 1; t < nt; ++t) th.emplace_back(rows, (int)((long long)n_ab * t / nt), (int)((long long)n_ab * (t + 1) / nt));
     rows(0, (int)((long long)n_ab / nt));
     for (auto& x : th) x.join();
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// transition-table generator (device pointers; no context: the tables are made before any model exists)
+// ------------------------------------------------------------------------------------------------
+namespace {
+// 2-D fp64 tensor [rows][cols] with row pitch ld doubles, box = 16 columns x box_rows rows, 128-byte swizzle;
+// out-of-range parts of a box read as zero
+int make_tmap_ld(CUtensorMap* out, const double* base, uint64_t rows, uint64_t cols, int ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(MOPE_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MOPE_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows %llu, cols %llu, ld %d)", (int)r,
+                                       (unsigned long long)rows, (unsigned long long)cols, ld);
+    return 0;
+}
+
+template <int NTW>
+int launch_dgemm_tn(const double* A, const double* Bt, double* C, int M, int N, int K, int lda, int ldbt, int ldc, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(dgemm_tn_kernel<NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<NTW>::SMEM_BYTES));
+        attr_set = true;
+    }
+    GemmParams gp{};
+    if (int rc = make_tmap_ld(&gp.tmapA, A, (uint64_t)M, (uint64_t)K, lda, TM)) return rc;
+    if (int rc = make_tmap_ld(&gp.tmapB, Bt, (uint64_t)N, (uint64_t)K, ldbt, 16 * NTW)) return rc;
+    gp.C = C; gp.M = M; gp.N = N; gp.K = K; gp.ldc = ldc;
+    gp.tiles_n = (N + 16 * NTW - 1) / (16 * NTW);
+    const int tiles_m = (M + TM - 1) / TM;
+    dgemm_tn_kernel<NTW><<<tiles_m * gp.tiles_n, NTHREADS, GemmCfg<NTW>::SMEM_BYTES, st>>>(gp);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int mope_b200_gen_binom_matrix(double* P_dev, int ld, int rows, int cols, int rows_valid, int n_trials, const double* p_host, void* stream) {
+    if (!P_dev || !p_host || rows <= 0 || cols <= 0 || ld < cols || rows_valid < 0 || rows_valid > rows || n_trials < 0)
+        return fail(MOPE_E_INVALID, "gen_binom_matrix: bad argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int nj = n_trials + 1;
+    std::vector<double> buf((size_t)2 * rows_valid + nj);
+    std::vector<int8_t> cls(std::max(rows_valid, 1));
+    double* logp = buf.data(); double* log1mp = logp + rows_valid; double* lnc = log1mp + rows_valid;
+    for (int i = 0; i < rows_valid; ++i) {
+        const double p = p_host[i];
+        if (!(p >= 0.0 && p <= 1.0)) return fail(MOPE_E_INVALID, "gen_binom_matrix: probability %g of row %d outside [0, 1]", p, i);
+        cls[i] = p == 0.0 ? 1 : (p == 1.0 ? 2 : 0);
+        logp[i] = cls[i] ? 0.0 : std::log(p);
+        log1mp[i] = cls[i] ? 0.0 : std::log1p(-p);
+    }
+    const double lg = std::lgamma((double)n_trials + 1.0);
+    for (int j = 0; j < nj; ++j) lnc[j] = lg - std::lgamma((double)j + 1.0) - std::lgamma((double)(n_trials - j) + 1.0);
+    double* d_buf = nullptr; int8_t* d_cls = nullptr;
+    CUDA_TRY(cudaMallocAsync(&d_buf, buf.size() * sizeof(double), st));
+    CUDA_TRY(cudaMallocAsync(&d_cls, cls.size(), st));
+    CUDA_TRY(cudaMemcpyAsync(d_buf, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_cls, cls.data(), cls.size(), cudaMemcpyHostToDevice, st));
+    dim3 grid((ld + 255) / 256, rows);
+    binom_matrix_kernel<<<grid, 256, 0, st>>>(P_dev, ld, rows, cols, rows_valid, n_trials, d_buf, d_buf + rows_valid, d_buf + 2 * rows_valid, d_cls);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(d_buf, st));
+    CUDA_TRY(cudaFreeAsync(d_cls, st));
+    return 0;
+}
+
+int mope_b200_gen_transpose(const double* A_dev, double* At_dev, int rows, int cols, int lda, int ldt, void* stream) {
+    if (!A_dev || !At_dev || rows <= 0 || cols <= 0 || lda < cols || ldt < rows) return fail(MOPE_E_INVALID, "gen_transpose: bad argument");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A_dev, At_dev, rows, cols, lda, ldt);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int mope_b200_gen_dgemm_tn(const double* A_dev, const double* Bt_dev, double* C_dev, int M, int N, int K, int lda, int ldbt, int ldc, void* stream) {
+    if (!A_dev || !Bt_dev || !C_dev || M <= 0 || N <= 0 || K <= 0 || lda < K || ldbt < K || ldc < N)
+        return fail(MOPE_E_INVALID, "gen_dgemm_tn: bad argument");
+    if ((lda & 1) || (ldbt & 1) || (ldc & 1) || ((uintptr_t)A_dev & 15) || ((uintptr_t)Bt_dev & 15) || ((uintptr_t)C_dev & 15))
+        return fail(MOPE_E_INVALID, "gen_dgemm_tn: operands must be 16-byte aligned with even leading dimensions (TMA row pitch)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // tile width: the one whose tile count wastes the fewest SM slots (1001 x 1001: 16 x 9 = 144 tiles of 64 x 112)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tiles_m = (M + TM - 1) / TM;
+    auto cost = [&](int ntw) {   // waves x tile work
+        const long long tiles = (long long)tiles_m * ((N + 16 * ntw - 1) / (16 * ntw));
+        return (double)((tiles + sms - 1) / sms) * ntw;
+    };
+    const double c7 = cost(7), c13 = cost(13);
+    if (c13 < c7) return launch_dgemm_tn<13>(A_dev, Bt_dev, C_dev, M, N, K, lda, ldbt, ldc, st);
+    return launch_dgemm_tn<7>(A_dev, Bt_dev, C_dev, M, N, K, lda, ldbt, ldc, st);
+}
+
+int mope_b200_gen_bin_matrix(const double* P_dev, int ld, int n_states, const int32_t* breaks_dev, int F, double* out_dev, void* stream) {
+    if (!P_dev || !breaks_dev || !out_dev || n_states <= 0 || F <= 0 || F > n_states || ld < n_states) return fail(MOPE_E_INVALID, "gen_bin_matrix: bad argument");
+    bin_matrix_kernel<<<(F * F + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P_dev, ld, n_states, breaks_dev, F, out_dev);
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 

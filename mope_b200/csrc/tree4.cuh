@@ -87,7 +87,8 @@ struct Tree4Params {
     double* uni_msg;
     int32_t n_uroot, canonical;
     int32_t* work_ctr;       // zeroed before the launch: next item to hand out (items differ in cost: identity branches)
-    unsigned long long* unit_rows;   // statistics: += real rows x GEMM units actually run through the tensor pipe (may be null)
+    unsigned long long* unit_rows;   // statistics: += real rows x k columns actually run through the tensor pipe (may be null)
+    const unsigned long long* emask;   // [n_leaves][R_pad / 8]: K chunks of an 8-row group of E that are not all zero (may be null)
     const int32_t* wstatus;  // device-planned evaluations: per-walker MOPE_ST_* bits, non-zero = skip the walker (may be null)
 };
 
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
         if (!no_copy && lane == 0 && warp < PF4 && warp < total_chunks) issue_next();
         __syncwarp();
         int crel = 0;   // chunks of this item consumed so far
-        int my_units = 0;   // GEMM units (branch x generation segment) this warp ran through the tensor pipe
+        int my_kcols = 0;   // k columns (over all GEMM units = branch x generation segment) this warp ran through the tensor pipe
         PROF_MARK(0)   // item setup
 
         for (int oi = 0; oi < p.n_ops; ++oi) {
@@ -447,6 +448,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             const bool asc_leaf = asc_tile && op.leaf >= 0;
             const bool asc_uroot = asc_cse && op.uni == 2 && op.leaf < 0;
             const int nseg = (identity || asc_leaf || asc_uroot) ? 0 : (op.kind == 0 ? 1 : max(0, ts->seg_hi[oi] - ts->seg_lo[oi] + 1));
+            // leaf branches: K chunks in which the warp's 8 emission rows are all zero add nothing (emission_mask_kernel)
+            unsigned long long cmask = ~0ull;
+            if (op.leaf >= 0 && nseg > 0 && p.emask != nullptr && !p.canonical) cmask = p.emask[((size_t)op.leaf * p.R_pad + row0) / 8 + warp];
             for (int si = 0; si < nseg; ++si) {
                 double wgt = 1.0;
                 if (op.kind == 1) {
@@ -456,7 +460,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                 // a warp none of whose 8 rows blends this grid generation only keeps pace with the ring (its products would
                 // all be zero); the warp it shares the sub-partition's DMMA pipe with then runs the segment at full rate
                 const bool seg_active = (op.kind != 1) || __any_sync(0xffffffffu, wgt != 0.0);
-                my_units += seg_active ? 1 : 0;
                 uint32_t an[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // chained A values of the coming chunk (tcgen05.ld in flight)
                 if (op.leaf < 0) tmem_ld4_issue(t_chain, an);
                 for (int c = 0; c < nchunks; ++c) {
@@ -479,7 +482,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
                     PROF_MARK(3)   // waiting for the stage
                     const int nq = (c + 1 == nchunks) ? nq_last : 4;
                     const unsigned char* st = ring + (size_t)s * Cfg::STAGE_BYTES;
-                    if (!no_mma && seg_active) {
+                    const bool do_mma = seg_active && ((cmask >> c) & 1ull);
+                    my_kcols += do_mma ? min(KC, p.F - KC * c) : 0;
+                    if (!no_mma && do_mma) {
                         // the four operand flavours get their own straight-line code: nothing but LDS + DMMA between k steps
                         if (op.leaf >= 0) {
                             if (op.kind == 1) chunk_mma<NTT, NFULL, SCALAR, true, true, no_lds>(acc, sacc, st, a_base, b_base, z, bs_base, z0, ac, wgt, nq);
@@ -630,9 +635,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             PROF_MARK(4)   // post-op
         }  // ops
 
-        if (p.unit_rows != nullptr && lane == 0 && my_units > 0) {
+        if (p.unit_rows != nullptr && lane == 0 && my_kcols > 0) {
             const int real = max(0, min(8, p.R - (row0 + warp * 8)));
-            if (real > 0) atomicAdd(p.unit_rows, (unsigned long long)my_units * (unsigned)real);
+            if (real > 0) atomicAdd(p.unit_rows, (unsigned long long)my_kcols * (unsigned)real);
         }
         __syncthreads();   // rowval complete; every warp is done with the item's tables
         if (p.Yout == nullptr && !p.canonical && warp == 0) {

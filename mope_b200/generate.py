@@ -3,11 +3,11 @@
 Produces the same tables as the reference's `mope generate-transitions` + `make-master-transitions`:
 Wright-Fisher matrix (mope/generate_transitions.py:57-67), matrix-power chain over the generation list
 (:217-228, :386-414), bottleneck products through the doubling schedule (:29-54, mope/_transition.pyx:6-33),
-symmetric frequency binning (:133-214).  With a GPU everything heavy stays on the device: the binomial rows of the
-Wright-Fisher and bottleneck factors (log-pmf from host-computed log binomial coefficients), the 1001^3 fp64 matrix products (plain library GEMMs,
-torch.matmul -> cuBLAS) and the binning (one GEMM with the bin-membership matrix + a row gather); only the F x F
-tables come back (default 94 x 44 drift grid + 48 x 44 bottleneck grid: ~1.5 minutes, was ~6).  Without a GPU the
-same steps run in NumPy / SciPy.  The two paths agree to ~1e-11 relative (summation order, lgamma vs SciPy's pmf);
+symmetric frequency binning (:133-214).  With a GPU everything heavy stays on the device, in the library's own kernels
+(csrc/generate.cuh through the C ABI `mope_b200_gen_*`): the binomial rows of the Wright-Fisher and bottleneck factors
+(log-pmf from host libm), the 1001^3 fp64 matrix products (`dgemm_tn_kernel`: TMA ring + mma.sync.m8n8k4.f64, the tensor
+pipe of the pruning kernels) and the binning (`bin_matrix_kernel`); torch only owns the buffers and only the F x F tables
+come back.  `device="cpu"` runs the same steps in NumPy / SciPy (the build container has no GPU; the CPU tests use it).  The two paths agree to ~1e-11 relative (summation order, lgamma vs SciPy's pmf);
 the tables are an input shared by both implementations, so this does not enter the parity of the likelihood.
 Powers of the one-generation matrix are cached by repeated squaring, so a step of d generations costs
 popcount(d)-1 products instead of a fresh matrix_power.
@@ -101,7 +101,7 @@ def var_n_matrix(N1: int, N2: int, N0: int, mu: float) -> np.ndarray:
 
 
 class _Mat:
-    """Matrix products on the GPU (torch, fp64) when available, NumPy otherwise."""
+    """Matrix chain backend: the library's CUDA kernels (torch tensors as buffers) when a GPU is present, NumPy otherwise."""
 
     def __init__(self, device: Optional[str]):
         self.torch = None
@@ -114,77 +114,89 @@ class _Mat:
                 device = None
         if device is not None and device != "cpu":
             import torch
+            from . import _lib
             self.torch = torch
-            self.device = device
+            self.device = torch.device(device)
+            self.lib = _lib.lib()           # raises if the CUDA library is missing
+            self._check = _lib.check
+            self.gemms = 0
+
+    # -- device helpers ----------------------------------------------------------------------------------------------
+    def _new(self, n: int):
+        """n x n matrix with an even leading dimension (16-byte row pitch for the tensor maps)."""
+        ld = n + (n & 1)
+        return self.torch.empty((n, ld), dtype=self.torch.float64, device=self.device)
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
 
     def put(self, a):
-        return self.torch.as_tensor(a, dtype=self.torch.float64, device=self.device) if self.torch else np.asarray(a)
+        if not self.torch:
+            return np.asarray(a)
+        a = np.asarray(a, dtype=np.float64)
+        out = self._new(a.shape[0])
+        out[:, : a.shape[1]] = self.torch.as_tensor(a, device=self.device)
+        if out.shape[1] > a.shape[1]:
+            out[:, a.shape[1]:] = 0.0
+        return out
 
     def get(self, a):
-        return a.cpu().numpy() if self.torch else a
+        return a[:, : a.shape[0]].cpu().numpy() if self.torch else a
 
     def mm(self, a, b):
-        return self.torch.matmul(a, b) if self.torch else a @ b
+        """a . b (square, same size)."""
+        if not self.torch:
+            return a @ b
+        n, ld = a.shape
+        bt = self._new(n)
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.mope_b200_gen_transpose(b.data_ptr(), bt.data_ptr(), n, n, ld, ld, self._stream()), "gen_transpose")
+            out = self._new(n)
+            self._check(self.lib.mope_b200_gen_dgemm_tn(a.data_ptr(), bt.data_ptr(), out.data_ptr(), n, n, n, ld, ld, ld, self._stream()),
+                        "gen_dgemm_tn")
+        self.gemms += 1
+        return out
+
+    def _binom(self, n_states: int, rows_valid: int, n_trials: int, p: np.ndarray):
+        out = self._new(n_states)
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.mope_b200_gen_binom_matrix(out.data_ptr(), out.shape[1], n_states, n_states, rows_valid, n_trials,
+                                                            p.ctypes.data, self._stream()), "gen_binom_matrix")
+        return out
 
     def wright_fisher(self, N: int, s: float, u: float, v: float):
-        """wright_fisher_matrix on the device (binomial log-pmf from lgamma); host SciPy when there is no device or the
-        mutated frequency reaches 0 or 1."""
-        i = np.arange(N + 1)
-        p = i / N
+        """wright_fisher_matrix (generate_transitions.py:57-67); on the device by binom_matrix_kernel."""
+        if not self.torch:
+            return wright_fisher_matrix(N, s, u, v)
+        p = np.arange(N + 1) / N
         pmut = (1 - u) * p + v * (1 - p)
         pstar = np.minimum(pmut * (1 + s) / (pmut * (1 + s) + 1 - pmut), 1.0)
-        if not self.torch or pstar.min() <= 0.0 or pstar.max() >= 1.0:
-            return self.put(wright_fisher_matrix(N, s, u, v))
-        t = self.torch
-        ps = t.as_tensor(pstar, dtype=t.float64, device=self.device)
-        k = t.arange(N + 1, dtype=t.float64, device=self.device)
-        lc = self._log_binom(N)
-        return t.exp(lc[None, :] + k[None, :] * t.log(ps)[:, None] + (N - k)[None, :] * t.log1p(-ps)[:, None])
-
-    def _log_binom(self, n: int):
-        """log C(n, k), k = 0..n, from SciPy's gammaln on the host (n + 1 values; keeps torch's JIT-compiled lgamma out of
-        the device path)."""
-        cache = self.__dict__.setdefault("_lc_cache", {})
-        if n not in cache:
-            k = np.arange(n + 1, dtype=np.float64)
-            cache[n] = self.torch.as_tensor(gammaln(n + 1.0) - gammaln(k + 1.0) - gammaln(n - k + 1.0), dtype=self.torch.float64,
-                                            device=self.device)
-        return cache[n]
+        return self._binom(N + 1, N + 1, N, pstar)
 
     def binner(self, n_states: int, breaks: np.ndarray):
-        """bin_matrix for device matrices: column sums per bin as one GEMM with the 0/1 membership matrix, then the middle
-        row(s) of every bin; only the F x F result leaves the device."""
+        """bin_matrix for device matrices (bin_matrix_kernel); only the F x F result leaves the device."""
         if not self.torch:
             return lambda P: bin_matrix(P, breaks)
         t = self.torch
-        breaks = np.asarray(breaks)
-        lengths = np.concatenate((np.diff(breaks), [n_states - breaks[-1]]))
-        member = np.zeros((n_states, breaks.shape[0]))
-        member[np.arange(n_states), np.repeat(np.arange(breaks.shape[0]), lengths)] = 1.0
-        M = t.as_tensor(member, dtype=t.float64, device=self.device)
-        lo = t.as_tensor(breaks + np.floor((lengths - 1) / 2).astype(np.int64), device=self.device)
-        hi = t.as_tensor(breaks + np.ceil((lengths - 1) / 2).astype(np.int64), device=self.device)
-        even = t.as_tensor((lengths % 2 == 0)[:, None], device=self.device)
+        F = int(np.asarray(breaks).shape[0])
+        brk = t.as_tensor(np.asarray(breaks, dtype=np.int32), device=self.device)
 
         def run(P):
-            colsum = t.matmul(P, M)
-            return t.where(even, (colsum[lo, :] + colsum[hi, :]) / 2, colsum[lo, :]).cpu().numpy()
+            out = t.empty((F, F), dtype=t.float64, device=self.device)
+            with t.cuda.device(self.device):
+                self._check(self.lib.mope_b200_gen_bin_matrix(P.data_ptr(), P.shape[1], n_states, brk.data_ptr(), F, out.data_ptr(),
+                                                              self._stream()), "gen_bin_matrix")
+            return out.cpu().numpy()
         return run
 
     def var_n(self, N1: int, N2: int, N0: int, mu: float):
-        """var_n_matrix on the device: the binomial pmf from lgamma (the host version calls scipy.stats.binom.pmf on up
-        to a million cells per factor, which dominated the bottleneck grid's generation time)."""
+        """var_n_matrix (_transition.pyx:6-33) on the device."""
         if not self.torch:
             return var_n_matrix(N1, N2, N0, mu)
-        t = self.torch
-        f = t.arange(N1 + 1, dtype=t.float64, device=self.device) / N1
-        f = (1 - mu) * f + (1 - f) * mu                       # strictly inside (0, 1) for 0 < mu < 1
-        k = t.arange(N2 + 1, dtype=t.float64, device=self.device)
-        lc = self._log_binom(N2)
-        logpmf = lc[None, :] + k[None, :] * t.log(f)[:, None] + (N2 - k)[None, :] * t.log1p(-f)[:, None]
-        P = t.zeros((N0 + 1, N0 + 1), dtype=t.float64, device=self.device)
-        P[: N1 + 1, : N2 + 1] = t.exp(logpmf)
-        return P
+        f = np.arange(N1 + 1) / N1
+        f = (1 - mu) * f + (1 - f) * mu
+        return self._binom(N0 + 1, N1 + 1, N2, f)
 
 
 def _power_from_cache(mat: _Mat, squares: list, n: int):
@@ -250,8 +262,7 @@ def bottleneck_matrix(N: int, Nb: int, mu: float, mat: Optional[_Mat] = None, on
     Ns = [N, Nb] + [Nb * 2 ** d for d in range(1, num_doublings + 1)]
     if num_gens > num_doublings:
         Ns.append(N)
-    use_dev = mat.torch is not None and 0.0 < mu < 1.0
-    fac = (lambda a, b: mat.var_n(a, b, N, mu)) if use_dev else (lambda a, b: mat.put(var_n_matrix(a, b, N, mu)))
+    fac = lambda a, b: mat.var_n(a, b, N, mu)   # noqa: E731
     P = fac(Ns[0], Ns[1])
     for N1, N2 in zip(Ns[1:-1], Ns[2:]):
         P = mat.mm(P, fac(N1, N2))

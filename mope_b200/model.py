@@ -7,6 +7,7 @@ columns) and flattens the result into the mope_pedigree_desc layout of include/m
 from __future__ import annotations
 
 import io
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -164,6 +165,39 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
         new_index[uorder] = np.arange(len(uorder))
         asc_mult = np.ascontiguousarray(asc_mult[:, uorder])
         fam_asc = new_index[fam_asc].astype(np.int32)
+
+    if sort_rows and L > 8:
+        # A binomial emission is an exact 0.0 far from the observed frequency, and the pruning kernels skip the K chunks in
+        # which the 8 rows a warp owns are all zero (emission_mask_kernel), so rows with similar allele frequencies go next
+        # to each other; rows with a missing tissue (emission all ones for that leaf) are grouped by the tissue they miss.
+        # Without age-scaled branches the row order is free (global sort); with them the 64-row tiles of the k-d order above
+        # are kept (a tile's rows decide the generation segments of its GEMMs) and only the rows inside a tile are ordered.
+        # Only the association order of the final sum over loci changes.
+        with np.errstate(invalid="ignore", divide="ignore"):
+            fr = X / n
+        miss = np.isnan(fr)
+        all_miss = miss.all(axis=1)
+        mean_fr = np.where(all_miss, 0.0, np.nanmean(np.where(all_miss[:, None], 0.0, fr), axis=1))
+        any_miss = miss.any(axis=1)
+        first_miss = np.where(any_miss, miss.argmax(axis=1), -1)
+        if M == 0:
+            order = np.lexsort((mean_fr, first_miss, any_miss))
+        else:
+            classes = int(os.environ.get("MOPE_FREQ_CLASSES", "1"))
+            block = int(os.environ.get("MOPE_FREQ_BLOCK", "0"))
+            order = None
+            if classes > 1 or block > 0:
+                cls = np.zeros(L, dtype=np.int64)
+                if classes > 1:
+                    cls = np.searchsorted(np.quantile(mean_fr, np.arange(1, classes) / classes), mean_fr)
+                o1 = np.lexsort((np.arange(L), cls))
+                order = o1
+                if block > 0:
+                    o2 = np.lexsort((mean_fr[o1], first_miss[o1], any_miss[o1], np.arange(L) // block))
+                    order = o1[o2]
+        if order is not None:
+            X, n, family = np.ascontiguousarray(X[order]), np.ascontiguousarray(n[order]), family[order]
+            row_mult = np.ascontiguousarray(row_mult[:, order])
 
     idx_of = {id(nd): i for i, nd in enumerate(nodes)}
     idx_of[id(tree)] = len(nodes)

@@ -30,26 +30,30 @@ def test_generated_tables_match_reference_generator():
     np.testing.assert_allclose(tb.bot, TB["bot"][np.ix_(bi, ui)], rtol=1e-9, atol=1e-15)
 
 
-def test_device_generator_path_matches_host_path():
-    """The device path of the generator (binomial rows from lgamma, binning as a GEMM with the bin-membership matrix)
-    run on CPU tensors against the NumPy / SciPy path: same tables to rounding."""
+@pytest.mark.gpu
+def test_gpu_generator_kernels_match_host():
+    """The generator's own kernels through the C ABI (mope_b200_gen_*): binomial rows vs SciPy, dgemm_tn_kernel vs a NumPy
+    fp64 product (odd sizes, rectangular tile edges), bin_matrix_kernel vs bin_matrix, and the chained tables vs the host path."""
     import torch
-
-    class CpuTorchMat(generate._Mat):
-        def __init__(self, device):
-            self.torch, self.device = torch, "cpu"
-
-    host = generate.generate_tables(N=1000, breaks=(0.5, 0.02), gens=[1, 3, 10], us=[1e-7, 1e-3], nbs=[2, 20, 500],
+    mat = generate._Mat("cuda")
+    N = 1000
+    P = mat.wright_fisher(N, 0.0, 1e-3, 1e-3)
+    ref = generate.wright_fisher_matrix(N, 0.0, 1e-3, 1e-3)
+    np.testing.assert_allclose(mat.get(P), ref, rtol=1e-10, atol=1e-300)
+    V = mat.var_n(20, 40, N, 1e-5)
+    np.testing.assert_allclose(mat.get(V), generate.var_n_matrix(20, 40, N, 1e-5), rtol=1e-10, atol=1e-300)
+    rng = np.random.RandomState(3)
+    for n in (1001, 65, 208, 333):
+        a, b = rng.rand(n, n), rng.rand(n, n) - 0.5
+        got = mat.get(mat.mm(mat.put(a), mat.put(b)))
+        np.testing.assert_allclose(got, a @ b, rtol=0, atol=1e-12 * n)
+    br = generate.get_breaks_symmetric(N, 0.5, 0.02)
+    np.testing.assert_allclose(mat.binner(N + 1, br)(P), generate.bin_matrix(ref, br), rtol=1e-13, atol=1e-300)
+    host = generate.generate_tables(N=N, breaks=(0.5, 0.02), gens=[1, 3, 10], us=[1e-7, 1e-3], nbs=[2, 20, 500],
                                     bot_us=[1e-7, 1e-3], device="cpu")
-    orig = generate._Mat
-    generate._Mat = CpuTorchMat
-    try:
-        dev = generate.generate_tables(N=1000, breaks=(0.5, 0.02), gens=[1, 3, 10], us=[1e-7, 1e-3], nbs=[2, 20, 500],
-                                       bot_us=[1e-7, 1e-3], device="cpu")
-    finally:
-        generate._Mat = orig
+    dev = generate.generate_tables(N=N, breaks=(0.5, 0.02), gens=[1, 3, 10], us=[1e-7, 1e-3], nbs=[2, 20, 500],
+                                   bot_us=[1e-7, 1e-3], device="cuda")
     np.testing.assert_allclose(dev.drift, host.drift, rtol=1e-9, atol=1e-15)
     np.testing.assert_allclose(dev.bot, host.bot, rtol=1e-9, atol=1e-15)
-    np.testing.assert_array_equal(dev.breaks, host.breaks)
-    # rows of a transition matrix are probability vectors
     assert np.abs(dev.drift.sum(axis=-1) - 1).max() < 1e-9 and np.abs(dev.bot.sum(axis=-1) - 1).max() < 1e-9
+    torch.cuda.synchronize()
