@@ -170,8 +170,8 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
         # A binomial emission is an exact 0.0 far from the observed frequency, and the pruning kernels skip the K chunks in
         # which the 8 rows a warp owns are all zero (emission_mask_kernel), so rows with similar allele frequencies go next
         # to each other; rows with a missing tissue (emission all ones for that leaf) are grouped by the tissue they miss.
-        # Without age-scaled branches the row order is free (global sort); with them the 64-row tiles of the k-d order above
-        # are kept (a tile's rows decide the generation segments of its GEMMs) and only the rows inside a tile are ordered.
+        # Without age-scaled branches the row order is free (global sort); with them the rows stay in the k-d order above
+        # (a tile's rows decide the generation segments of its GEMMs) inside a few frequency classes / inside large blocks.
         # Only the association order of the final sum over loci changes.
         with np.errstate(invalid="ignore", divide="ignore"):
             fr = X / n
@@ -183,8 +183,11 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
         if M == 0:
             order = np.lexsort((mean_fr, first_miss, any_miss))
         else:
-            classes = int(os.environ.get("MOPE_FREQ_CLASSES", "1"))
-            block = int(os.environ.get("MOPE_FREQ_BLOCK", "0"))
+            # Measured on B200 (profiles/r02_row_order.md): one multiplier column (the k-d order is a plain sort by age, whole
+            # runs of tiles share their generation segments): frequency order inside blocks of 32768 rows, cfg4 4228 -> 3868 ms
+            # per step; several columns (small k-d cells): two frequency classes, each in k-d order, cfg3 499 -> 483 ms.
+            classes = int(os.environ.get("MOPE_FREQ_CLASSES", "1" if M == 1 else "2"))
+            block = int(os.environ.get("MOPE_FREQ_BLOCK", "32768" if M == 1 else "0"))
             order = None
             if classes > 1 or block > 0:
                 cls = np.zeros(L, dtype=np.int64)

@@ -75,6 +75,31 @@ class TransitionTables:
     def get_max_mutsel_rate(self):
         return self.us.max() * 2 * self.N
 
+    def save_hdf5(self, transitions_file: str, bottleneck_file: Optional[str] = None, breaks_args=None) -> None:
+        """Write master files in the reference's HDF5 layout (generate_transitions.py:242-323, :420-470): datasets `P<idx>`
+        with attributes N, s, u, v, gen (drift) or N, Nb, u (bottleneck), root attributes N, breaks, frequencies (and
+        min_bin_size / uniform_weight when `breaks_args = (uniform_weight, min_bin_size)` is given).  Written by the
+        built-in HDF5 writer (hdf5_lite): the image has no libhdf5."""
+        from . import hdf5_lite
+        root = {"N": int(self.N), "breaks": np.asarray(self.breaks, dtype=np.int64), "frequencies": self.freqs}
+        if breaks_args is not None:
+            root["uniform_weight"], root["min_bin_size"] = float(breaks_args[0]), float(breaks_args[1])
+        dsets, idx = {}, 0
+        for j, u in enumerate(self.us):
+            for i, g in enumerate(self.gens):
+                dsets["P%d" % idx] = (self.drift[i, j], {"N": int(self.N), "s": 0.0, "u": float(u), "v": float(u), "gen": int(g)})
+                idx += 1
+        hdf5_lite.write_file(transitions_file, root, dsets)
+        if bottleneck_file is not None:
+            if self.bot is None:
+                raise ValueError("no bottleneck tables to write")
+            dsets, idx = {}, 0
+            for j, u in enumerate(self.bot_us):
+                for i, nb in enumerate(self.nbs):
+                    dsets["P%d" % idx] = (self.bot[i, j], {"N": int(self.N), "Nb": int(nb), "u": float(u)})
+                    idx += 1
+            hdf5_lite.write_file(bottleneck_file, root, dsets)
+
     def save(self, path: str) -> None:
         d = dict(drift=self.drift, gens=self.gens, us=self.us, N=np.float64(self.N), freqs=self.freqs, breaks=self.breaks)
         if self.bot is not None:
@@ -90,25 +115,43 @@ def load_npz(path: str) -> TransitionTables:
     return TransitionTables(**kw)
 
 
-def _grid_from_h5(path: str, axis_attr: str, xkey: str = "u"):
-    """Read a mope master HDF5 file (datasets with attrs N, gen|Nb, u; file attrs frequencies, breaks)."""
-    import h5py  # gated: not part of this image; present wherever the reference runs
-
-    mats, N = {}, None
+def _read_h5(path: str):
+    """-> (root attrs, {dataset name: (array, attrs)}) of a master file.  Real HDF5 files are parsed by h5py where it is
+    installed and by the built-in reader (hdf5_lite) otherwise; anything else is handed to whatever `h5py` module the
+    process has (the reference's test installs use a stand-in)."""
+    from . import hdf5_lite
+    with open(path, "rb") as f:
+        head = f.read(8)
+    is_hdf5 = head == hdf5_lite.SIGNATURE
+    try:
+        import h5py
+    except ImportError:
+        h5py = None
+    if h5py is None or (is_hdf5 and not hasattr(h5py, "h5")):   # no h5py, or a stand-in that cannot read real HDF5
+        if not is_hdf5:
+            raise ValueError("{}: not an HDF5 file".format(path))
+        return hdf5_lite.read_file(path)
     with h5py.File(path, "r") as f:
-        for name in f:
-            ds = f[name]
-            a = ds.attrs
-            if N is None:
-                N = a["N"]
-            elif a["N"] != N:
-                raise Exception("Found multiple population sizes in master file's datasets")
-            key = (float(a[axis_attr]), float(a[xkey]))
-            if key in mats:
-                raise Exception("Found duplicate grid point in matrices: {}".format(key))
-            mats[key] = np.array(ds[:, :], dtype=np.float64)
-        freqs = np.array(f.attrs["frequencies"])
-        breaks = np.array(f.attrs["breaks"])
+        dsets = {name: (np.array(f[name][:, :], dtype=np.float64), dict(f[name].attrs)) for name in f}
+        return dict(f.attrs), dsets
+
+
+def _grid_from_h5(path: str, axis_attr: str, xkey: str = "u"):
+    """Read a mope master HDF5 file (datasets with attrs N, gen|Nb, u; file attrs frequencies, breaks), with the checks
+    of TransitionData._add_dataset / _add_master_file (transition_data_2d.py:43-111)."""
+    root, dsets = _read_h5(path)
+    mats, N = {}, None
+    for name, (mat, a) in dsets.items():
+        if N is None:
+            N = a["N"]
+        elif a["N"] != N:
+            raise Exception("Found multiple population sizes in master file's datasets")
+        key = (float(a[axis_attr]), float(a[xkey]))
+        if key in mats:
+            raise Exception("Found duplicate grid point in matrices: {}".format(key))
+        mats[key] = np.array(mat, dtype=np.float64)
+    freqs = np.array(root["frequencies"])
+    breaks = np.array(root["breaks"])
     ax = np.array(sorted({k[0] for k in mats}))
     xs = np.array(sorted({k[1] for k in mats}))
     missing = [(g, x) for g in ax for x in xs if (g, x) not in mats]
