@@ -269,9 +269,11 @@ int mope_b200_beta_cdf_table(void* betainc_fn, const double* ab, int n_ab, const
 
 /* P[i][j] = Binomial(j; n_trials, p_host[i]) for i < rows_valid and j <= n_trials, 0 elsewhere in the rows x cols matrix
  * (leading dimension ld): the Wright-Fisher matrix (generate_transitions.py:57-67: n_trials = N, p = pstar) and the
- * bottleneck factors (_transition.pyx:6-33: rows_valid = N1 + 1, n_trials = N2). */
+ * bottleneck factors (_transition.pyx:6-33: rows_valid = N1 + 1, n_trials = N2).  lnchoose_host: ln C(n_trials, j),
+ * j = 0..n_trials, from the caller's log-gamma (the reference's pmf is SciPy's: its gammaln and libm's lgamma differ in
+ * the last bit, which a 10 000-generation matrix power amplifies to ~1e-8); NULL = libm lgamma. */
 int mope_b200_gen_binom_matrix(double* P_dev, int ld, int rows, int cols, int rows_valid, int n_trials,
-                               const double* p_host, void* stream);
+                               const double* p_host, const double* lnchoose_host, void* stream);
 
 /* At[c][r] = A[r][c] (rows x cols -> cols x rows). */
 int mope_b200_gen_transpose(const double* A_dev, double* At_dev, int rows, int cols, int lda, int ldt, void* stream);

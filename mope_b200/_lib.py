@@ -117,7 +117,7 @@ def lib():
     L.mope_b200_branch_update.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, C.c_double, vp, ip]
     L.mope_b200_non_asc_probs.argtypes = [vp, dp, C.POINTER(C.c_int64), C.c_int, dp, C.c_int, C.c_double, vp, dp]
     L.mope_b200_beta_cdf_table.argtypes = [vp, dp, C.c_int, dp, C.c_int, dp, C.c_int]
-    L.mope_b200_gen_binom_matrix.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.mope_b200_gen_binom_matrix.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.mope_b200_gen_transpose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.mope_b200_gen_dgemm_tn.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.mope_b200_gen_bin_matrix.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]

@@ -2075,7 +2075,8 @@ int launch_dgemm_tn(const double* A, const double* Bt, double* C, int M, int N, 
 
 extern "C" {
 
-int mope_b200_gen_binom_matrix(double* P_dev, int ld, int rows, int cols, int rows_valid, int n_trials, const double* p_host, void* stream) {
+int mope_b200_gen_binom_matrix(double* P_dev, int ld, int rows, int cols, int rows_valid, int n_trials, const double* p_host,
+                               const double* lnchoose_host, void* stream) {
     if (!P_dev || !p_host || rows <= 0 || cols <= 0 || ld < cols || rows_valid < 0 || rows_valid > rows || n_trials < 0)
         return fail(MOPE_E_INVALID, "gen_binom_matrix: bad argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -2090,8 +2091,12 @@ int mope_b200_gen_binom_matrix(double* P_dev, int ld, int rows, int cols, int ro
         logp[i] = cls[i] ? 0.0 : std::log(p);
         log1mp[i] = cls[i] ? 0.0 : std::log1p(-p);
     }
-    const double lg = std::lgamma((double)n_trials + 1.0);
-    for (int j = 0; j < nj; ++j) lnc[j] = lg - std::lgamma((double)j + 1.0) - std::lgamma((double)(n_trials - j) + 1.0);
+    if (lnchoose_host) {
+        std::memcpy(lnc, lnchoose_host, (size_t)nj * sizeof(double));
+    } else {
+        const double lg = std::lgamma((double)n_trials + 1.0);
+        for (int j = 0; j < nj; ++j) lnc[j] = lg - (std::lgamma((double)j + 1.0) + std::lgamma((double)(n_trials - j) + 1.0));
+    }
     double* d_buf = nullptr; int8_t* d_cls = nullptr;
     CUDA_TRY(cudaMallocAsync(&d_buf, buf.size() * sizeof(double), st));
     CUDA_TRY(cudaMallocAsync(&d_cls, cls.size(), st));

@@ -160,9 +160,14 @@ class _Mat:
     def _binom(self, n_states: int, rows_valid: int, n_trials: int, p: np.ndarray):
         out = self._new(n_states)
         p = np.ascontiguousarray(p, dtype=np.float64)
+        cache = self.__dict__.setdefault("_lc_cache", {})
+        if n_trials not in cache:   # ln C(n, k) exactly as scipy.stats.binom._logpmf forms it (the reference's pmf)
+            k = np.arange(n_trials + 1, dtype=np.float64)
+            cache[n_trials] = np.ascontiguousarray(gammaln(n_trials + 1.0) - (gammaln(k + 1.0) + gammaln(n_trials - k + 1.0)))
+        lc = cache[n_trials]
         with self.torch.cuda.device(self.device):
             self._check(self.lib.mope_b200_gen_binom_matrix(out.data_ptr(), out.shape[1], n_states, n_states, rows_valid, n_trials,
-                                                            p.ctypes.data, self._stream()), "gen_binom_matrix")
+                                                            p.ctypes.data, lc.ctypes.data, self._stream()), "gen_binom_matrix")
         return out
 
     def wright_fisher(self, N: int, s: float, u: float, v: float):
