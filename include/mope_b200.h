@@ -287,6 +287,35 @@ int mope_b200_gen_dgemm_tn(const double* A_dev, const double* Bt_dev, double* C_
 int mope_b200_gen_bin_matrix(const double* P_dev, int ld, int n_states, const int32_t* breaks_dev, int F,
                              double* out_dev, void* stream);
 
+/* ---- selection model and masked-matrix variants ----
+ * The context's drift grid is read as (generations x selection coefficient s): `us` of mope_tables_desc holds the s values
+ * of a selection table set (TransitionData(selection=True), transition_data_2d.py:52-55); the scaled coefficient is
+ * alpha = 2 N s, exactly like the scaled mutation rate of the neutral model. */
+
+/* parent[r][:] *= Pmask_r . child[r][:] with P_r = get_transition_probabilities_2d(time_r, alphas[r]) for n_rows rows.
+ *   mask 0  the full matrix: _likes.compute_rate_transition_likelihood_selection (_likes.pyx:59-79; per_row_times = 1,
+ *           times[n_rows]) and compute_length_transition_likelihood_selection (:155-175; per_row_times = 0, times[1]);
+ *   mask 1  Pzero[0,0] = P[0,0]: compute_leaf_zero_transition_likelihood / compute_length_transition_likelihood_zero
+ *           (:82-98, :178-194);  mask 2  Pzero[0,1:-1]: ..._focal_node_zero / ..._zero_focalnode (:101-117, :197-212);
+ *   mask 3  Pzero[1:-1,1:-1]: ..._zero_descendant (:120-136, :215-229).  For the masked variants pass the single mutation
+ *           rate in every alphas[r].
+ * child / parent host [n_rows][F]; out_trans (may be NULL) host [n_rows][F] receives the products Pmask_r . child[r]
+ * (the `ret` array of the selection variants).  *out_status = MOPE_ST_* of the first failing fetch (nothing is modified). */
+#define MOPE_MASK_BOTTLENECK 4
+int mope_b200_sel_branch_update(mope_ctx* ctx, int mask, const double* child, double* parent, int n_rows,
+                                const double* times, int per_row_times, const double* alphas, double* out_trans,
+                                void* stream, int32_t* out_status);
+
+/* likelihoods.get_log_l_and_asc_prob_selection (likelihoods.py:404-525) for pedigree `ped` of the context, one parameter
+ * vector: branch_lengths host [n_branches] (branch order), locus_alphas host [n_branches][n_pos] scaled selection
+ * coefficient of every branch at every unique position, position_idx host [n_loci] unique-position index of every locus
+ * row (in the row order of the pedigree description), stat host [F] root distribution.  Three rows per locus (likelihood,
+ * all-zero, all-one: e0 = 1[freq <= min_freq], eN = 1[freq >= 1 - min_freq]) go through the tree; out_loglikes /
+ * out_log_asc host [n_loci]. */
+int mope_b200_sel_loglike(mope_ctx* ctx, int ped, const double* branch_lengths, const double* locus_alphas, int n_pos,
+                          const int32_t* position_idx, const double* stat, void* stream, double* out_loglikes,
+                          double* out_log_asc, int32_t* out_status);
+
 const char* mope_b200_last_error(void);
 const char* mope_b200_version(void);
 

@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile mope_b200/csrc into libmope_b200.so in-tree with nvcc for sm_100a."""
     srcs = [os.path.join(CSRC, "mope_b200.cu")]
-    deps = srcs + [os.path.join(CSRC, "kernels.cuh"), os.path.join(CSRC, "tree4.cuh"), os.path.join(HERE, "..", "include", "mope_b200.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")] + [os.path.join(HERE, "..", "include", "mope_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -68,6 +68,7 @@ SYMBOLS = ["mope_b200_arena_bytes", "mope_b200_create", "mope_b200_destroy", "mo
            "mope_b200_kernel_times", "mope_b200_fp64_peak", "mope_b200_transition_matrix",
            "mope_b200_leaf_likelihoods", "mope_b200_branch_update", "mope_b200_non_asc_probs", "mope_b200_beta_cdf_table",
            "mope_b200_gen_binom_matrix", "mope_b200_gen_transpose", "mope_b200_gen_dgemm_tn", "mope_b200_gen_bin_matrix",
+           "mope_b200_sel_branch_update", "mope_b200_sel_loglike",
            "mope_b200_last_error", "mope_b200_version"]
 
 ST_MESSAGES = {
@@ -121,6 +122,8 @@ def lib():
     L.mope_b200_gen_transpose.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.mope_b200_gen_dgemm_tn.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.mope_b200_gen_bin_matrix.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]
+    L.mope_b200_sel_branch_update.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, C.c_int, dp, dp, vp, ip]
+    L.mope_b200_sel_loglike.argtypes = [vp, C.c_int, dp, dp, C.c_int, ip, dp, vp, dp, dp, ip]
     L.mope_b200_last_error.restype = C.c_char_p
     L.mope_b200_version.restype = C.c_char_p
     for name in SYMBOLS:

@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "tree4.cuh"
 #include "generate.cuh"
+#include "selection.cuh"
 
 using namespace mope;
 
@@ -82,6 +83,9 @@ struct Pedigree {
     int n_slots4 = 0;
     int asc_offset = 0;
     CUtensorMap tmapE;
+    // host copies for the selection-model entry points (per-row plans are made on the host)
+    std::vector<int32_t> br_parent_h, br_leaf_h, br_mult_h;
+    std::vector<double> row_mult_h;   // [n_mult][L]
 };
 
 struct FixedKey { int var; int bott; };
@@ -1483,6 +1487,10 @@ int mope_b200_create(const mope_tables_desc* t, const mope_model_desc* m, int de
         P.R = pd.n_loci + 2 * pd.n_asc;
         P.R_pad = round_up_i(std::max(P.R, 1), TM);
         P.n_tiles = P.R_pad / TM;
+        P.br_parent_h.assign(pd.br_parent, pd.br_parent + pd.n_branches);
+        P.br_leaf_h.assign(pd.br_leaf, pd.br_leaf + pd.n_branches);
+        P.br_mult_h.assign(pd.br_mult, pd.br_mult + pd.n_branches);
+        if (pd.n_mult > 0 && pd.n_loci > 0) P.row_mult_h.assign(pd.row_mult, pd.row_mult + (size_t)pd.n_mult * pd.n_loci);
         P.asc_offset = asc_off;
         asc_off += pd.n_asc;
         if (int rc = compile_schedule(pd, fk[k], rk[k], P)) return cleanup_fail(rc);
@@ -2142,6 +2150,230 @@ int mope_b200_gen_bin_matrix(const double* P_dev, int ld, int n_states, const in
     if (!P_dev || !breaks_dev || !out_dev || n_states <= 0 || F <= 0 || F > n_states || ld < n_states) return fail(MOPE_E_INVALID, "gen_bin_matrix: bad argument");
     bin_matrix_kernel<<<(F * F + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P_dev, ld, n_states, breaks_dev, F, out_dev);
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// selection model / masked-matrix variants (selection.cuh)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct SelPlan {
+    PlanOut po;                       // jobs + mat_off per distinct (time, alpha) pair
+    std::vector<int32_t> row_off, rows;
+    size_t n_blocks = 0;
+    int32_t status = 0;
+};
+
+// distinct (time, alpha) pairs of the rows -> interpolation jobs + row lists
+void plan_sel_rows(const mope_ctx* c, bool bott, int n_rows, const double* times, int time_stride, const double* alphas, SelPlan& pl) {
+    std::vector<int32_t> order(n_rows);
+    for (int i = 0; i < n_rows; ++i) order[i] = i;
+    auto key_less = [&](int a, int b) {
+        const double ta = times[(size_t)a * time_stride], tb = times[(size_t)b * time_stride];
+        if (ta != tb) return ta < tb;
+        if (alphas[a] != alphas[b]) return alphas[a] < alphas[b];
+        return a < b;
+    };
+    std::sort(order.begin(), order.end(), key_less);
+    pl.rows = order;
+    pl.row_off.clear();
+    size_t b = 0;
+    for (int k = 0; k < n_rows; ++k) {
+        const int r = order[k];
+        const double t = times[(size_t)r * time_stride], al = alphas[r];
+        const bool fresh = k == 0 || !(t == times[(size_t)order[k - 1] * time_stride] && al == alphas[order[k - 1]]);
+        if (!fresh) continue;
+        pl.row_off.push_back(k);
+        const int32_t st = status_fixed(c, bott, t, al);
+        pl.status |= st;
+        if (st) { pl.po.mat_off.push_back(-1); continue; }
+        emit_fixed_job(c, bott, t, al, b, pl.po);
+    }
+    pl.row_off.push_back(n_rows);
+    pl.n_blocks = b;
+}
+
+// device side of one branch: interpolate the distinct matrices into `pool`, apply them (plan arrays staged in `stage`)
+int run_sel_branch(mope_ctx* c, const SelPlan& pl, char* stage, size_t stage_bytes, double* pool, const double* V, double* parent, double* trans,
+                   int mask, cudaStream_t st) {
+    const int n_jobs = (int)pl.po.mat_off.size();
+    if (n_jobs == 0) return 0;
+    Bump sb;
+    sb.base = stage; sb.cap = stage_bytes;
+    InterpJob* d_jobs = sb.take<InterpJob>(std::max<size_t>(pl.po.jobs.size(), 1));
+    int64_t* d_off = sb.take<int64_t>(n_jobs);
+    int32_t* d_roff = sb.take<int32_t>(n_jobs + 1);
+    int32_t* d_rows = sb.take<int32_t>(std::max<size_t>(pl.rows.size(), 1));
+    if (!sb.ok()) return fail(MOPE_E_NOMEM, "selection: staging area too small");
+    if (!pl.po.jobs.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(d_jobs, pl.po.jobs.data(), pl.po.jobs.size() * sizeof(InterpJob), cudaMemcpyHostToDevice, st));
+        if (int rc = launch_interp(c, d_jobs, pl.po.jobs.size(), pool, st, false)) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_off, pl.po.mat_off.data(), (size_t)n_jobs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_roff, pl.row_off.data(), (size_t)(n_jobs + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_rows, pl.rows.data(), pl.rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    sel_matvec_kernel<<<n_jobs, 256, (size_t)SEL_ROWS * c->Fp * sizeof(double), st>>>(pool, d_off, d_roff, d_rows, V, parent, trans, c->F, c->Fp, mask);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    // the host vectors of the plan are pageable: the copies above were staged synchronously by the runtime
+    return 0;
+}
+size_t sel_stage_bytes(int n_rows) {
+    return align_up((size_t)n_rows * sizeof(InterpJob), 256) + align_up((size_t)n_rows * 8, 256) + align_up((size_t)(n_rows + 1) * 4, 256) +
+           align_up((size_t)n_rows * 4, 256) + 1024;
+}
+}  // namespace
+
+extern "C" {
+
+int mope_b200_sel_branch_update(mope_ctx* c, int mask, const double* child, double* parent, int n_rows, const double* times, int per_row_times,
+                                const double* alphas, double* out_trans, void* stream, int32_t* out_status) {
+    if (!c || !child || !parent || !times || !alphas || !out_status || n_rows <= 0 || mask < 0 || mask > 7)
+        return fail(MOPE_E_INVALID, "sel_branch_update: bad argument");
+    const bool bott = (mask & MOPE_MASK_BOTTLENECK) != 0;
+    mask &= 3;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = c->F, Fp = c->Fp;
+    SelPlan pl;
+    plan_sel_rows(c, bott, n_rows, times, per_row_times ? 1 : 0, alphas, pl);
+    *out_status = pl.status;
+    if (pl.status) return 0;   // the reference raises at the first matrix fetch: nothing is modified
+    const size_t blk = blk_doubles(Fp);
+    const size_t stage_b = sel_stage_bytes(n_rows);
+    const size_t raw_b = align_up((size_t)n_rows * F * sizeof(double), 256), pad_b = align_up((size_t)n_rows * Fp * sizeof(double), 256);
+    const size_t need = stage_b + align_up(std::max<size_t>(pl.n_blocks, 1) * blk * sizeof(double), 256) + 2 * raw_b + 3 * pad_b + 1024;
+    if (ensure_opbuf(c, need)) return MOPE_E_CUDA;
+    Bump bb;
+    bb.base = c->opbuf; bb.cap = c->opbuf_cap;
+    char* stage = bb.take<char>(stage_b);
+    double* pool = bb.take<double>(std::max<size_t>(pl.n_blocks, 1) * blk);
+    double* raw_c = bb.take<double>((size_t)n_rows * F);
+    double* raw_p = bb.take<double>((size_t)n_rows * F);
+    double* V = bb.take<double>((size_t)n_rows * Fp);
+    double* Pn = bb.take<double>((size_t)n_rows * Fp);
+    double* T = bb.take<double>((size_t)n_rows * Fp);
+    if (!bb.ok()) return fail(MOPE_E_NOMEM, "sel_branch_update: scratch layout");
+    CUDA_TRY(cudaMemcpyAsync(raw_c, child, (size_t)n_rows * F * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(raw_p, parent, (size_t)n_rows * F * sizeof(double), cudaMemcpyHostToDevice, st));
+    const long long tot = (long long)n_rows * Fp;
+    pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(raw_c, V, n_rows, F, Fp, n_rows, 0);
+    pad_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(raw_p, Pn, n_rows, F, Fp, n_rows, 0);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 2;
+    if (int rc = run_sel_branch(c, pl, stage, stage_b, pool, V, Pn, out_trans ? T : nullptr, mask, st)) return rc;
+    const long long totu = (long long)n_rows * F;
+    unpad_rows_kernel<<<(unsigned)((totu + 255) / 256), 256, 0, st>>>(Pn, raw_p, n_rows, F, Fp);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(parent, raw_p, (size_t)n_rows * F * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out_trans) {
+        unpad_rows_kernel<<<(unsigned)((totu + 255) / 256), 256, 0, st>>>(T, raw_c, n_rows, F, Fp);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out_trans, raw_c, (size_t)n_rows * F * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    c->launches += 2;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int mope_b200_sel_loglike(mope_ctx* c, int ped, const double* branch_lengths, const double* locus_alphas, int n_pos, const int32_t* position_idx,
+                          const double* stat, void* stream, double* out_loglikes, double* out_log_asc, int32_t* out_status) {
+    if (!c || ped < 0 || ped >= c->n_ped || !branch_lengths || !locus_alphas || !position_idx || !stat || !out_loglikes || !out_log_asc ||
+        !out_status || n_pos <= 0)
+        return fail(MOPE_E_INVALID, "sel_loglike: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Pedigree& P = c->peds[ped];
+    const int F = c->F, Fp = c->Fp, L = P.L, B = P.n_branches, R3 = 3 * L;
+    if (L <= 0) return fail(MOPE_E_INVALID, "sel_loglike: pedigree without loci");
+    for (int i = 0; i < L; ++i)
+        if (position_idx[i] < 0 || position_idx[i] >= n_pos) return fail(MOPE_E_INVALID, "sel_loglike: position index %d of row %d out of range", position_idx[i], i);
+    // per-branch plans first: a parameter outside the tables fails the whole evaluation like the reference's ValueError
+    std::vector<SelPlan> plans(B);
+    std::vector<double> times(R3), alphas(R3);
+    size_t max_blocks = 1;
+    int32_t status = 0;
+    for (int b = 0; b < B; ++b) {
+        const int mc = P.br_mult_h[b];
+        for (int i = 0; i < L; ++i) {
+            // np.tile(data[multipliername].values * branch_lengths[branch_index], 3) / np.tile(alphas[position_idxs], 3)
+            const double t = mc >= 0 ? P.row_mult_h[(size_t)mc * L + i] * branch_lengths[b] : branch_lengths[b];
+            const double a = locus_alphas[(size_t)b * n_pos + position_idx[i]];
+            times[i] = times[L + i] = times[2 * L + i] = t;
+            alphas[i] = alphas[L + i] = alphas[2 * L + i] = a;
+        }
+        plan_sel_rows(c, false, R3, times.data(), 1, alphas.data(), plans[b]);
+        status |= plans[b].status;
+        max_blocks = std::max(max_blocks, plans[b].n_blocks);
+    }
+    *out_status = status;
+    if (status) return 0;
+    // buffers: cond[node] for internal nodes and the root, one leaf buffer, trans, asc
+    std::vector<int> node_buf(B + 1, -1);
+    int n_internal = 0;
+    for (int b = 0; b < B; ++b) if (P.br_leaf_h[b] < 0) node_buf[b] = n_internal++;
+    node_buf[B] = n_internal++;
+    const size_t blk = blk_doubles(Fp), nodeN = (size_t)R3 * Fp;
+    const size_t stage_b = sel_stage_bytes(R3);
+    const size_t need = stage_b + align_up(max_blocks * blk * 8, 256) + (size_t)(n_internal + 3) * align_up(nodeN * 8, 256) + align_up((size_t)Fp * 8, 256) +
+                        align_up((size_t)2 * L * 8, 256) + 4096;
+    if (ensure_opbuf(c, need)) return MOPE_E_CUDA;
+    Bump bb;
+    bb.base = c->opbuf; bb.cap = c->opbuf_cap;
+    char* stage = bb.take<char>(stage_b);
+    double* pool = bb.take<double>(max_blocks * blk);
+    double* cond = bb.take<double>((size_t)n_internal * nodeN);
+    double* leafbuf = bb.take<double>(nodeN);
+    double* trans = bb.take<double>(nodeN);
+    double* asc = bb.take<double>((size_t)L * Fp);
+    double* d_stat = bb.take<double>(Fp);
+    double* d_out = bb.take<double>((size_t)2 * L);
+    int8_t* d_e = bb.take<int8_t>(2 * (size_t)F);
+    if (!bb.ok()) return fail(MOPE_E_NOMEM, "sel_loglike: scratch layout");
+    std::vector<int8_t> e(2 * (size_t)F);
+    for (int f = 0; f < F; ++f) {   // likelihoods.py:425-430: inclusive comparisons
+        e[f] = c->freqs[f] <= c->min_freq ? 1 : 0;
+        e[F + f] = c->freqs[f] >= 1.0 - c->min_freq ? 1 : 0;
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_e, e.data(), e.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_stat, stat, (size_t)F * sizeof(double), cudaMemcpyHostToDevice, st));
+    {
+        const long long n1 = (long long)n_internal * nodeN, n2 = (long long)L * Fp;
+        sel_fill_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(cond, n1, 1.0);   // reset_likes_ones
+        sel_fill_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(asc, n2, 1.0);
+        CUDA_TRY(cudaGetLastError());
+        c->launches += 2;
+    }
+    for (int b = 0; b < B; ++b) {
+        const double* V;
+        if (P.br_leaf_h[b] >= 0) {
+            const long long n = (long long)nodeN;
+            sel_leaf_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P.E + (size_t)P.br_leaf_h[b] * P.R_pad * Fp, c->use_v4 ? 1 : 0, L, F, Fp, d_e, d_e + F, leafbuf);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+            V = leafbuf;
+        } else {
+            V = cond + (size_t)node_buf[b] * nodeN;
+        }
+        const int parent = P.br_parent_h[b];
+        const bool do_asc = parent == B;
+        // the plan arrays of consecutive branches share the staging area and the pool: everything is ordered by the stream
+        if (int rc = run_sel_branch(c, plans[b], stage, stage_b, pool, V, cond + (size_t)node_buf[parent] * nodeN, do_asc ? trans : nullptr, 0, st)) return rc;
+        if (do_asc) {
+            const long long n = (long long)L * Fp;
+            sel_asc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(trans, asc, L, Fp);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+        }
+    }
+    sel_root_kernel<<<(unsigned)(((long long)L * 32 + 255) / 256), 256, 0, st>>>(cond + (size_t)node_buf[B] * nodeN, asc, d_stat, L, F, Fp, d_out, d_out + L);
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out_loglikes, d_out, (size_t)L * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_log_asc, d_out + L, (size_t)L * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }
 

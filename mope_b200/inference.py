@@ -53,8 +53,6 @@ class Inference(object):
                  log_unif_drift=False, inverse_bot_priors=False, post_is_prior=False, lower_drift_limit=1e-3,
                  upper_drift_limit=3, min_phred_score=None, selection_model=False, device=0, workspace_bytes=None,
                  _inputs_are_text=False, mult_bounds=None, root_prior=None):
-        if selection_model:
-            raise NotImplementedError("the selection model is outside the GPU log-likelihood path")
         if data_are_freqs:
             raise NotImplementedError("frequency-format data (get_nearest_likelihoods_cython) is outside the GPU "
                                       "log-likelihood path; use allele counts")
@@ -77,7 +75,7 @@ class Inference(object):
         self.lower_drift_limit = lower_drift_limit
         self.upper_drift_limit = upper_drift_limit
         self.min_phred_score = min_phred_score
-        self.selection_model = False
+        self.selection_model = bool(selection_model)
         # where the root (stationary) distribution is computed: "auto" (default) = on the device for walkers with
         # ab >= ROOT_PRIOR_HOST_BELOW, SciPy's betainc on the host below it (there the reference's CDF differences are
         # dominated by rounding noise that only the same betainc reproduces); "device" = always the device kernel (the more
@@ -91,7 +89,7 @@ class Inference(object):
         self.true_loglike = None
 
         # tables (inference.py:741-763)
-        self.transition_data = _tables.load(transitions_file, bottleneck_file)
+        self.transition_data = _tables.load(transitions_file, bottleneck_file, selection=self.selection_model)
         self.bottleneck_data = self.transition_data if self.transition_data.bot is not None else None
         self.freqs = self.transition_data.get_bin_frequencies()
         self.num_freqs = self.freqs.shape[0]
@@ -108,6 +106,11 @@ class Inference(object):
                     tree_str = fin.read().strip()
             self.tree_strings.append(tree_str)
             datp = _model.read_table(dat_fn, _inputs_are_text)
+            if self.selection_model:
+                if "position" not in datp.columns:
+                    raise ValueError('The selection model requires a "position" column in each dataframe. Could not find '
+                                     'one in {}'.format("<text>" if _inputs_are_text else dat_fn))
+                datp = datp.sort_values(["family", "position"], kind="stable").reset_index(drop=True)   # inference.py:341-342
             agep = _model.read_table(age_fn, _inputs_are_text)
             self.peds.append(_model.compile_pedigree(datp, tree_str, agep))
 
@@ -146,6 +149,10 @@ class Inference(object):
         self.header = "\t".join(["ll"] + [v + "_l" for v in self.varnames] + [v + "_m" for v in self.varnames]
                                 + ["log10ab", "log10polyprob"])
         self.lower, self.upper, self.ndim = self._get_likelihood_limits()
+        if self.selection_model:
+            # per-position selection coefficients, DFEs, the selection prior box and header (mope_b200/selection.py)
+            from . import selection as _selection
+            _selection.init_selection(self)
 
         self.engine = Engine(self.transition_data, self.peds, [self.var_indices] * len(self.peds), nv, min_phred_score,
                              min_freq, genome_size, poisson_like_penalty, device=device, workspace_bytes=workspace_bytes)
@@ -180,8 +187,9 @@ class Inference(object):
         lower_len[isb] = 2
         upper_len[isb] = 500
         lower_len, upper_len = np.log10(lower_len), np.log10(upper_len)
-        min_mut = max(-8, np.log10(td.get_min_mutsel_rate()))
-        max_mut = min(-1, np.log10(td.get_max_mutsel_rate()))
+        with np.errstate(invalid="ignore", divide="ignore"):   # selection tables hold coefficients <= 0; the selection box replaces these
+            min_mut = max(-8, np.log10(td.get_min_mutsel_rate()))
+            max_mut = min(-1, np.log10(td.get_max_mutsel_rate()))
         lower = np.concatenate((lower_len, np.repeat(min_mut, nv), (-9, -9)))
         upper = np.concatenate((upper_len, np.repeat(max_mut, nv), (0, 0)))
         return lower, upper, 2 * nv + 2
@@ -209,6 +217,8 @@ class Inference(object):
         X = np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))
         if X.shape[1] != self.ndim:
             raise ValueError("expected parameter vectors of length {}".format(self.ndim))
+        if self.selection_model:   # per-position matrices: one device evaluation per vector
+            return np.array([self.loglike(x.copy()) for x in X])
         if self.root_prior != "scipy":
             ll, status = self.engine.loglike_hybrid(X, self.root_prior_host_mask(X), self.stationary_distributions)
         elif X.shape[0] >= 32:
@@ -233,6 +243,9 @@ class Inference(object):
         return ll, status, out
 
     def loglike(self, orig_params):
+        if self.selection_model:
+            from . import selection as _selection
+            return _selection.loglike(self, orig_params)
         return float(self.loglike_batch(np.asarray(orig_params, dtype=np.float64)[None, :])[0])
 
     def like_obj(self, varparams):

@@ -57,6 +57,9 @@ class PedigreeModel:
     br_leaf: np.ndarray
     br_mult: np.ndarray
     br_bottleneck: np.ndarray
+    position: Optional[np.ndarray] = None    # [L] base-pair position of every locus row (selection model), row order of `counts`
+    row_order: Optional[np.ndarray] = None   # [L] index of every row in the data file after removal of fixed loci
+    dfe: Optional[np.ndarray] = None         # [L] DFE label of every locus row (selection model, optional "dfe" column)
 
     @property
     def num_loci(self) -> int:
@@ -92,7 +95,7 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
 
     data = data.copy()
     for col in data.columns:
-        if col not in ("family", "position"):
+        if col not in ("family", "position", "dfe"):
             data[col] = data[col].astype(np.float64)
     missing = [c for c in leaf_names + [l + "_n" for l in leaf_names] if c not in data.columns]
     if missing:
@@ -103,6 +106,9 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
     data = data.loc[keep, :].reset_index(drop=True)
     X, n = np.ascontiguousarray(X[keep]), np.ascontiguousarray(n[keep])
     family = data["family"].values
+    position = data["position"].values if "position" in data.columns else None
+    dfe = data["dfe"].values if "dfe" in data.columns else None
+    row_order = np.arange(X.shape[0])
 
     ages = ages.copy()
     fam_ids = ages["family"].values
@@ -157,6 +163,9 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
         order = np.argsort(locus_rank, kind="stable")
         X, n, family = np.ascontiguousarray(X[order]), np.ascontiguousarray(n[order]), family[order]
         row_mult = np.ascontiguousarray(row_mult[:, order])
+        row_order = row_order[order]
+        position = position[order] if position is not None else None
+        dfe = dfe[order] if dfe is not None else None
         # distinct ascertainment pairs in the same order
         uniq_rank = np.full(asc_mult.shape[1], len(fam_ids), dtype=np.int64)
         np.minimum.at(uniq_rank, fam_asc, rank_of_fam_pos)
@@ -186,7 +195,7 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
             # Measured on B200 (profiles/r02_row_order.md): one multiplier column (the k-d order is a plain sort by age, whole
             # runs of tiles share their generation segments): frequency order inside blocks of 32768 rows, cfg4 4228 -> 3868 ms
             # per step; several columns (small k-d cells): two frequency classes, each in k-d order, cfg3 499 -> 483 ms.
-            classes = int(os.environ.get("MOPE_FREQ_CLASSES", "1" if M == 1 else "2"))
+            classes = int(os.environ.get("MOPE_FREQ_CLASSES", "2" if (M > 1 and L >= 8192) else "1"))   # small data: keep the k-d cells
             block = int(os.environ.get("MOPE_FREQ_BLOCK", "32768" if M == 1 else "0"))
             order = None
             if classes > 1 or block > 0:
@@ -201,6 +210,9 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
         if order is not None:
             X, n, family = np.ascontiguousarray(X[order]), np.ascontiguousarray(n[order]), family[order]
             row_mult = np.ascontiguousarray(row_mult[:, order])
+            row_order = row_order[order]
+            position = position[order] if position is not None else None
+            dfe = dfe[order] if dfe is not None else None
 
     idx_of = {id(nd): i for i, nd in enumerate(nodes)}
     idx_of[id(tree)] = len(nodes)
@@ -213,7 +225,8 @@ def compile_pedigree(data: pd.DataFrame, tree_str: str, ages: pd.DataFrame, sort
                          multiplier_of=multiplier_of, bottleneck_of_var=bott, multipliernames=multipliernames,
                          counts=X, coverage=n, family=family, ages=ages, row_mult=np.ascontiguousarray(row_mult),
                          asc_mult=asc_mult, fam_asc=fam_asc, fam_count=counts.astype(np.float64),
-                         br_parent=br_parent, br_leaf=br_leaf, br_mult=br_mult, br_bottleneck=br_bott)
+                         br_parent=br_parent, br_leaf=br_leaf, br_mult=br_mult, br_bottleneck=br_bott, position=position,
+                         row_order=row_order, dfe=dfe)
 
 
 def _kd_order(P: np.ndarray, leaf_size: int = 8) -> np.ndarray:

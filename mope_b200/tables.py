@@ -75,11 +75,12 @@ class TransitionTables:
     def get_max_mutsel_rate(self):
         return self.us.max() * 2 * self.N
 
-    def save_hdf5(self, transitions_file: str, bottleneck_file: Optional[str] = None, breaks_args=None) -> None:
+    def save_hdf5(self, transitions_file: str, bottleneck_file: Optional[str] = None, breaks_args=None, selection: bool = False) -> None:
         """Write master files in the reference's HDF5 layout (generate_transitions.py:242-323, :420-470): datasets `P<idx>`
         with attributes N, s, u, v, gen (drift) or N, Nb, u (bottleneck), root attributes N, breaks, frequencies (and
         min_bin_size / uniform_weight when `breaks_args = (uniform_weight, min_bin_size)` is given).  Written by the
-        built-in HDF5 writer (hdf5_lite): the image has no libhdf5."""
+        built-in HDF5 writer (hdf5_lite): the image has no libhdf5.  `selection`: `us` holds selection coefficients, written
+        as attribute s with u = v = 0 (the recipe of `mope generate-commands --selection`, generate_transitions.py:549-551)."""
         from . import hdf5_lite
         root = {"N": int(self.N), "breaks": np.asarray(self.breaks, dtype=np.int64), "frequencies": self.freqs}
         if breaks_args is not None:
@@ -87,7 +88,9 @@ class TransitionTables:
         dsets, idx = {}, 0
         for j, u in enumerate(self.us):
             for i, g in enumerate(self.gens):
-                dsets["P%d" % idx] = (self.drift[i, j], {"N": int(self.N), "s": 0.0, "u": float(u), "v": float(u), "gen": int(g)})
+                attrs = {"N": int(self.N), "s": float(u), "u": 0.0, "v": 0.0, "gen": int(g)} if selection else \
+                    {"N": int(self.N), "s": 0.0, "u": float(u), "v": float(u), "gen": int(g)}
+                dsets["P%d" % idx] = (self.drift[i, j], attrs)
                 idx += 1
         hdf5_lite.write_file(transitions_file, root, dsets)
         if bottleneck_file is not None:
@@ -165,9 +168,11 @@ def _grid_from_h5(path: str, axis_attr: str, xkey: str = "u"):
     return dense, ax, xs, float(N), freqs, breaks
 
 
-def load(transitions_file, bottleneck_file=None) -> TransitionTables:
+def load(transitions_file, bottleneck_file=None, selection=False) -> TransitionTables:
     """`transitions_file` / `bottleneck_file` as given to `mope run`: HDF5 master files, or one .npz
-    holding both grids (written by TransitionTables.save), or an already-built TransitionTables."""
+    holding both grids (written by TransitionTables.save), or an already-built TransitionTables.  `selection`: the
+    second axis of the drift grid is the selection coefficient `s` of every dataset instead of its mutation rate `u`
+    (TransitionData(selection=True), transition_data_2d.py:52-55); `us` then holds the s values."""
     if isinstance(transitions_file, TransitionTables):
         return transitions_file
     if str(transitions_file).endswith(".npz"):
@@ -180,7 +185,7 @@ def load(transitions_file, bottleneck_file=None) -> TransitionTables:
         elif bottleneck_file is None:
             tb.bot = tb.nbs = tb.bot_us = None
         return tb
-    drift, gens, us, N, freqs, breaks = _grid_from_h5(transitions_file, "gen")
+    drift, gens, us, N, freqs, breaks = _grid_from_h5(transitions_file, "gen", "s" if selection else "u")
     kw = dict(drift=drift, gens=gens, us=us, N=N, freqs=freqs, breaks=breaks)
     if bottleneck_file is not None:
         bot, nbs, bus, _, _, _ = _grid_from_h5(bottleneck_file, "Nb")

@@ -81,6 +81,10 @@ def test_row_sorting_is_a_consistent_permutation():
                       for i in range(pm.num_loci))
     assert rows(a) == rows(b)
     assert not np.array_equal(a.family, b.family)          # it did reorder something
+    # row_order maps every row back to its row of the (filtered) data file
+    np.testing.assert_array_equal(a.row_order, np.arange(a.num_loci))
+    np.testing.assert_array_equal(np.sort(b.row_order), np.arange(a.num_loci))
+    np.testing.assert_array_equal(a.coverage[b.row_order], b.coverage)
     np.testing.assert_array_equal(a.fam_count, b.fam_count)
     for f in range(a.n_fam):
         np.testing.assert_array_equal(a.asc_mult[:, a.fam_asc[f]], b.asc_mult[:, b.fam_asc[f]])
