@@ -298,7 +298,9 @@ int mope_b200_gen_bin_matrix(const double* P_dev, int ld, int n_states, const in
  *   mask 1  Pzero[0,0] = P[0,0]: compute_leaf_zero_transition_likelihood / compute_length_transition_likelihood_zero
  *           (:82-98, :178-194);  mask 2  Pzero[0,1:-1]: ..._focal_node_zero / ..._zero_focalnode (:101-117, :197-212);
  *   mask 3  Pzero[1:-1,1:-1]: ..._zero_descendant (:120-136, :215-229).  For the masked variants pass the single mutation
- *           rate in every alphas[r].
+ *           rate in every alphas[r].  mask | MOPE_MASK_BOTTLENECK: the matrix comes from the bottleneck tables and times[0]
+ *           is the bottleneck size: compute_bottleneck_transition_likelihood_zero / _zero_focalnode / _zero_descendant
+ *           (:251-307).
  * child / parent host [n_rows][F]; out_trans (may be NULL) host [n_rows][F] receives the products Pmask_r . child[r]
  * (the `ret` array of the selection variants).  *out_status = MOPE_ST_* of the first failing fetch (nothing is modified). */
 #define MOPE_MASK_BOTTLENECK 4
