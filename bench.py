@@ -460,6 +460,7 @@ def measure(D, inf, X, steps, warmup, locus_sharded=False, sample_clocks=True):
     tree_ms, tree_n, interp_ms, interp_n = eng.kernel_times()
     gemm_ops, identity_ops = eng.last_eval_stats()
     unit_rows = eng.last_eval_unit_rows()
+    warp_segs, warp_segs_active = eng.last_eval_segment_stats()
     eng.set_profiling(False)
     ms = D.max_over_ranks(ms_local)
     ll_dev = out_dev.cpu().numpy()
@@ -486,6 +487,7 @@ def measure(D, inf, X, steps, warmup, locus_sharded=False, sample_clocks=True):
             "tree_ms_per_step": tree_ms / max(steps, 1), "tree_launches_per_step": steps_per_eval,
             "interp_ms_per_step": interp_ms / max(steps, 1), "interp_launches_per_step": interp_n / max(steps, 1),
             "gemm_ops": int(gemm_ops), "identity_ops": int(identity_ops), "unit_rows": int(unit_rows),
+            "warp_segs": int(warp_segs), "warp_segs_active": int(warp_segs_active),
             "ll_host": ll_host, "clocks": clocks.summary() if clocks else None}
 
 
@@ -597,6 +599,17 @@ def run_extra_config(D, name, base_tb, workdir, peak, do_cpu, steps_cap):
               "tree_kernel4<26,25,scalar" + (",ascfast>" if R_exec - ped.num_loci >= 64 else ">") +
               (" + canonical launch (family-independent ascertainment subtrees once per walker)" if m["tree_launches_per_step"] > 1.5 else ""))
     roof = tree_roofline(m, F, R_exec, R_ref, B, X.shape[0], peak, kernel)
+    n_rate = int((ped.br_mult >= 0).sum())
+    if n_rate > 0 and m["warp_segs"] > 0:
+        # age-scaled branches: every branch multiplies against each grid generation the tile's rows blend (2 is the minimum: a
+        # row blends two generations); a warp none of whose 8 rows touches a segment idles through it
+        warps = (R_exec + 7) // 8
+        roof["age_scaled"] = {"branches": n_rate,
+                              "segments_per_warp_and_branch": m["warp_segs"] / float(X.shape[0] * n_rate * warps),
+                              "active_segments_per_warp_and_branch": m["warp_segs_active"] / float(X.shape[0] * n_rate * warps),
+                              "idle_warp_segment_frac": 1.0 - m["warp_segs_active"] / float(m["warp_segs"]),
+                              "note": "counted by the kernel (mope_b200_last_eval_segment_stats); pure pseudo-row tiles take the "
+                                      "messages of age-scaled leaf branches from the stored column sums and run no segment"}
     per_rank = {"ms_per_step": D.gather(m["ms_local"]), "e2e_ms_per_step": D.gather(m["e2e_local_s"] * 1e3),
                 "tree_kernel_ms_per_step": D.gather(m["tree_ms_per_step"]), "loci": D.gather(inf.num_loci[0]),
                 "rows_per_walker": D.gather(R_exec)}
@@ -604,6 +617,9 @@ def run_extra_config(D, name, base_tb, workdir, peak, do_cpu, steps_cap):
     e2e_value = W_total * L_total / m["e2e_s"]
     ll_host = m["ll_host"]
 
+    pb = None
+    if name == "cfg4" and D.rank == 0:
+        pb = poisson_binomial_leg(inf, tb, do_cpu and D.world == 1)
     parity = None
     sharded_parity = None
     if locus:
@@ -633,6 +649,35 @@ def run_extra_config(D, name, base_tb, workdir, peak, do_cpu, steps_cap):
            "setup_s": {"data": t_data, "model_and_tables": t_setup - t_data, "total_wall": time.perf_counter() - t_begin}}
     if sharded_parity is not None:
         out["parity_sharded_vs_single_gpu"] = sharded_parity
+    if pb is not None:
+        out["poisson_binomial"] = pb
+    return out
+
+
+def poisson_binomial_leg(inf, tb, do_cpu):
+    """cfg4's emission variant: Poisson-binomial non-ascertainment vectors P(alt reads < ceil(min_freq * nreads) | f)
+    for read sets with nreads ~ Poisson(1000) and per-read phred from {20, 30, 40} w.p. {0.1, 0.6, 0.3}, on the F = 201 grid
+    (mope_b200_non_asc_probs; _poisson_binom.get_non_asc_probs is referenced by nothing in the reference, so this is a
+    function-level leg, not part of the log-likelihood).  Host read sets in, host vectors out."""
+    rng = np.random.RandomState(41)
+    n_sets = 2048
+    sets = [rng.choice([20.0, 30.0, 40.0], size=max(1, int(n)), p=[0.1, 0.6, 0.3]) for n in rng.poisson(1000, n_sets)]
+    n_reads = int(sum(len(q) for q in sets))
+    eng = inf.engine
+    out = {"read_sets": n_sets, "reads": n_reads, "F": int(tb.F), "runs": []}
+    for mf in (0.001, 0.05):
+        eng.non_asc_probs(sets[:64], tb.freqs, mf)                       # warm-up
+        t0 = time.perf_counter()
+        res = eng.non_asc_probs(sets, tb.freqs, mf)
+        dt = time.perf_counter() - t0
+        K = int(np.ceil(mf * 1000))
+        run = {"min_freq": mf, "K_typical": K, "ms": dt * 1e3, "read_sets_per_s": n_sets / dt, "dp_updates_per_s": n_reads * K * tb.F / dt}
+        if do_cpu:
+            from oracle import mope_oracle as orc
+            ref = np.array([orc.get_non_asc_probs(sets[i], tb.freqs, mf) for i in range(2)])
+            run["parity_max_rel_err_vs_oracle"] = float((np.abs(res[:2] - ref) / np.maximum(np.abs(ref), 1e-300)).max())
+            run["parity_sets_compared"] = 2
+        out["runs"].append(run)
     return out
 
 
@@ -740,9 +785,9 @@ def run_ours(args):
                                        if locus else "walker-sharded x%d" % world),
                        "l2_policy": "inputs larger than L2 (emissions %.0f MB + per-walker matrices %.0f MB per step)" % (
                            R_local * len(inf.leaf_names[0]) * Fp * 8 / 1e6, W * n_keys * Fp * (Fp + 3) * 8 / 1e6),
-                       "value_note": "value = device-resident step: tables, emissions and the walkers' root prior (a function of two "
-                                     "parameters, computed on the host by SciPy's betainc) already in HBM; e2e includes the root prior, "
-                                     "pipelined against the device work",
+                       "value_note": "value = device-resident step: tables, emissions and the walkers' root prior (a function of two of "
+                                     "the parameters) already in HBM; e2e includes the root prior (device kernel; SciPy's betainc on the "
+                                     "host for walkers with ab < 1e-6, pipelined against the device work)",
                        "finite_walkers": int(np.isfinite(ll_host).sum())},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": m["e2e_s"] * 1e3},

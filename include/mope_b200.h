@@ -222,6 +222,12 @@ int mope_b200_last_eval_stats(const mope_ctx* ctx, int64_t* gemm_ops, int64_t* i
  * that sum / F.  Synchronises the stream of the last eval. */
 int mope_b200_last_eval_unit_rows(mope_ctx* ctx, int64_t* unit_rows);
 
+/* Age-scaled branches of the last eval: (warp, generation segment) pairs the pruning kernel went through -- a warp = 8
+ * rows of a tile, a segment = one grid generation the tile's rows blend on that branch -- and how many of them the warp
+ * actually multiplied in (at least one of its rows has a non-zero weight there).  The difference is tensor-pipe time the
+ * warp's partner spends alone.  F <= 208 only (zeros otherwise).  Synchronises the stream of the last eval. */
+int mope_b200_last_eval_segment_stats(mope_ctx* ctx, int64_t* warp_segments, int64_t* active_warp_segments);
+
 /* Measurement support (bench.py).  With profiling on, every pruning-kernel launch is bracketed by CUDA events on
  * its stream; mope_b200_kernel_times synchronises, returns the accumulated device time (ms) and launch count of the
  * pruning kernel and of the interpolation kernel since the last call, and resets the accumulators. */

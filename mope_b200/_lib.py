@@ -68,7 +68,7 @@ SYMBOLS = ["mope_b200_arena_bytes", "mope_b200_create", "mope_b200_destroy", "mo
            "mope_b200_kernel_times", "mope_b200_fp64_peak", "mope_b200_transition_matrix",
            "mope_b200_leaf_likelihoods", "mope_b200_branch_update", "mope_b200_non_asc_probs", "mope_b200_beta_cdf_table",
            "mope_b200_gen_binom_matrix", "mope_b200_gen_transpose", "mope_b200_gen_dgemm_tn", "mope_b200_gen_bin_matrix",
-           "mope_b200_sel_branch_update", "mope_b200_sel_loglike",
+           "mope_b200_sel_branch_update", "mope_b200_sel_loglike", "mope_b200_last_eval_segment_stats",
            "mope_b200_last_error", "mope_b200_version"]
 
 ST_MESSAGES = {
@@ -124,6 +124,7 @@ def lib():
     L.mope_b200_gen_bin_matrix.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]
     L.mope_b200_sel_branch_update.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, C.c_int, dp, dp, vp, ip]
     L.mope_b200_sel_loglike.argtypes = [vp, C.c_int, dp, dp, C.c_int, ip, dp, vp, dp, dp, ip]
+    L.mope_b200_last_eval_segment_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.mope_b200_last_error.restype = C.c_char_p
     L.mope_b200_version.restype = C.c_char_p
     for name in SYMBOLS:

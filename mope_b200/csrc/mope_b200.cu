@@ -974,7 +974,7 @@ int eval_impl(mope_ctx* c, const double* params, const double* stat, bool stat_o
 
     c->last_gemm_ops = 0;
     c->last_identity_ops = 0;
-    CUDA_TRY(cudaMemsetAsync(c->work_ctr + 8, 0, sizeof(unsigned long long), st));   // executed row x unit counter of this eval
+    CUDA_TRY(cudaMemsetAsync(c->work_ctr + 8, 0, 3 * sizeof(unsigned long long), st));   // executed row x unit counter + segment counters of this eval
     c->last_stream = st;
     hp_mark("fill_nan");
     // 3. chunk the valid walkers
@@ -1217,7 +1217,7 @@ int eval_resident_impl(mope_ctx* c, const double* params_dev, const double* stat
     const int Wchunk = (int)std::min<size_t>((size_t)W, (avail - slack) / pw);
 
     CUDA_TRY(cudaMemsetAsync(out_status_dev, 0, (size_t)W * sizeof(int32_t), st));
-    CUDA_TRY(cudaMemsetAsync(c->work_ctr + 8, 0, sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(c->work_ctr + 8, 0, 3 * sizeof(unsigned long long), st));
     c->last_stream = st;
     c->last_gemm_ops = -1;
     c->last_identity_ops = -1;
@@ -1708,6 +1708,17 @@ int mope_b200_last_eval_unit_rows(mope_ctx* c, int64_t* unit_rows) {
     unsigned long long v = 0;
     CUDA_TRY(cudaMemcpy(&v, c->work_ctr + 8, sizeof v, cudaMemcpyDeviceToHost));
     *unit_rows = (int64_t)((double)v / (double)c->F + 0.5);   // the kernels count rows x k columns; a full unit has F of them
+    return 0;
+}
+
+int mope_b200_last_eval_segment_stats(mope_ctx* c, int64_t* warp_segments, int64_t* active_warp_segments) {
+    if (!c || !warp_segments || !active_warp_segments) return fail(MOPE_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->last_stream));
+    unsigned long long v[3] = {0, 0, 0};
+    CUDA_TRY(cudaMemcpy(v, c->work_ctr + 8, sizeof v, cudaMemcpyDeviceToHost));
+    *warp_segments = (int64_t)v[1];
+    *active_warp_segments = (int64_t)v[2];
     return 0;
 }
 

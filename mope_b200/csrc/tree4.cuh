@@ -87,7 +87,8 @@ struct Tree4Params {
     double* uni_msg;
     int32_t n_uroot, canonical;
     int32_t* work_ctr;       // zeroed before the launch: next item to hand out (items differ in cost: identity branches)
-    unsigned long long* unit_rows;   // statistics: += real rows x k columns actually run through the tensor pipe (may be null)
+    unsigned long long* unit_rows;   // statistics (may be null): [0] += real rows x k columns actually run through the tensor pipe;
+                                     // [1] / [2] += (warp, generation segment) pairs of age-scaled branches sat through / multiplied in
     const unsigned long long* emask;   // [n_leaves][R_pad / 8]: K chunks of an 8-row group of E that are not all zero (may be null)
     const int32_t* wstatus;  // device-planned evaluations: per-walker MOPE_ST_* bits, non-zero = skip the walker (may be null)
 };
@@ -451,6 +452,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             // leaf branches: K chunks in which the warp's 8 emission rows are all zero add nothing (emission_mask_kernel)
             unsigned long long cmask = ~0ull;
             if (op.leaf >= 0 && nseg > 0 && p.emask != nullptr && !p.canonical) cmask = p.emask[((size_t)op.leaf * p.R_pad + row0) / 8 + warp];
+            if (op.kind == 1 && nseg > 0 && p.unit_rows != nullptr && row0 + warp * 8 < p.R) {
+                // statistics, outside the GEMM loops: (warp, segment) pairs of this branch and those the warp multiplies in
+                int act = 0;
+                for (int si = 0; si < nseg; ++si) {
+                    const int seg = ts->seg_lo[oi] + si;
+                    const bool nz = gi >= 0 && ((seg == gi - 1 && ra != 0.0) || (seg == gi && rd != 0.0));
+                    act += __any_sync(0xffffffffu, nz) ? 1 : 0;
+                }
+                if (lane == 0) { atomicAdd(p.unit_rows + 1, (unsigned long long)nseg); atomicAdd(p.unit_rows + 2, (unsigned long long)act); }
+            }
             for (int si = 0; si < nseg; ++si) {
                 double wgt = 1.0;
                 if (op.kind == 1) {
@@ -639,6 +650,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tree_kernel4(const __grid_constan
             const int real = max(0, min(8, p.R - (row0 + warp * 8)));
             if (real > 0) atomicAdd(p.unit_rows, (unsigned long long)my_kcols * (unsigned)real);
         }
+
         __syncthreads();   // rowval complete; every warp is done with the item's tables
         if (p.Yout == nullptr && !p.canonical && warp == 0) {
             double part = ts->rowval[lane] + ts->rowval[lane + 32];

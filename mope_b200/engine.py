@@ -330,6 +330,12 @@ class Engine:
         _lib.check(self.lib.mope_b200_last_eval_unit_rows(self.ctx, C.byref(v)), "mope_b200_last_eval_unit_rows")
         return int(v.value)
 
+    def last_eval_segment_stats(self):
+        """(warp x generation-segment pairs of age-scaled branches the pruning kernel went through, those it multiplied in)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.lib.mope_b200_last_eval_segment_stats(self.ctx, C.byref(a), C.byref(b)), "mope_b200_last_eval_segment_stats")
+        return int(a.value), int(b.value)
+
     def kernel_times(self):
         """(tree_ms, tree_launches, interp_ms, interp_launches) accumulated since the last call; synchronises."""
         tm, im = C.c_double(0), C.c_double(0)
