@@ -64,6 +64,20 @@ struct Bump {
     bool ok() const { return dry || used <= cap; }
 };
 
+// selection model: parameter-independent row groups of a pedigree (selection.cuh), built at the first mope_b200_sel_loglike
+struct SelCache {
+    bool valid = false;
+    std::vector<int32_t> pos_idx;            // the position index the cache was built for
+    int n_pos = 0;
+    std::vector<int> br_first, br_groups;    // per branch: first group (flat index) and number of groups
+    int total_groups = 0;
+    char* dev = nullptr;                     // one allocation: g_mult, g_pos, g_branch, g_local, g_row_off, g_rows
+    double* g_mult = nullptr;
+    int32_t *g_pos = nullptr, *g_branch = nullptr, *g_local = nullptr;
+    int32_t* g_row_off = nullptr;            // [total_groups + n_branches]: per branch n_groups + 1 offsets into that branch's g_rows
+    int32_t* g_rows = nullptr;               // [n_branches][3 L]
+};
+
 struct Pedigree {
     int n_leaves = 0, n_branches = 0, L = 0, n_fam = 0, n_mult = 0, n_asc = 0;
     int R = 0, R_pad = 0, n_tiles = 0, n_slots = 0, n_ops = 0;
@@ -86,6 +100,7 @@ struct Pedigree {
     // host copies for the selection-model entry points (per-row plans are made on the host)
     std::vector<int32_t> br_parent_h, br_leaf_h, br_mult_h;
     std::vector<double> row_mult_h;   // [n_mult][L]
+    SelCache sel;
 };
 
 struct FixedKey { int var; int bott; };
@@ -1605,6 +1620,7 @@ int mope_b200_destroy(mope_ctx* c) {
     for (int i = 0; i < 2; ++i) if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
     if (c->opbuf) cudaFree(c->opbuf);
     if (c->plan_consts) cudaFree(c->plan_consts);
+    for (auto& P : c->peds) if (P.sel.dev) cudaFree(P.sel.dev);
     for (auto& pr : c->ev_tree) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pr : c->ev_interp) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -2231,6 +2247,70 @@ int run_sel_branch(mope_ctx* c, const SelPlan& pl, char* stage, size_t stage_byt
     // the host vectors of the plan are pageable: the copies above were staged synchronously by the runtime
     return 0;
 }
+// Row groups of the selection model: on branch b the rows (locus i and its two pseudo-rows L + i, 2L + i) with the same
+// (multiplier value, position) share their transition matrix for every parameter vector.  Built once per pedigree and
+// position index; everything the per-evaluation planning kernel needs stays on the device.
+int build_sel_cache(mope_ctx* c, Pedigree& P, const int32_t* position_idx, int n_pos, cudaStream_t st) {
+    SelCache& S = P.sel;
+    const int L = P.L, B = P.n_branches, R3 = 3 * L;
+    if (S.valid && S.n_pos == n_pos && (int)S.pos_idx.size() == L && std::memcmp(S.pos_idx.data(), position_idx, (size_t)L * sizeof(int32_t)) == 0)
+        return 0;
+    for (int i = 0; i < L; ++i)
+        if (position_idx[i] < 0 || position_idx[i] >= n_pos) return fail(MOPE_E_INVALID, "sel_loglike: position index %d of row %d out of range", position_idx[i], i);
+    if (S.dev) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(S.dev); S.dev = nullptr; }
+    S.valid = false;
+    S.pos_idx.assign(position_idx, position_idx + L);
+    S.n_pos = n_pos;
+    S.br_first.assign(B, 0);
+    S.br_groups.assign(B, 0);
+    std::vector<double> g_mult;
+    std::vector<int32_t> g_pos, g_branch, g_local, g_row_off, g_rows((size_t)B * R3);
+    std::vector<int32_t> order(L);
+    for (int b = 0; b < B; ++b) {
+        const int mc = P.br_mult_h[b];
+        const double* mult = mc >= 0 ? P.row_mult_h.data() + (size_t)mc * L : nullptr;
+        for (int i = 0; i < L; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int bq) {
+            const double ma = mult ? mult[a] : 1.0, mb = mult ? mult[bq] : 1.0;
+            if (ma != mb) return ma < mb;                  // NaN multipliers were rejected at create
+            if (position_idx[a] != position_idx[bq]) return position_idx[a] < position_idx[bq];
+            return a < bq;
+        });
+        S.br_first[b] = (int)g_mult.size();
+        int32_t* rows = g_rows.data() + (size_t)b * R3;
+        int nrow = 0, local = 0;
+        for (int k = 0; k < L; ++k) {
+            const int i = order[k];
+            const double m = mult ? mult[i] : 1.0;
+            const bool fresh = k == 0 || m != (mult ? mult[order[k - 1]] : 1.0) || position_idx[i] != position_idx[order[k - 1]];
+            if (fresh) {
+                g_mult.push_back(m); g_pos.push_back(position_idx[i]); g_branch.push_back(b); g_local.push_back(local++);
+                g_row_off.push_back(nrow);
+            }
+            rows[nrow++] = i; rows[nrow++] = L + i; rows[nrow++] = 2 * L + i;   // np.tile(..., 3): likelihood, all-zero, all-one rows
+        }
+        g_row_off.push_back(nrow);
+        S.br_groups[b] = local;
+    }
+    S.total_groups = (int)g_mult.size();
+    const size_t TG = g_mult.size();
+    const size_t bytes = align_up(TG * 8, 256) + 3 * align_up(TG * 4, 256) + align_up(g_row_off.size() * 4, 256) + align_up(g_rows.size() * 4, 256) + 1024;
+    CUDA_TRY(cudaMalloc(&S.dev, bytes));
+    Bump bb;
+    bb.base = S.dev; bb.cap = bytes;
+    S.g_mult = bb.take<double>(TG); S.g_pos = bb.take<int32_t>(TG); S.g_branch = bb.take<int32_t>(TG); S.g_local = bb.take<int32_t>(TG);
+    S.g_row_off = bb.take<int32_t>(g_row_off.size()); S.g_rows = bb.take<int32_t>(g_rows.size());
+    if (!bb.ok()) return fail(MOPE_E_NOMEM, "sel_loglike: group cache layout");
+    CUDA_TRY(cudaMemcpy(S.g_mult, g_mult.data(), TG * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(S.g_pos, g_pos.data(), TG * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(S.g_branch, g_branch.data(), TG * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(S.g_local, g_local.data(), TG * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(S.g_row_off, g_row_off.data(), g_row_off.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(S.g_rows, g_rows.data(), g_rows.size() * 4, cudaMemcpyHostToDevice));
+    S.valid = true;
+    return 0;
+}
+
 size_t sel_stage_bytes(int n_rows) {
     return align_up((size_t)n_rows * sizeof(InterpJob), 256) + align_up((size_t)n_rows * 8, 256) + align_up((size_t)(n_rows + 1) * 4, 256) +
            align_up((size_t)n_rows * 4, 256) + 1024;
@@ -2296,45 +2376,36 @@ int mope_b200_sel_loglike(mope_ctx* c, int ped, const double* branch_lengths, co
         return fail(MOPE_E_INVALID, "sel_loglike: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const Pedigree& P = c->peds[ped];
+    Pedigree& P = c->peds[ped];
     const int F = c->F, Fp = c->Fp, L = P.L, B = P.n_branches, R3 = 3 * L;
     if (L <= 0) return fail(MOPE_E_INVALID, "sel_loglike: pedigree without loci");
-    for (int i = 0; i < L; ++i)
-        if (position_idx[i] < 0 || position_idx[i] >= n_pos) return fail(MOPE_E_INVALID, "sel_loglike: position index %d of row %d out of range", position_idx[i], i);
-    // per-branch plans first: a parameter outside the tables fails the whole evaluation like the reference's ValueError
-    std::vector<SelPlan> plans(B);
-    std::vector<double> times(R3), alphas(R3);
-    size_t max_blocks = 1;
-    int32_t status = 0;
-    for (int b = 0; b < B; ++b) {
-        const int mc = P.br_mult_h[b];
-        for (int i = 0; i < L; ++i) {
-            // np.tile(data[multipliername].values * branch_lengths[branch_index], 3) / np.tile(alphas[position_idxs], 3)
-            const double t = mc >= 0 ? P.row_mult_h[(size_t)mc * L + i] * branch_lengths[b] : branch_lengths[b];
-            const double a = locus_alphas[(size_t)b * n_pos + position_idx[i]];
-            times[i] = times[L + i] = times[2 * L + i] = t;
-            alphas[i] = alphas[L + i] = alphas[2 * L + i] = a;
-        }
-        plan_sel_rows(c, false, R3, times.data(), 1, alphas.data(), plans[b]);
-        status |= plans[b].status;
-        max_blocks = std::max(max_blocks, plans[b].n_blocks);
-    }
-    *out_status = status;
-    if (status) return 0;
-    // buffers: cond[node] for internal nodes and the root, one leaf buffer, trans, asc
+    if (int rc = build_sel_cache(c, P, position_idx, n_pos, st)) return rc;
+    const SelCache& S = P.sel;
+    const int TG = S.total_groups;
+    // buffers: cond[node] for internal nodes and the root, one leaf buffer, trans, asc, the matrix pool (a branch's groups go
+    // through it in chunks of pool_blocks)
     std::vector<int> node_buf(B + 1, -1);
     int n_internal = 0;
     for (int b = 0; b < B; ++b) if (P.br_leaf_h[b] < 0) node_buf[b] = n_internal++;
     node_buf[B] = n_internal++;
     const size_t blk = blk_doubles(Fp), nodeN = (size_t)R3 * Fp;
-    const size_t stage_b = sel_stage_bytes(R3);
-    const size_t need = stage_b + align_up(max_blocks * blk * 8, 256) + (size_t)(n_internal + 3) * align_up(nodeN * 8, 256) + align_up((size_t)Fp * 8, 256) +
-                        align_up((size_t)2 * L * 8, 256) + 4096;
+    int max_groups = 1;
+    for (int b = 0; b < B; ++b) max_groups = std::max(max_groups, S.br_groups[b]);
+    const size_t pool_cap_bytes = (size_t)1 << 30;   // at most ~1 GB of interpolated matrices in flight
+    const int pool_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_groups, pool_cap_bytes / (blk * sizeof(double))));
+    const size_t need = align_up((size_t)TG * sizeof(InterpJob), 256) + align_up((size_t)TG * 8, 256) + align_up((size_t)B * 8, 256) +
+                        align_up((size_t)B * n_pos * 8, 256) + align_up((size_t)pool_blocks * blk * 8, 256) +
+                        (size_t)(n_internal + 3) * align_up(nodeN * 8, 256) + align_up((size_t)Fp * 8, 256) + align_up((size_t)2 * L * 8, 256) +
+                        align_up(2 * (size_t)F, 256) + 8192;
     if (ensure_opbuf(c, need)) return MOPE_E_CUDA;
     Bump bb;
     bb.base = c->opbuf; bb.cap = c->opbuf_cap;
-    char* stage = bb.take<char>(stage_b);
-    double* pool = bb.take<double>(max_blocks * blk);
+    InterpJob* d_jobs = bb.take<InterpJob>(TG);
+    int64_t* d_moff = bb.take<int64_t>(TG);
+    double* d_len = bb.take<double>(B);
+    double* d_alpha = bb.take<double>((size_t)B * n_pos);
+    int32_t* d_status = bb.take<int32_t>(64);
+    double* pool = bb.take<double>((size_t)pool_blocks * blk);
     double* cond = bb.take<double>((size_t)n_internal * nodeN);
     double* leafbuf = bb.take<double>(nodeN);
     double* trans = bb.take<double>(nodeN);
@@ -2343,6 +2414,27 @@ int mope_b200_sel_loglike(mope_ctx* c, int ped, const double* branch_lengths, co
     double* d_out = bb.take<double>((size_t)2 * L);
     int8_t* d_e = bb.take<int8_t>(2 * (size_t)F);
     if (!bb.ok()) return fail(MOPE_E_NOMEM, "sel_loglike: scratch layout");
+    // ---- plan on the device: (time, alpha) of every group, range checks, interpolation jobs ----
+    CUDA_TRY(cudaMemcpyAsync(d_len, branch_lengths, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_alpha, locus_alphas, (size_t)B * n_pos * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t), st));
+    {
+        SelPlanParams sp{};
+        sp.g_mult = S.g_mult; sp.g_pos = S.g_pos; sp.g_branch = S.g_branch; sp.g_local = S.g_local;
+        sp.branch_len = d_len; sp.alphas = d_alpha; sp.n = TG; sp.n_pos = n_pos; sp.pool_blocks = pool_blocks;
+        sp.gens = c->gens_dev; sp.us = c->us_dev; sp.n_gens = c->n_gens; sp.n_us = c->n_us;
+        sp.N = c->N; sp.max_coal = c->max_coal; sp.min_mut = c->min_mut; sp.max_mut = c->max_mut;
+        sp.F = F; sp.Fp = Fp; sp.jobs = d_jobs; sp.mat_off = d_moff; sp.status = d_status;
+        sel_plan_kernel<<<(TG + 255) / 256, 256, 0, st>>>(sp);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+    }
+    int32_t status = 0;
+    CUDA_TRY(cudaMemcpyAsync(&status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *out_status = status;
+    if (status) return 0;   // a parameter outside the tables fails the whole evaluation like the reference's ValueError
+    // ---- the pass ----
     std::vector<int8_t> e(2 * (size_t)F);
     for (int f = 0; f < F; ++f) {   // likelihoods.py:425-430: inclusive comparisons
         e[f] = c->freqs[f] <= c->min_freq ? 1 : 0;
@@ -2370,8 +2462,17 @@ int mope_b200_sel_loglike(mope_ctx* c, int ped, const double* branch_lengths, co
         }
         const int parent = P.br_parent_h[b];
         const bool do_asc = parent == B;
-        // the plan arrays of consecutive branches share the staging area and the pool: everything is ordered by the stream
-        if (int rc = run_sel_branch(c, plans[b], stage, stage_b, pool, V, cond + (size_t)node_buf[parent] * nodeN, do_asc ? trans : nullptr, 0, st)) return rc;
+        double* par = cond + (size_t)node_buf[parent] * nodeN;
+        const int g0 = S.br_first[b], ng = S.br_groups[b];
+        const int32_t* roff = S.g_row_off + g0 + b;            // this branch's ng + 1 offsets
+        const int32_t* rows = S.g_rows + (size_t)b * R3;
+        for (int k0 = 0; k0 < ng; k0 += pool_blocks) {         // groups in chunks that fit the pool (stream order protects the reuse)
+            const int nk = std::min(pool_blocks, ng - k0);
+            if (int rc = launch_interp(c, d_jobs + g0 + k0, (size_t)nk, pool, st, false)) return rc;
+            sel_matvec_kernel<<<nk, 256, (size_t)SEL_ROWS * Fp * sizeof(double), st>>>(pool, d_moff + g0 + k0, roff + k0, rows, V, par, do_asc ? trans : nullptr, F, Fp, 0);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+        }
         if (do_asc) {
             const long long n = (long long)L * Fp;
             sel_asc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(trans, asc, L, Fp);

@@ -9,6 +9,12 @@
 // matrix of the main path, natural column order) and sel_matvec_kernel applies it to all of its rows: one CTA per
 // matrix, the operand rows staged in shared memory, one warp per matrix row with the row read coalesced exactly once.
 // The work is bound by moving the interpolated matrices (one F x F block per distinct pair), not by arithmetic.
+//
+// Which rows share a matrix does not depend on the parameters: time = multiplier(row) * length(branch) and
+// alpha = coefficient(position(row)) * size(branch), so rows with the same (multiplier value, position) on a branch form
+// a GROUP for every parameter vector.  The groups are built once per pedigree (host, mope_b200.cu) and stay on the
+// device; per evaluation sel_plan_kernel derives every group's (time, alpha), the range checks of
+// TransitionData.get_transition_probabilities_2d and the interpolation job -- nothing is planned on the host.
 #pragma once
 #include "kernels.cuh"
 
@@ -81,6 +87,70 @@ __global__ void __launch_bounds__(256) sel_matvec_kernel(const double* __restric
             }
         }
     }
+}
+
+// One thread per (branch, group): time = g_mult * branch_length, alpha = locus_alphas[branch][g_pos]; range checks
+// (transition_data_2d.py:158-173) OR-ed into *status; the interpolation job of the group (transition_data_2d.py:183-224,
+// dst = slot of the group inside the pool chunk it will be processed in) and its matrix offset (-1: identity short-cut).
+struct SelPlanParams {
+    const double* g_mult;        // [n] multiplier value of the group (1 for branches without a multiplier)
+    const int32_t* g_pos;        // [n] unique-position index
+    const int32_t* g_branch;     // [n]
+    const int32_t* g_local;      // [n] index of the group inside its branch
+    const double* branch_len;    // [B]
+    const double* alphas;        // [B][n_pos]
+    int32_t n, n_pos, pool_blocks;
+    const double *gens, *us;
+    int32_t n_gens, n_us;
+    double N, max_coal, min_mut, max_mut;
+    int32_t F, Fp;
+    InterpJob* jobs;             // [n]
+    int64_t* mat_off;            // [n]
+    int32_t* status;
+};
+
+__global__ void sel_plan_kernel(SelPlanParams p) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= p.n) return;
+    const int b = p.g_branch[gid];
+    const double len = __dmul_rn(p.g_mult[gid], p.branch_len[b]);     // data[multipliername].values * branch_lengths[b]
+    const double mut = p.alphas[(size_t)b * p.n_pos + p.g_pos[gid]];
+    const size_t FF = (size_t)p.F * p.F;
+    int32_t st = 0;
+    if (!isfinite(len) || !isfinite(mut)) st |= 32;
+    if (len > p.max_coal) st |= 1;
+    if (mut < p.min_mut) st |= 2;
+    if (mut > p.max_mut) st |= 4;
+    InterpJob jb;
+    jb.pad = 0;
+    jb.flags = 8;
+    jb.dst = (int64_t)((size_t)(p.g_local[gid] % p.pool_blocks) * blk_doubles(p.Fp));
+    jb.src[0] = jb.src[1] = jb.src[2] = jb.src[3] = 0;
+    jb.w[0] = jb.w[1] = jb.w[2] = jb.w[3] = 0.0;
+    int64_t moff = -1;
+    const double t = __dmul_rn(p.N, len);
+    if (!st && !(t < p.gens[0])) {
+        const int G = p.n_gens, U = p.n_us;
+        const int gi = min(lower_bound_dev(p.gens, G, t), G - 1);
+        const double xd = mut / (2.0 * p.N);
+        const int xi = min(lower_bound_dev(p.us, U, xd), U - 1);
+        const int g1 = gi > 0 ? gi - 1 : G - 1, x1i = xi > 0 ? xi - 1 : U - 1;   // python's index -1 wraps
+        const double t1 = p.gens[g1], t2 = p.gens[gi], x1 = p.us[x1i], x2 = p.us[xi];
+        const double denom = __dmul_rn(__dsub_rn(t2, t1), __dsub_rn(x2, x1));
+        jb.w[0] = __ddiv_rn(__dmul_rn(__dsub_rn(t2, t), __dsub_rn(x2, xd)), denom);
+        jb.w[2] = __ddiv_rn(__dmul_rn(__dsub_rn(t, t1), __dsub_rn(x2, xd)), denom);
+        jb.w[1] = __ddiv_rn(__dmul_rn(__dsub_rn(t2, t), __dsub_rn(xd, x1)), denom);
+        jb.w[3] = __ddiv_rn(__dmul_rn(__dsub_rn(t, t1), __dsub_rn(xd, x1)), denom);
+        jb.src[0] = (int64_t)(((size_t)g1 * U + x1i) * FF);
+        jb.src[1] = (int64_t)(((size_t)g1 * U + xi) * FF);
+        jb.src[2] = (int64_t)(((size_t)gi * U + x1i) * FF);
+        jb.src[3] = (int64_t)(((size_t)gi * U + xi) * FF);
+        jb.flags = 1;
+        moff = jb.dst;
+    }
+    p.jobs[gid] = jb;
+    p.mat_off[gid] = moff;
+    if (st) atomicOr(p.status, st);
 }
 
 // node_likes of a leaf in the selection model (likelihoods.py:427-433,465-469): rows [0, L) the leaf's emissions, rows
