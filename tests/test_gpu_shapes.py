@@ -68,7 +68,15 @@ def test_cfg3_cfg4_shape_rate_and_bottleneck_branches_vs_oracle():
     ds = synth.make_dataset(200, 8, tree=tree, seed=6)
     I, X, ll = _check_vs_oracle(ds, _tables_small(), 3, shrink=0.25)
     assert I.peds[0].n_asc == I.peds[0].n_fam                   # ages differ per family: no sharing
+    # the kernel's own count of (warp, generation segment) pairs of the age-scaled branches: every warp with real rows sits
+    # through at least one segment per age-scaled branch that is not identity-forwarded, and multiplies in at most those
+    segs, active = I.engine.last_eval_segment_stats()
+    assert 0 < active <= segs
     I.close()
+    # fixed-length branches only: no segments
+    J, _, _ = _check_vs_oracle(synth.make_dataset(64, 4, tree=synth.balanced_tree(4), seed=8), _tables_small(), 1)
+    assert J.engine.last_eval_segment_stats() == (0, 0)
+    J.close()
     # several frequency bins below min_freq / above 1 - min_freq: the ascertainment tiles take the leaf-branch messages
     # from multi-column low / high sums of the matrices (no GEMM), the mixed tile still multiplies
     I, X, ll = _check_vs_oracle(ds, _tables_small(), 2, shrink=0.25, min_freq=0.004)
