@@ -479,15 +479,37 @@ def measure(D, inf, X, steps, warmup, locus_sharded=False, sample_clocks=True):
     torch.cuda.synchronize()
     e2e_local = (time.perf_counter() - t0) / steps
     e2e_s = D.max_over_ranks(e2e_local)
-    if not os.environ.get("MOPE_DEBUG_MODE"):
-        assert np.array_equal(np.isnan(ll_host), np.isnan(ll_dev)) and \
-            np.allclose(ll_host[np.isfinite(ll_host)], ll_dev[np.isfinite(ll_dev)], rtol=1e-12), "device-resident and e2e results differ"
+    # the two legs evaluate the same walkers; they differ only in where the root prior comes from (value leg: SciPy for every
+    # walker; e2e leg: the device kernel for ab >= 1e-6), i.e. by ~1e-13 relative.  Anything beyond 1e-10 is an error: it is
+    # reported on stderr with the walker, both legs are evaluated once more, and a second disagreement aborts the run.
+    def legs_diff(a_host, a_dev):
+        both = np.isfinite(a_host) & np.isfinite(a_dev)
+        rel = np.where(both, np.abs(a_host - a_dev) / np.maximum(np.abs(a_dev), 1e-300), 0.0)
+        return float(rel.max()) if rel.size else 0.0, int(np.argmax(rel)) if rel.size else 0, np.array_equal(np.isnan(a_host), np.isnan(a_dev))
+
+    legs_rel, worst, nan_ok = legs_diff(ll_host, ll_dev)
+    legs_retried = 0
+    if not os.environ.get("MOPE_DEBUG_MODE") and (not nan_ok or legs_rel > 1e-10):
+        sys.stderr.write("[bench] rank %d: device-resident and e2e results differ: max rel %.3e at walker %d (%.17g vs %.17g, log10ab %.4f), "
+                         "NaN patterns %s; evaluating both legs again\n" % (D.rank, legs_rel, worst, ll_dev[worst], ll_host[worst], X[worst, -2],
+                                                                            "equal" if nan_ok else "DIFFER"))
+        legs_retried = 1
+        step()
+        torch.cuda.synchronize()
+        ll_dev2 = out_dev.cpu().numpy()
+        ll_host2 = e2e_step()
+        sys.stderr.write("[bench] rank %d: second evaluation: value leg changed by %.3e, e2e leg changed by %.3e\n" % (
+            D.rank, legs_diff(ll_dev2, ll_dev)[0], legs_diff(ll_host2, ll_host)[0]))
+        ll_dev, ll_host = ll_dev2, ll_host2
+        legs_rel, worst, nan_ok = legs_diff(ll_host, ll_dev)
+        if not nan_ok or legs_rel > 1e-10:
+            raise AssertionError("device-resident and e2e results differ (twice)")
     steps_per_eval = tree_n / max(steps, 1)
     return {"ms": ms, "ms_local": ms_local, "e2e_s": e2e_s, "e2e_local_s": e2e_local, "launches_per_step": int(launches),
             "tree_ms_per_step": tree_ms / max(steps, 1), "tree_launches_per_step": steps_per_eval,
             "interp_ms_per_step": interp_ms / max(steps, 1), "interp_launches_per_step": interp_n / max(steps, 1),
             "gemm_ops": int(gemm_ops), "identity_ops": int(identity_ops), "unit_rows": int(unit_rows),
-            "warp_segs": int(warp_segs), "warp_segs_active": int(warp_segs_active),
+            "warp_segs": int(warp_segs), "warp_segs_active": int(warp_segs_active), "legs_max_rel_diff": legs_rel, "legs_retried": legs_retried,
             "ll_host": ll_host, "clocks": clocks.summary() if clocks else None}
 
 
@@ -643,7 +665,8 @@ def run_extra_config(D, name, base_tb, workdir, peak, do_cpu, steps_cap):
     out = {"name": name, "workload": desc, "n_gpus": D.world, "scaling": "strong" if name == "cfg4" else "weak",
            "walkers_total": W_total, "loci_total": int(L_total), "steps": steps, "warmup": 1,
            "ms_per_step": m["ms"], "value": value, "unit": UNIT,
-           "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": m["e2e_s"] * 1e3},
+           "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": m["e2e_s"] * 1e3, "max_rel_diff_vs_value_leg": m["legs_max_rel_diff"],
+                   "legs_retried": m["legs_retried"]},
            "gpu_launches_per_step": m["launches_per_step"], "finite_walkers": int(np.isfinite(ll_host).sum()),
            "roofline": roof, "per_rank": per_rank, "parity_vs_reference": parity, "clocks": m["clocks"],
            "setup_s": {"data": t_data, "model_and_tables": t_setup - t_data, "total_wall": time.perf_counter() - t_begin}}
@@ -790,6 +813,7 @@ def run_ours(args):
                                      "host for walkers with ab < 1e-6, pipelined against the device work)",
                        "finite_walkers": int(np.isfinite(ll_host).sum())},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "max_rel_diff_vs_value_leg": m["legs_max_rel_diff"], "legs_retried": m["legs_retried"],
                     "ms_per_step": m["e2e_s"] * 1e3},
             "gpu_launches": int(m["launches_per_step"] * args.steps),
             "clocks": m["clocks"],
