@@ -38,6 +38,16 @@ def post_clone(x):
     return inf_data.log_posterior(x)
 
 
+def target(x):
+    """mope/inference.py:62-65: the optimiser's objective (optimize_posterior's PSO / L-BFGS-B stages)."""
+    return -1.0 * inf_data.penalty_bound_log_posterior(x)
+
+
+def inf_bound_target(x):
+    """mope/inference.py:67-70: the Nelder-Mead stage's objective."""
+    return -1.0 * inf_data.log_posterior(x)
+
+
 def _get_valid_start_from(sf_str):
     for v in ("prior", "true", "map"):
         if sf_str == v:
@@ -259,6 +269,48 @@ class Inference(object):
             print("inf:", x)
             return np.inf
         return self.like_obj(x)
+
+    def _get_bounds_penalty(self, x):
+        """inference.py:1170-1192: parameters clipped into the prior box and a positive quadratic penalty for what was
+        clipped, in units of the box width."""
+        x = np.asarray(x, dtype=np.float64)
+        scaling = self.upper - self.lower
+        lower_penalty = ((np.maximum(self.lower - x, 0.0) / scaling) ** 2).sum()
+        upper_penalty = ((np.maximum(x - self.upper, 0.0) / scaling) ** 2).sum()
+        good_params = np.minimum(np.maximum(x, self.lower), self.upper)
+        return good_params, lower_penalty + upper_penalty
+
+    def penalty_bound_like_obj(self, x):
+        """inference.py:1018-1020."""
+        good_x, penalty = self._get_bounds_penalty(x)
+        return self.like_obj(good_x) + penalty
+
+    def penalty_bound_log_posterior(self, x):
+        """inference.py:1163-1167."""
+        good_x, penalty = self._get_bounds_penalty(x)
+        return self.log_posterior(good_x) - penalty
+
+    def debug_loglike_components(self, varparams):
+        """inference.py:925-972: per pedigree [tree log-likelihood, per-family log ascertainment probabilities, family counts,
+        (mean log ascertainment probability, Poisson term when the penalty is on,) total, log prior] -- one device call."""
+        varparams = np.asarray(varparams, dtype=np.float64)
+        _ll, _status, comps = self.loglike_components(varparams[None, :])
+        out = []
+        for i, ped in enumerate(self.peds):
+            tll = float(comps[i]["root_ll"][0])
+            log_asc = np.array(comps[i]["log_asc"][0])
+            counts = np.array(ped.ages["count"].values)
+            tcomps = [tll, log_asc, counts.copy()]
+            tll -= (log_asc * counts).sum()
+            if self.poisson_like_penalty > 0:
+                from scipy.special import gammaln
+                loglams = log_asc + np.log(self.genome_size)
+                logpoisson = (-np.exp(loglams) + counts * loglams - gammaln(counts + 1)).sum()   # inference.py:1113-1129
+                tll += logpoisson * self.poisson_like_penalty
+                tcomps += [np.mean(log_asc), logpoisson]
+            tcomps += [tll, self.logprior(varparams)]
+            out.append(tcomps)
+        return out
 
     # ------------------------------------------------------------------------------------------
     # prior / posterior
