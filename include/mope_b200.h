@@ -21,11 +21,21 @@
  *   mope_b200_leaf_likelihoods  <- _binom.get_binom_likelihoods_cython      mope/_binom.pyx:49-92
  *   mope_b200_branch_update     <- _likes.compute_{length,rate,bottleneck}_transition_likelihood
  *   mope_b200_non_asc_probs     <- _poisson_binom.get_non_asc_probs         mope/_poisson_binom.pyx:18-90
+ *   mope_b200_root_prior        <- likelihoods.get_stationary_distribution_double_beta   mope/likelihoods.py:27-60
+ *   mope_b200_eval_resident     <- Inference.loglike with the parameter vectors in HBM (planning by a kernel)
+ *   mope_b200_mcmc_halfstep     <- one half-step of emcee's stretch move as Inference.run_mcmc drives it
+ *                                  (mope/inference.py:1353-1356) + Inference.log_posterior (:1132-1161)
+ *   mope_b200_gen_*             <- generate_transitions.py:57-67,194-228,386-414, _transition.pyx:6-33 (table generator)
+ *   mope_b200_sel_loglike       <- likelihoods.get_log_l_and_asc_prob_selection          mope/likelihoods.py:404-525
+ *   mope_b200_sel_branch_update <- _likes selection / masked operators      mope/_likes.pyx:59-136,155-229,251-307
  *
  * Conventions: plain C, no exceptions across the boundary.  Every function returns 0 on success or a
  * negative MOPE_E_* code; mope_b200_last_error() gives the message of the last failure on the calling
  * thread.  All arithmetic is fp64.  Device memory is OWNED BY THE CALLER (PyTorch in the Python host):
- * the caller asks for sizes with the *_bytes queries, allocates, and passes device pointers in.
+ * the caller asks for sizes with the *_bytes queries, allocates, and passes device pointers in.  (The operator-level entry
+ * points -- transition_matrix, leaf_likelihoods, branch_update, non_asc_probs, sel_* -- take host arrays and stage them
+ * through a grow-only scratch the context owns and mope_b200_destroy frees; mope_b200_sel_loglike also keeps its
+ * per-pedigree row-group tables there.)
  * Functions taking a `stream` enqueue their work on that CUDA stream (cudaStream_t passed as void*);
  * unless documented otherwise they return after the work is enqueued.  A context is bound to one device
  * and is not re-entrant (external locking), matching the reference's process-private Inference object.
