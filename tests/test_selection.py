@@ -291,3 +291,37 @@ def test_gpu_selection_matches_oracle_on_fresh_vectors():
             assert abs(got - ref) <= 1e-10 * abs(ref)
     finally:
         I.close()
+
+
+@pytest.mark.gpu
+def test_gpu_selection_on_the_benchmark_grid_size_vs_oracle():
+    """F = 201 (Fp = 208: the other interpolation-kernel staging variant, the k-permuted emission layout of the main path read
+    back in natural order): the F = 201 fixture's drift matrices with their rate axis relabelled as selection coefficients
+    (any complete grid of stochastic matrices is a valid table set for an oracle-vs-GPU comparison)."""
+    from mope_b200 import Inference, TransitionTables
+    tb = H.load_tables("tables_f201.npz")
+    ss = np.array([-2e-3, 3e-3])
+    assert tb["drift"].shape[1] == ss.shape[0]
+    tables = TransitionTables(drift=tb["drift"], gens=tb["gens"], us=ss, N=float(tb["N"]), freqs=tb["freqs"], breaks=tb["breaks"])
+    case = CASES["sel_example"]
+    peds = case["peds"]
+    I = Inference([p["data"] for p in peds], [p["tree"] for p in peds], [p["ages"] for p in peds], tables, selection_model=True,
+                  log_unif_drift=True, min_freq=0.001, _inputs_are_text=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        drift = orc.TransitionData(tb["drift"], tb["gens"], ss, int(tb["N"]), tb["freqs"], tb["breaks"])
+        O = osel.SelectionInference([(H.read_tsv(p["data"]), p["tree"], H.read_tsv(p["ages"])) for p in peds], drift, log_unif_drift=True,
+                                    min_freq=0.001)
+    try:
+        rng = np.random.RandomState(4)
+        npos = I.num_unique_positions
+        for _ in range(2):
+            x = rng.uniform(0.7 * I.lower + 0.3 * I.upper, 0.3 * I.lower + 0.7 * I.upper)
+            x[I.num_varnames:2 * I.num_varnames] = rng.uniform(-0.2, 0.2, I.num_varnames)
+            x[-npos:] = rng.choice([-1.0, 1.0], npos) * (10.0 + rng.uniform(0, 2.5, npos)) * (rng.rand(npos) < 0.7)
+            O.clear_cache()
+            ref = O.loglike(x.copy())
+            got = I.loglike(x.copy())
+            assert np.isfinite(ref) and abs(got - ref) <= 1e-10 * abs(ref), (got, ref)
+    finally:
+        I.close()
