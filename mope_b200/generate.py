@@ -257,6 +257,36 @@ def generate_tables(N: int = 1000, breaks=(0.5, 0.01), gens: Sequence[int] = DEF
                             freqs=freqs, breaks=br, **kw)
 
 
+def generate_selection_tables(N: int = 1000, breaks=(0.5, 0.01), gens: Sequence[int] = DEFAULT_GENS, ss: Sequence[float] = (0.0,),
+                              u: float = 0.0, v: float = 0.0, device: Optional[str] = None, progress=None) -> TransitionTables:
+    """Selection table set (the files `mope generate-commands --selection` asks for, generate_transitions.py:545-556: one
+    chain per selection coefficient, u = v = 0): drift grid [len(gens), len(ss)] whose second axis (`us` of the returned
+    tables) holds the selection coefficients -- what TransitionData(selection=True) builds from the `s` attribute.  The
+    selection model needs negative coefficients and 0 on the grid (Inference.loglike maps |x| < 10 to alpha = 0)."""
+    mat = _Mat(device)
+    gens = [int(g) for g in gens]
+    ss = [float(x) for x in ss]
+    if sorted(gens) != gens or len(set(gens)) != len(gens) or sorted(ss) != ss or len(set(ss)) != len(ss):
+        raise ValueError("generations and selection coefficients must be strictly ascending")
+    br = get_breaks_symmetric(N, breaks[0], breaks[1])
+    freqs = get_binned_frequencies(N, br)
+    F = br.shape[0]
+    drift = np.empty((len(gens), len(ss), F, F))
+    binned = mat.binner(N + 1, br)
+    for j, sc in enumerate(ss):
+        P = mat.wright_fisher(N, sc, u, v)
+        squares = [P]
+        cur = _power_from_cache(mat, squares, gens[0])
+        drift[0, j] = binned(cur)
+        for i in range(1, len(gens)):
+            cur = mat.mm(cur, _power_from_cache(mat, squares, gens[i] - gens[i - 1]))
+            drift[i, j] = binned(cur)
+        if progress:
+            progress("selection s=%g done" % sc)
+    return TransitionTables(drift=drift, gens=np.array(gens, dtype=np.float64), us=np.array(ss, dtype=np.float64),
+                            N=float(N), freqs=freqs, breaks=br)
+
+
 def bottleneck_matrix(N: int, Nb: int, mu: float, mat: Optional[_Mat] = None, on_device: bool = False):
     """Instantaneous bottleneck to Nb followed by doubling back to N (generate_transitions.py:29-54)."""
     if Nb >= N:

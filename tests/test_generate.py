@@ -30,6 +30,32 @@ def test_generated_tables_match_reference_generator():
     np.testing.assert_allclose(tb.bot, TB["bot"][np.ix_(bi, ui)], rtol=1e-9, atol=1e-15)
 
 
+def test_generated_selection_tables_match_reference_generator():
+    """generate_selection_tables (one Wright-Fisher chain per selection coefficient, u = v = 0) against the selection table set
+    the reference's own generator produced (tests/golden/tables_sel.npz, make_golden_selection.py)."""
+    ref = H.load_tables("tables_sel.npz")
+    gens, ss = [1, 5, 20, 100], [-1e-3, 0.0, 5e-3]
+    tb = generate.generate_selection_tables(N=1000, breaks=(0.5, 0.02), gens=gens, ss=ss, device="cpu")
+    gi = [list(ref["gens"]).index(g) for g in gens]
+    si = [list(ref["us"]).index(x) for x in ss]
+    np.testing.assert_allclose(tb.drift, ref["drift"][np.ix_(gi, si)], rtol=1e-9, atol=1e-15)
+    np.testing.assert_array_equal(tb.us, ss)
+    np.testing.assert_array_equal(tb.breaks, ref["breaks"])
+    with pytest.raises(ValueError):
+        generate.generate_selection_tables(N=1000, breaks=(0.5, 0.02), gens=gens, ss=[0.0, -1e-3], device="cpu")
+
+
+@pytest.mark.gpu
+def test_gpu_selection_tables_match_reference_generator():
+    """The same on the device (binom_matrix_kernel, dgemm_tn_kernel, bin_matrix_kernel), the whole fixture grid (to 3 000
+    generations, negative and positive coefficients)."""
+    ref = H.load_tables("tables_sel.npz")
+    tb = generate.generate_selection_tables(N=1000, breaks=(0.5, 0.02), gens=[int(g) for g in ref["gens"]], ss=[float(x) for x in ref["us"]],
+                                            device="cuda")
+    np.testing.assert_allclose(tb.drift, ref["drift"], rtol=1e-8, atol=1e-14)
+    assert tb.drift.min() >= 0.0 and tb.drift.max() <= 1.0
+
+
 @pytest.mark.gpu
 def test_gpu_generator_kernels_match_host():
     """The generator's own kernels through the C ABI (mope_b200_gen_*): binomial rows vs SciPy, dgemm_tn_kernel vs a NumPy
