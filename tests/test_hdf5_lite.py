@@ -66,3 +66,20 @@ def test_master_files_in_the_reference_layout(tmp_path):
     for k in ("drift", "gens", "us", "freqs", "bot", "nbs", "bot_us"):
         assert np.array_equal(getattr(back, k), getattr(T, k)), k
     assert np.array_equal(back.breaks, T.breaks) and back.N == T.N
+
+
+def test_selection_master_file_round_trip(tmp_path):
+    """A selection table set written in the reference's layout (attribute s per dataset, u = v = 0) and read back with the
+    `s` attribute as the second grid axis (TransitionData(selection=True), transition_data_2d.py:52-55)."""
+    tb = H.load_tables("tables_sel.npz")
+    T = tables.TransitionTables(drift=tb["drift"], gens=tb["gens"], us=tb["us"], N=float(tb["N"]), freqs=tb["freqs"], breaks=tb["breaks"])
+    path = str(tmp_path / "selection_transitions.h5")
+    T.save_hdf5(path, selection=True)
+    _root, dsets = hdf5_lite.read_file(path)
+    assert {a["u"] for _m, a in dsets.values()} == {0.0} and {a["s"] for _m, a in dsets.values()} == set(tb["us"].tolist())
+    back = tables.load(path, selection=True)
+    assert np.array_equal(back.drift, T.drift) and np.array_equal(back.us, T.us) and np.array_equal(back.gens, T.gens)
+    # read as a neutral set every generation appears once per coefficient with the same u = 0: rejected like the reference does
+    # (transition_data_2d.py:66-70, "Found duplicate generation & mutation/selection rate combination")
+    with pytest.raises(Exception, match="duplicate"):
+        tables.load(path)
