@@ -73,8 +73,10 @@ __global__ void __launch_bounds__(256) sel_matvec_kernel(const double* __restric
             }
 #pragma unroll
             for (int q = 0; q < SEL_ROWS; ++q) {
+                if (q < nr) {   // uniform: a group usually holds three rows (a locus and its two pseudo-rows)
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+                    for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+                }
             }
             if (lane < nr) {
                 double y = 0.0;
