@@ -2241,8 +2241,7 @@ int run_sel_branch(mope_ctx* c, const SelPlan& pl, char* stage, size_t stage_byt
     CUDA_TRY(cudaMemcpyAsync(d_off, pl.po.mat_off.data(), (size_t)n_jobs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_roff, pl.row_off.data(), (size_t)(n_jobs + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_rows, pl.rows.data(), pl.rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    sel_matvec_kernel<<<n_jobs, 256, (size_t)SEL_ROWS * c->Fp * sizeof(double), st>>>(pool, d_off, d_roff, d_rows, V, parent, trans, c->F, c->Fp, mask);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_sel_matvec(n_jobs, st, pool, d_off, d_roff, d_rows, V, parent, trans, c->F, c->Fp, mask));
     c->launches++;
     // the host vectors of the plan are pageable: the copies above were staged synchronously by the runtime
     return 0;
@@ -2469,8 +2468,7 @@ int mope_b200_sel_loglike(mope_ctx* c, int ped, const double* branch_lengths, co
         for (int k0 = 0; k0 < ng; k0 += pool_blocks) {         // groups in chunks that fit the pool (stream order protects the reuse)
             const int nk = std::min(pool_blocks, ng - k0);
             if (int rc = launch_interp(c, d_jobs + g0 + k0, (size_t)nk, pool, st, false)) return rc;
-            sel_matvec_kernel<<<nk, 256, (size_t)SEL_ROWS * Fp * sizeof(double), st>>>(pool, d_moff + g0 + k0, roff + k0, rows, V, par, do_asc ? trans : nullptr, F, Fp, 0);
-            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(launch_sel_matvec(nk, st, pool, d_moff + g0 + k0, roff + k0, rows, V, par, do_asc ? trans : nullptr, F, Fp, 0));
             c->launches++;
         }
         if (do_asc) {

@@ -20,7 +20,7 @@
 
 namespace mope {
 
-constexpr int SEL_ROWS = 8;   // operand rows applied per pass over a matrix
+constexpr int SEL_ROWS = 4;   // operand rows applied per pass over a matrix (a group usually holds 3: a locus and its two pseudo-rows)
 
 // mask: 0 none; 1 "zero" Pzero[0,0] = P[0,0]; 2 "focal node" Pzero[0,1:-1] = P[0,1:-1]; 3 "descendant"
 // Pzero[1:-1,1:-1] = P[1:-1,1:-1] (everything else zero).
@@ -33,6 +33,9 @@ __device__ __forceinline__ void sel_mask_ranges(int mask, int F, int& i_lo, int&
 
 // Y[r][:] = Pmask_j . V[r][:] for the rows r of job j; parent[r][:] *= Y[r][:]; trans[r][:] = Y[r][:] (optional).
 // mat_off[j] < 0: identity matrix (N*t below the first table generation, transition_data_2d.py:184-187).
+// One CTA per matrix.  The kernel is bound by the latency of its global loads, so every warp keeps TWO matrix rows (J
+// 32-wide pieces each) and the parent values it will update in flight at once, and only then runs the dot products.
+template <int J>
 __global__ void __launch_bounds__(256) sel_matvec_kernel(const double* __restrict__ pool, const int64_t* __restrict__ mat_off,
                                                          const int32_t* __restrict__ job_row_off, const int32_t* __restrict__ job_rows,
                                                          const double* __restrict__ V, double* __restrict__ parent, double* __restrict__ trans,
@@ -47,9 +50,99 @@ __global__ void __launch_bounds__(256) sel_matvec_kernel(const double* __restric
     for (int rb = r0; rb < r1; rb += SEL_ROWS) {
         const int nr = min(SEL_ROWS, r1 - rb);
         __syncthreads();
-        for (int e = threadIdx.x; e < nr * Fp; e += blockDim.x) {
+        for (int e = threadIdx.x; e < SEL_ROWS * Fp; e += blockDim.x) {
             const int q = e / Fp, f = e - q * Fp;
-            vs[e] = (f < F) ? V[(size_t)job_rows[rb + q] * Fp + f] : 0.0;
+            vs[e] = (q < nr && f < F) ? V[(size_t)job_rows[rb + q] * Fp + f] : 0.0;   // unused rows / padding: zeros
+        }
+        __syncthreads();
+        // lanes 0..nr-1 update row i of the matrix for the group's rows, lanes 8..8+nr-1 row i + 8
+        const int half = lane >> 3, ql = lane & 7;
+        const bool upd_lane = half < 2 && ql < nr;
+        const size_t row_base = upd_lane ? (size_t)job_rows[rb + ql] * Fp : 0;
+        for (int i = warp; i < Fp; i += 16) {
+            const int ia = i, ib = i + 8;
+            const bool va = ia < Fp, vb = ib < Fp;
+            const bool ina = va && ia >= i_lo && ia < i_hi, inb = vb && ib >= i_lo && ib < i_hi;
+            double pa[J], pb[J];
+#pragma unroll
+            for (int jj = 0; jj < J; ++jj) {
+                const int k = lane + 32 * jj;
+                const bool kin = k >= k_lo && k < k_hi;
+                pa[jj] = (ina && off >= 0 && kin) ? pool[off + (size_t)ia * Fp + k] : 0.0;
+                pb[jj] = (inb && off >= 0 && kin) ? pool[off + (size_t)ib * Fp + k] : 0.0;
+            }
+            // the parent values this lane will update, in flight with the matrix rows
+            const int my_i = half == 0 ? ia : ib;
+            const bool my_valid = upd_lane && (half == 0 ? va : vb);
+            double pv = 1.0;
+            if (my_valid && parent != nullptr && my_i < F) pv = parent[row_base + my_i];
+            double acca[SEL_ROWS], accb[SEL_ROWS];
+#pragma unroll
+            for (int q = 0; q < SEL_ROWS; ++q) { acca[q] = 0.0; accb[q] = 0.0; }
+            if (off < 0) {
+                // identity: Y[r][i] = V[r][i] inside the mask
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < SEL_ROWS; ++q) {
+                        if (ina && ia >= k_lo && ia < k_hi) acca[q] = vs[q * Fp + ia];
+                        if (inb && ib >= k_lo && ib < k_hi) accb[q] = vs[q * Fp + ib];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < J; ++jj) {
+                    const int k = lane + 32 * jj;
+                    if (k < Fp) {
+#pragma unroll
+                        for (int q = 0; q < SEL_ROWS; ++q) {
+                            const double v = vs[q * Fp + k];
+                            acca[q] = fma(pa[jj], v, acca[q]);
+                            accb[q] = fma(pb[jj], v, accb[q]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < SEL_ROWS; ++q) {
+                if (q < nr) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        acca[q] += __shfl_xor_sync(0xffffffffu, acca[q], o);
+                        accb[q] += __shfl_xor_sync(0xffffffffu, accb[q], o);
+                    }
+                }
+            }
+            if (my_valid) {
+                double y = 0.0;
+#pragma unroll
+                for (int q = 0; q < SEL_ROWS; ++q) if (q == ql) y = half == 0 ? acca[q] : accb[q];
+                if (my_i >= F) y = 0.0;
+                const size_t o = row_base + my_i;
+                if (parent) parent[o] = (my_i < F) ? pv * y : 0.0;
+                if (trans) trans[o] = y;
+            }
+        }
+    }
+}
+
+// generic row length: the same in pieces of J = 4 (wide grids)
+__global__ void __launch_bounds__(256) sel_matvec_wide_kernel(const double* __restrict__ pool, const int64_t* __restrict__ mat_off,
+                                                              const int32_t* __restrict__ job_row_off, const int32_t* __restrict__ job_rows,
+                                                              const double* __restrict__ V, double* __restrict__ parent, double* __restrict__ trans,
+                                                              int F, int Fp, int mask) {
+    extern __shared__ double vs[];   // [SEL_ROWS][Fp]
+    const int j = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = job_row_off[j], r1 = job_row_off[j + 1];
+    const int64_t off = mat_off[j];
+    int i_lo, i_hi, k_lo, k_hi;
+    sel_mask_ranges(mask, F, i_lo, i_hi, k_lo, k_hi);
+    for (int rb = r0; rb < r1; rb += SEL_ROWS) {
+        const int nr = min(SEL_ROWS, r1 - rb);
+        __syncthreads();
+        for (int e = threadIdx.x; e < SEL_ROWS * Fp; e += blockDim.x) {
+            const int q = e / Fp, f = e - q * Fp;
+            vs[e] = (q < nr && f < F) ? V[(size_t)job_rows[rb + q] * Fp + f] : 0.0;
         }
         __syncthreads();
         for (int i = warp; i < Fp; i += 8) {
@@ -60,20 +153,20 @@ __global__ void __launch_bounds__(256) sel_matvec_kernel(const double* __restric
                 if (off < 0) {
                     if (lane == 0 && i >= k_lo && i < k_hi) {
 #pragma unroll
-                        for (int q = 0; q < SEL_ROWS; ++q) if (q < nr) acc[q] = vs[q * Fp + i];
+                        for (int q = 0; q < SEL_ROWS; ++q) acc[q] = vs[q * Fp + i];
                     }
                 } else {
                     const double* prow = pool + off + (size_t)i * Fp;
                     for (int k = k_lo + lane; k < k_hi; k += 32) {
                         const double p = prow[k];
 #pragma unroll
-                        for (int q = 0; q < SEL_ROWS; ++q) if (q < nr) acc[q] = fma(p, vs[q * Fp + k], acc[q]);
+                        for (int q = 0; q < SEL_ROWS; ++q) acc[q] = fma(p, vs[q * Fp + k], acc[q]);
                     }
                 }
             }
 #pragma unroll
             for (int q = 0; q < SEL_ROWS; ++q) {
-                if (q < nr) {   // uniform: a group usually holds three rows (a locus and its two pseudo-rows)
+                if (q < nr) {
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
                 }
@@ -89,6 +182,17 @@ __global__ void __launch_bounds__(256) sel_matvec_kernel(const double* __restric
             }
         }
     }
+}
+
+// launcher: the instance whose J pieces cover a row
+inline cudaError_t launch_sel_matvec(int n_jobs, cudaStream_t st, const double* pool, const int64_t* mat_off, const int32_t* job_row_off,
+                                     const int32_t* job_rows, const double* V, double* parent, double* trans, int F, int Fp, int mask) {
+    const size_t smem = (size_t)SEL_ROWS * Fp * sizeof(double);
+    if (Fp <= 96) sel_matvec_kernel<3><<<n_jobs, 256, smem, st>>>(pool, mat_off, job_row_off, job_rows, V, parent, trans, F, Fp, mask);
+    else if (Fp <= 128) sel_matvec_kernel<4><<<n_jobs, 256, smem, st>>>(pool, mat_off, job_row_off, job_rows, V, parent, trans, F, Fp, mask);
+    else if (Fp <= 224) sel_matvec_kernel<7><<<n_jobs, 256, smem, st>>>(pool, mat_off, job_row_off, job_rows, V, parent, trans, F, Fp, mask);
+    else sel_matvec_wide_kernel<<<n_jobs, 256, smem, st>>>(pool, mat_off, job_row_off, job_rows, V, parent, trans, F, Fp, mask);
+    return cudaGetLastError();
 }
 
 // One thread per (branch, group): time = g_mult * branch_length, alpha = locus_alphas[branch][g_pos]; range checks
