@@ -361,12 +361,26 @@ __device__ __forceinline__ void interp_blend_ldg(double* __restrict__ tile, int 
     }
 }
 
-template <bool BULK>
+// APPLY (selection model / masked operators, selection.cuh): the interpolated, checked matrix is not written to the pool
+// but applied on the spot to the rows of the job's group -- Y[q][i] = sum_f Pmask[i][f] V[q][f], parent[q][i] *= Y[q][i],
+// trans[q][i] = Y[q][i] -- by the warp that holds matrix row i in phase 3 (the normalised entries stay in registers, the
+// operand rows come through L1).  A job flagged 8 is the identity matrix there (N t below the first table generation).
+constexpr int APPLY_MAXJ = 8;   // 32-wide pieces of a matrix row kept in registers: Fp <= 256
+struct ApplyArgs {
+    const int32_t* job_row_off;   // [n_jobs + 1] offsets into job_rows
+    const int32_t* job_rows;      // rows of the operand / parent arrays, grouped by job
+    const double* V;              // [.][Fp] operand rows
+    double* parent;               // [.][Fp], may be null
+    double* trans;                // [.][Fp], may be null
+    int32_t mask;                 // 0 none, 1 [0,0], 2 [0,1:-1], 3 [1:-1,1:-1]
+};
+
+template <bool BULK, bool APPLY>
 __global__ void __launch_bounds__(INTERP_THREADS, 4)
 interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __restrict__ tables, double* __restrict__ pool, int F, int Fp,
               int perm, const int8_t* __restrict__ asc_mask /* [2][F]: e0 then eN, may be null */,
               const unsigned* __restrict__ lane_masks /* [2][32] bit k of word l: column l + 32 k is in e0 / eN (F <= 1024), may be null */,
-              int rows, int tiles_per_job, unsigned div_magic /* ceil(2^32 / F), register-staged variant */) {
+              int rows, int tiles_per_job, unsigned div_magic /* ceil(2^32 / F), register-staged variant */, ApplyArgs ap) {
     extern __shared__ __align__(16) double stage[];   // BULK: [4][interp_buf_doubles(rows, F)]; else the tile [rows][F | 1]
     __shared__ double s_sum[32];
     __shared__ unsigned long long bar;
@@ -374,8 +388,9 @@ interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __re
     const int TS = BULK ? F : interp_row_stride_ldg(F);   // row stride of the blended tile
     const int j = blockIdx.x / tiles_per_job;
     const int i0 = (blockIdx.x - j * tiles_per_job) * rows;   // first matrix row of the tile
-    const InterpJob jb = jobs[j];
-    if (jb.flags & 8) return;                 // unused slot of a statically laid out job list (device-side planning)
+    InterpJob jb = jobs[j];
+    if (APPLY) { if (jb.flags & 8) jb.flags = 2; }   // identity group
+    else if (jb.flags & 8) return;            // unused slot of a statically laid out job list (device-side planning)
     double* dst0 = pool + jb.dst;
     double* dsum = dst0 + (size_t)Fp * Fp;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -457,6 +472,88 @@ interp_kernel(const InterpJob* __restrict__ jobs, int n_jobs, const double* __re
             }
     }
     const int pl = perm ? kperm(lane) : lane;   // storage position of column lane + 32 k is pl + 32 k (chunks are 16 wide)
+    if (APPLY) {
+        int i_lo = 0, i_hi = F, k_lo = 0, k_hi = F;
+        if (ap.mask == 1) { i_hi = 1; k_hi = 1; }
+        else if (ap.mask == 2) { i_hi = 1; k_lo = 1; k_hi = F - 1; }
+        else if (ap.mask == 3) { i_lo = 1; i_hi = F - 1; k_lo = 1; k_hi = F - 1; }
+        const int q0 = ap.job_row_off[j], q1 = ap.job_row_off[j + 1];
+        for (int r = warp; r < rows; r += INTERP_THREADS / 32) {
+            const int i = i0 + r;
+            if (i >= Fp) break;
+            const bool in_rows = i < F && i >= i_lo && i < i_hi;
+            // the normalised, masked entries of matrix row i for this lane's columns
+            double pv[APPLY_MAXJ];
+#pragma unroll
+            for (int k = 0; k < APPLY_MAXJ; ++k) pv[k] = 0.0;
+            if (in_rows && !ident) {
+                const double* row = tile + r * TS;
+                const double s = s_sum[r];
+                const bool div = check && (s > 1.0);
+                const double rcp = div ? __drcp_rn(s) : 1.0;
+#pragma unroll
+                for (int k = 0; k < APPLY_MAXJ; ++k) {
+                    const int f = lane + 32 * k;
+                    if (f >= k_lo && f < k_hi) {
+                        double v = row[f];
+                        if (div && v != 0.0) {
+                            if (v >= 1e-290) {
+                                const double qq = __dmul_rn(v, rcp);
+                                const double rem = __fma_rn(-qq, s, v);
+                                v = __fma_rn(rem, rcp, qq);
+                            } else {
+                                v = __ddiv_rn(v, s);
+                            }
+                        }
+                        pv[k] = v;
+                    }
+                }
+            }
+            // the group's rows four at a time: their operand values and the parent entries to update are all in flight
+            // before the dot products (the apply phase is bound by load latency, not by bandwidth)
+            for (int qb = q0; qb < q1; qb += 4) {
+                const int nq = min(4, q1 - qb);
+                size_t rbase[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) rbase[t] = (size_t)ap.job_rows[qb + min(t, nq - 1)] * Fp;
+                const size_t my_base = rbase[0] * (lane == 0) + rbase[1] * (lane == 1) + rbase[2] * (lane == 2) + rbase[3] * (lane == 3);
+                double par = 1.0;
+                if (lane < nq && ap.parent != nullptr && i < F) par = ap.parent[my_base + i];
+                double y[4] = {0.0, 0.0, 0.0, 0.0};
+                if (in_rows) {
+                    if (ident) {
+                        if (lane == 0 && i >= k_lo && i < k_hi) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) y[t] = __ldg(ap.V + rbase[t] + i);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < APPLY_MAXJ; ++k) {
+                            const int f = lane + 32 * k;
+                            if (f < F) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) y[t] = fma(pv[k], __ldg(ap.V + rbase[t] + f), y[t]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (t < nq) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) y[t] += __shfl_xor_sync(0xffffffffu, y[t], o);
+                    }
+                }
+                if (lane < nq) {
+                    double yy = lane == 0 ? y[0] : (lane == 1 ? y[1] : (lane == 2 ? y[2] : y[3]));
+                    if (i >= F) yy = 0.0;
+                    if (ap.parent) ap.parent[my_base + i] = (i < F) ? par * yy : 0.0;
+                    if (ap.trans) ap.trans[my_base + i] = yy;
+                }
+            }
+        }
+        return;
+    }
     for (int r = warp; r < rows; r += INTERP_THREADS / 32) {
         const int i = i0 + r;
         if (i >= Fp) break;

@@ -649,7 +649,8 @@ int launch_tree_t(mope_ctx* c, const TreeParams& tp, int grid, cudaStream_t st) 
 }
 
 // one CTA per (matrix, tile of rows): see interp_kernel
-int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d_pool, cudaStream_t st, bool perm) {
+template <bool APPLY>
+int launch_interp_t(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d_pool, cudaStream_t st, bool perm, const ApplyArgs& ap) {
     const int F = c->F, Fp = c->Fp;
     const bool bulk = interp_use_bulk(F);
     const int rows = bulk ? interp_rows_per_tile(F) : interp_rows_per_tile_ldg(F);
@@ -657,10 +658,10 @@ int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d
     const size_t smem = bulk ? (size_t)4 * interp_buf_doubles(rows, F) * sizeof(double) : (size_t)rows * interp_row_stride_ldg(F) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<true, APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<true, APPLY>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<false, APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(interp_kernel<false, APPLY>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     if (!bulk && (size_t)rows * F >= 65536) return fail(MOPE_E_INVALID, "interp: tile of %d x %d elements exceeds the index range of the fast division", rows, F);
@@ -668,14 +669,21 @@ int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d
     const unsigned long long grid = (unsigned long long)n_jobs * tiles;
     if (grid > 0x7fffffffull) return fail(MOPE_E_INVALID, "interp: too many matrices in one launch (%zu)", n_jobs);
     if (bulk)
-        interp_kernel<true><<<(unsigned)grid, INTERP_THREADS, smem, st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, F, Fp, perm ? 1 : 0, c->asc_mask,
-                                                                          c->lane_masks, rows, tiles, magic);
+        interp_kernel<true, APPLY><<<(unsigned)grid, INTERP_THREADS, smem, st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, F, Fp, perm ? 1 : 0, c->asc_mask,
+                                                                                 c->lane_masks, rows, tiles, magic, ap);
     else
-        interp_kernel<false><<<(unsigned)grid, INTERP_THREADS, smem, st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, F, Fp, perm ? 1 : 0, c->asc_mask,
-                                                                           c->lane_masks, rows, tiles, magic);
+        interp_kernel<false, APPLY><<<(unsigned)grid, INTERP_THREADS, smem, st>>>(d_jobs, (int)n_jobs, c->tables, d_pool, F, Fp, perm ? 1 : 0, c->asc_mask,
+                                                                                  c->lane_masks, rows, tiles, magic, ap);
     CUDA_TRY(cudaGetLastError());
     c->launches++;
     return 0;
+}
+int launch_interp(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, double* d_pool, cudaStream_t st, bool perm) {
+    return launch_interp_t<false>(c, d_jobs, n_jobs, d_pool, st, perm, ApplyArgs{});
+}
+// interpolate and apply in one pass (selection model, masked operators): no matrix leaves the SM.  Fp <= 32 * APPLY_MAXJ.
+int launch_interp_apply(mope_ctx* c, const InterpJob* d_jobs, size_t n_jobs, cudaStream_t st, const ApplyArgs& ap) {
+    return launch_interp_t<true>(c, d_jobs, n_jobs, nullptr, st, false, ap);
 }
 
 template <int NTT, int NFULL, bool SCALAR, bool ASCFAST>
@@ -2238,6 +2246,7 @@ int run_sel_branch(mope_ctx* c, const SelPlan& pl, char* stage, size_t stage_byt
         CUDA_TRY(cudaMemcpyAsync(d_jobs, pl.po.jobs.data(), pl.po.jobs.size() * sizeof(InterpJob), cudaMemcpyHostToDevice, st));
         if (int rc = launch_interp(c, d_jobs, pl.po.jobs.size(), pool, st, false)) return rc;
     }
+    // (the host-planned operator path keeps the two-kernel form: its job list holds no entries for identity groups)
     CUDA_TRY(cudaMemcpyAsync(d_off, pl.po.mat_off.data(), (size_t)n_jobs * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_roff, pl.row_off.data(), (size_t)(n_jobs + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_rows, pl.rows.data(), pl.rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -2391,9 +2400,11 @@ int mope_b200_sel_loglike(mope_ctx* c, int ped, const double* branch_lengths, co
     int max_groups = 1;
     for (int b = 0; b < B; ++b) max_groups = std::max(max_groups, S.br_groups[b]);
     const size_t pool_cap_bytes = (size_t)1 << 30;   // at most ~1 GB of interpolated matrices in flight
-    const int pool_blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)max_groups, pool_cap_bytes / (blk * sizeof(double))));
+    const bool fused = Fp <= 32 * APPLY_MAXJ && !getenv("MOPE_SEL_UNFUSED");
+    const int pool_blocks = fused ? max_groups   // nothing is materialised: one launch per branch
+                                  : (int)std::max<size_t>(1, std::min<size_t>((size_t)max_groups, pool_cap_bytes / (blk * sizeof(double))));
     const size_t need = align_up((size_t)TG * sizeof(InterpJob), 256) + align_up((size_t)TG * 8, 256) + align_up((size_t)B * 8, 256) +
-                        align_up((size_t)B * n_pos * 8, 256) + align_up((size_t)pool_blocks * blk * 8, 256) +
+                        align_up((size_t)B * n_pos * 8, 256) + align_up((fused ? (size_t)1 : (size_t)pool_blocks) * blk * 8, 256) +
                         (size_t)(n_internal + 3) * align_up(nodeN * 8, 256) + align_up((size_t)Fp * 8, 256) + align_up((size_t)2 * L * 8, 256) +
                         align_up(2 * (size_t)F, 256) + 8192;
     if (ensure_opbuf(c, need)) return MOPE_E_CUDA;
@@ -2404,7 +2415,7 @@ int mope_b200_sel_loglike(mope_ctx* c, int ped, const double* branch_lengths, co
     double* d_len = bb.take<double>(B);
     double* d_alpha = bb.take<double>((size_t)B * n_pos);
     int32_t* d_status = bb.take<int32_t>(64);
-    double* pool = bb.take<double>((size_t)pool_blocks * blk);
+    double* pool = bb.take<double>((fused ? (size_t)1 : (size_t)pool_blocks) * blk);
     double* cond = bb.take<double>((size_t)n_internal * nodeN);
     double* leafbuf = bb.take<double>(nodeN);
     double* trans = bb.take<double>(nodeN);
@@ -2467,6 +2478,12 @@ int mope_b200_sel_loglike(mope_ctx* c, int ped, const double* branch_lengths, co
         const int32_t* rows = S.g_rows + (size_t)b * R3;
         for (int k0 = 0; k0 < ng; k0 += pool_blocks) {         // groups in chunks that fit the pool (stream order protects the reuse)
             const int nk = std::min(pool_blocks, ng - k0);
+            if (fused) {
+                // one pass: interpolate, check and apply -- the matrices never leave the SM
+                ApplyArgs ap{roff + k0, rows, V, par, do_asc ? trans : nullptr, 0};
+                if (int rc = launch_interp_apply(c, d_jobs + g0 + k0, (size_t)nk, st, ap)) return rc;
+                continue;
+            }
             if (int rc = launch_interp(c, d_jobs + g0 + k0, (size_t)nk, pool, st, false)) return rc;
             CUDA_TRY(launch_sel_matvec(nk, st, pool, d_moff + g0 + k0, roff + k0, rows, V, par, do_asc ? trans : nullptr, F, Fp, 0));
             c->launches++;

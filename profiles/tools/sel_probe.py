@@ -6,7 +6,12 @@ import numpy as np, torch
 from tests import helpers as H
 from mope_b200 import Inference, TransitionTables
 
-TB = H.load_tables("tables_sel.npz")
+if os.environ.get("SEL_PROBE_F201"):
+    # the F = 201 fixture's drift matrices with their rate axis relabelled as selection coefficients (a valid table set for timing)
+    TB = dict(H.load_tables("tables_f201.npz"))
+    TB["us"] = np.array([-6e-3, 6e-3])
+else:
+    TB = H.load_tables("tables_sel.npz")
 case = json.load(open(os.path.join(H.GOLDEN, "cases_sel.json")))["sel_example"]
 ped = case["peds"][0]
 lines = ped["data"].splitlines()
@@ -39,4 +44,5 @@ for reps, npos in ((1, 40), (20, 400), (100, 2000)):
                                    loci_per_s=L / dt, ll=float(ll))
     print(out["L%d_P%d" % (L, P)], flush=True)
     inf.close()
-json.dump(out, open(os.path.join("gpurun_out", "r02_sel_probe.json"), "w"), indent=1)
+json.dump(out, open(os.path.join("gpurun_out", "r02_sel_probe%s%s.json" % ("_f201" if os.environ.get("SEL_PROBE_F201") else "",
+                                                                             "_unfused" if os.environ.get("MOPE_SEL_UNFUSED") else "")), "w"), indent=1)
