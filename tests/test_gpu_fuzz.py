@@ -77,3 +77,52 @@ def test_random_pedigree_vs_oracle(seed):
         assert H.relerr(ll_res[ok], ll[ok]).max() <= 1e-9, (tree, ll_res, ll)
     finally:
         I.close()
+
+
+def _random_tree_no_bottleneck(rng, n_leaves):
+    while True:
+        t = random_tree(rng, n_leaves)
+        if "^" not in t:
+            return t
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_pedigree_selection_model_vs_oracle(seed):
+    """The selection model on random pedigrees (no bottleneck branches: the reference's selection path reads every branch
+    from the drift tables): random positions shared between families, coefficients of both signs."""
+    import io
+    import warnings
+    from mope_b200 import Inference, TransitionTables, synth
+    from oracle import mope_oracle as orc
+    from oracle import mope_oracle_selection as osel
+    rng = np.random.RandomState(2000 + seed)
+    n_leaves = int(rng.randint(2, 7))
+    tree = _random_tree_no_bottleneck(rng, n_leaves)
+    n_loci = int(rng.choice([5, 40, 90]))
+    ds = synth.make_dataset(n_loci, n_leaves, tree=tree, seed=70 + seed, loci_per_family=int(rng.randint(1, 4)), missing_frac=0.1)
+    df = ds.data.copy()
+    df["position"] = 100 + 7 * rng.randint(max(2, n_loci // 3), size=n_loci)
+    buf = io.StringIO()
+    df.to_csv(buf, sep="\t", na_rep="NA", index=False)
+    data_tsv = buf.getvalue()
+    tb = H.load_tables("tables_sel.npz")
+    tables = TransitionTables(drift=tb["drift"], gens=tb["gens"], us=tb["us"], N=float(tb["N"]), freqs=tb["freqs"], breaks=tb["breaks"])
+    I = Inference([data_tsv], [tree], [ds.ages_tsv], tables, selection_model=True, log_unif_drift=True, _inputs_are_text=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        drift = orc.TransitionData(tb["drift"], tb["gens"], tb["us"], int(tb["N"]), tb["freqs"], tb["breaks"])
+        O = osel.SelectionInference([(H.read_tsv(data_tsv), tree, H.read_tsv(ds.ages_tsv))], drift, log_unif_drift=True)
+    try:
+        assert I.ndim == O.ndim
+        np.testing.assert_allclose(I.lower, O.lower, rtol=1e-14)
+        npos, nv = I.num_unique_positions, I.num_varnames
+        for _ in range(2):
+            x = rng.uniform(0.7 * I.lower + 0.3 * I.upper, 0.3 * I.lower + 0.7 * I.upper)
+            x[nv:2 * nv] = rng.uniform(-0.2, 0.2, nv)
+            x[-npos:] = rng.choice([-1.0, 1.0], npos) * (10.0 + rng.uniform(0, 4, npos)) * (rng.rand(npos) < 0.7)
+            O.clear_cache()
+            ref = O.loglike(x.copy())
+            got = I.loglike(x.copy())
+            assert np.isfinite(ref) and abs(got - ref) <= 1e-10 * abs(ref), (tree, got, ref)
+    finally:
+        I.close()
